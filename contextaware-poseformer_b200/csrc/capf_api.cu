@@ -1,0 +1,183 @@
+// C ABI of libcapf_b200: error handling, device info, plans (validated op programs) and dispatch.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "capf_internal.h"
+
+namespace capf {
+
+int g_num_sms = 148;
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
+int set_errorf(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* name) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e));
+  return CAPF_OK;
+}
+
+static int use_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return set_errorf(CAPF_ERR_CUDA, "no CUDA device (%s): libcapf_b200 has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return set_errorf(CAPF_ERR_ARG, "device %d out of range (%d devices)", device, n);
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != device && (e = cudaSetDevice(device)) != cudaSuccess)
+    return set_errorf(CAPF_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  int sms = 0, major = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (major != 10) return set_errorf(CAPF_ERR_UNSUPPORTED, "device %d is sm_%dx; this library is built for sm_100a only", device, major);
+  g_num_sms = sms > 0 ? sms : 148;
+  return CAPF_OK;
+}
+
+static int dispatch(const capf_op& op, const TcConvState* tc, cudaStream_t st) {
+  switch (op.kind) {
+    case CAPF_OP_CONV2D:
+      if (op.i[12] == CAPF_IMPL_TCGEN05) return tc_conv_launch(op, tc, st);
+      return launch_conv_simt(op, st);
+    case CAPF_OP_FUSE_SUM: return launch_fuse_sum(op, st);
+    case CAPF_OP_MAXPOOL3X3S2: return launch_maxpool(op, st);
+    case CAPF_OP_BILINEAR: return launch_bilinear(op, st);
+    case CAPF_OP_LAYERNORM: return launch_layernorm(op, st);
+    case CAPF_OP_ATTENTION: return launch_attention(op, st);
+    case CAPF_OP_REF_SAMPLE:
+    case CAPF_OP_DEFORM_SAMPLE: return launch_sample(op, st);
+    case CAPF_OP_EMBED_COORD: return launch_embed_coord(op, st);
+    case CAPF_OP_LEVELS_TO_JOINT: return launch_levels_to_joint(op, st);
+    case CAPF_OP_CROP_NORMALIZE: return launch_crop_normalize(op, st);
+    case CAPF_OP_CAST: return launch_cast(op, st);
+    default: return set_errorf(CAPF_ERR_ARG, "unknown op kind %d", op.kind);
+  }
+}
+
+}  // namespace capf
+
+using namespace capf;
+
+struct capf_plan {
+  int device;
+  std::vector<capf_op> ops;
+  std::vector<TcConvState*> tc;  // parallel to ops; null unless impl == TCGEN05
+};
+
+extern "C" {
+
+int capf_abi_version(void) { return CAPF_ABI_VERSION; }
+
+const char* capf_last_error(void) { return g_err; }
+
+int capf_device_info(int device, int64_t* out4) {
+  if (!out4) return set_error(CAPF_ERR_ARG, "capf_device_info: null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || device < 0 || device >= n)
+    return set_errorf(CAPF_ERR_CUDA, "capf_device_info: no such device (%s)", cudaGetErrorString(e));
+  cudaDeviceProp p;
+  if ((e = cudaGetDeviceProperties(&p, device)) != cudaSuccess)
+    return set_errorf(CAPF_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  out4[0] = p.multiProcessorCount;
+  out4[1] = p.major;
+  out4[2] = p.minor;
+  out4[3] = (int64_t)p.totalGlobalMem;
+  return CAPF_OK;
+}
+
+int capf_plan_create(const capf_op* ops, int n_ops, int device, capf_plan** out_plan) {
+  if (!ops || n_ops <= 0 || !out_plan) return set_error(CAPF_ERR_ARG, "capf_plan_create: bad arguments");
+  int e = use_device(device);
+  if (e) return e;
+  capf_plan* pl = new (std::nothrow) capf_plan();
+  if (!pl) return set_error(CAPF_ERR_ARG, "capf_plan_create: out of host memory");
+  pl->device = device;
+  pl->ops.assign(ops, ops + n_ops);
+  pl->tc.assign(n_ops, nullptr);
+  for (int k = 0; k < n_ops; ++k) {
+    capf_op& op = pl->ops[k];
+    if (op.kind == CAPF_OP_CONV2D && op.i[12] == CAPF_IMPL_TCGEN05) {
+      if (!tc_conv_supported(op)) {
+        capf_plan_destroy(pl);
+        return set_errorf(CAPF_ERR_UNSUPPORTED, "op %d: conv2d shape/dtype not supported by the tcgen05 kernel", k);
+      }
+      e = tc_conv_prepare(op, &pl->tc[k]);
+      if (e) {
+        capf_plan_destroy(pl);
+        return e;
+      }
+    }
+  }
+  *out_plan = pl;
+  return CAPF_OK;
+}
+
+int capf_plan_run(const capf_plan* plan, int first, int count, void* stream) {
+  if (!plan) return set_error(CAPF_ERR_ARG, "capf_plan_run: null plan");
+  int n = (int)plan->ops.size();
+  if (count < 0) count = n - first;
+  if (first < 0 || first + count > n) return set_error(CAPF_ERR_ARG, "capf_plan_run: range out of bounds");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int k = first; k < first + count; ++k) {
+    int e = dispatch(plan->ops[k], plan->tc[k], st);
+    if (e) {
+      char prev[400];
+      snprintf(prev, sizeof(prev), "%s", capf_last_error());
+      return set_errorf(e, "op %d (kind %d): %s", k, plan->ops[k].kind, prev);
+    }
+  }
+  return CAPF_OK;
+}
+
+int capf_plan_num_launches(const capf_plan* plan) { return plan ? (int)plan->ops.size() : 0; }
+
+int capf_plan_destroy(capf_plan* plan) {
+  if (!plan) return CAPF_OK;
+  for (TcConvState* s : plan->tc)
+    if (s) tc_conv_release(s);
+  delete plan;
+  return CAPF_OK;
+}
+
+int capf_op_run(const capf_op* op, int device, void* stream) {
+  capf_plan* pl = nullptr;
+  int e = capf_plan_create(op, 1, device, &pl);
+  if (e) return e;
+  e = capf_plan_run(pl, 0, 1, stream);
+  if (!e && pl->tc[0]) {
+    // tensor maps live in the throw-away plan: finish before freeing it
+    cudaError_t ce = cudaStreamSynchronize((cudaStream_t)stream);
+    if (ce != cudaSuccess) e = set_errorf(CAPF_ERR_CUDA, "capf_op_run: %s", cudaGetErrorString(ce));
+  }
+  capf_plan_destroy(pl);
+  return e;
+}
+
+int capf_crop_normalize(float* crop_xy, int n_points, void* stream) {
+  capf_op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = CAPF_OP_CROP_NORMALIZE;
+  op.i[0] = n_points;
+  op.out[0] = crop_xy;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return capf_op_run(&op, dev, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,35 @@
+// Internal (non-ABI) declarations shared by the translation units of libcapf_b200.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/capf_b200.h"
+
+namespace capf {
+
+extern int g_num_sms;  // SM count of the device the current plan/op targets (148 on B200)
+
+int set_error(int code, const char* msg);       // records thread-local message, returns code
+int set_errorf(int code, const char* fmt, ...);
+int check_launch(const char* kernel_name);      // cudaGetLastError() -> status
+
+// SIMT launchers (capf_simt.cu)
+int launch_conv_simt(const capf_op& op, cudaStream_t st);
+int launch_fuse_sum(const capf_op& op, cudaStream_t st);
+int launch_maxpool(const capf_op& op, cudaStream_t st);
+int launch_bilinear(const capf_op& op, cudaStream_t st);
+int launch_layernorm(const capf_op& op, cudaStream_t st);
+int launch_attention(const capf_op& op, cudaStream_t st);
+int launch_sample(const capf_op& op, cudaStream_t st);
+int launch_embed_coord(const capf_op& op, cudaStream_t st);
+int launch_levels_to_joint(const capf_op& op, cudaStream_t st);
+int launch_crop_normalize(const capf_op& op, cudaStream_t st);
+int launch_cast(const capf_op& op, cudaStream_t st);
+
+// tcgen05 path (capf_tc.cu): per-op prepared state lives in the plan
+struct TcConvState;                                   // tensor maps + launch geometry
+int tc_conv_supported(const capf_op& op);             // 1 if the tcgen05 kernel handles this op
+int tc_conv_prepare(const capf_op& op, TcConvState** out);
+int tc_conv_launch(const capf_op& op, const TcConvState* s, cudaStream_t st);
+void tc_conv_release(TcConvState* s);
+
+}  // namespace capf

@@ -1,0 +1,818 @@
+// CUDA-core (SIMT) kernels of libcapf_b200: the fp32-parity implementation of every operator on the
+// CA_PF.forward path, plus the memory-bound operators (samplers, LayerNorm, tiny attention, fuse-sum)
+// that the fp16/bf16 tensor-core path shares.  Reference citations are relative to
+// /root/reference/ContextPose/mvn/models/.
+#include "capf_common.cuh"
+#include "capf_internal.h"
+
+namespace capf {
+
+// =======================================================================================================
+// conv2d / linear: implicit GEMM  y[m][co] = sum_k A[m][k] * Wt[k][co],  m = (n,oy,ox), k = (r,s,ci)
+// replaces nn.Conv2d+BatchNorm2d(+ReLU)(+residual) (pose_hrnet.py:79-136) and nn.Linear (pose_dformer.py:25-31)
+// =======================================================================================================
+struct ConvP {
+  int N, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, act;
+  int M, K;
+};
+
+template <typename TI, typename TW, typename TO, int BM, int BN, int TM, int TN, bool VEC>
+__global__ void __launch_bounds__(256)
+conv_nhwc_simt(ConvP p, const TI* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias,
+               const TO* res, TO* y) {
+  constexpr int BK = 16;
+  static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const bool pointwise = (p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  // ---- per-thread A-load coordinates --------------------------------------------------------------
+  constexpr int A_CHUNKS = VEC ? (BM * BK / 4) / 256 : 1;  // VEC: float4 chunks; scalar: one pixel/thread
+  int a_pix[A_CHUNKS], a_n[A_CHUNKS], a_iy0[A_CHUNKS], a_ix0[A_CHUNKS];
+  bool a_ok[A_CHUNKS];
+#pragma unroll
+  for (int c = 0; c < A_CHUNKS; ++c) {
+    int pix = VEC ? (tid + c * 256) / 4 : tid / 2;
+    a_pix[c] = pix;
+    int m = m0 + pix;
+    a_ok[c] = (pix < BM) && (m < p.M);
+    int mm = a_ok[c] ? m : 0;
+    int ox = mm % p.Wo, t = mm / p.Wo;
+    int oy = t % p.Ho;
+    a_n[c] = t / p.Ho;
+    a_iy0[c] = oy * p.stride - p.pad;
+    a_ix0[c] = ox * p.stride - p.pad;
+  }
+
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    if (VEC) {
+      // Cin % 16 == 0: the 16 k's of this slab share one filter tap.
+      int tap = k0 / p.Cin, ci0 = k0 - tap * p.Cin;
+      int r = tap / p.KW, s = tap - r * p.KW;
+      int kq = tid & 3;
+#pragma unroll
+      for (int c = 0; c < A_CHUNKS; ++c) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int iy = a_iy0[c] + r, ix = a_ix0[c] + s;
+        if (a_ok[c] && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+          size_t off = pointwise ? (size_t)(m0 + a_pix[c]) * p.Cin
+                                 : ((size_t)(a_n[c] * p.H + iy) * p.W + ix) * p.Cin;
+          v = ld4<TI>(x + off + ci0 + kq * 4);
+        }
+        As[kq * 4 + 0][a_pix[c]] = v.x;
+        As[kq * 4 + 1][a_pix[c]] = v.y;
+        As[kq * 4 + 2][a_pix[c]] = v.z;
+        As[kq * 4 + 3][a_pix[c]] = v.w;
+      }
+      constexpr int B_CHUNKS = (BK * BN / 4 + 255) / 256;
+#pragma unroll
+      for (int c = 0; c < B_CHUNKS; ++c) {
+        int id = tid + c * 256;
+        if (id < BK * BN / 4) {
+          int kk = id / (BN / 4), nq = id - kk * (BN / 4);
+          int n = n0 + nq * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n < p.Cout) v = ld4<TW>(w + (size_t)(k0 + kk) * p.Cout + n);
+          *reinterpret_cast<float4*>(&Bs[kk][nq * 4]) = v;
+        }
+      }
+    } else {
+      // generic path (stem Cin=3, head Cout=3, ragged K): scalar loads with full decode
+      int kb = (tid & 1) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int kk = kb + e, k = k0 + kk;
+        float v = 0.f;
+        if (a_ok[0] && k < p.K) {
+          int tap = k / p.Cin, ci = k - tap * p.Cin;
+          int r = tap / p.KW, s = tap - r * p.KW;
+          int iy = a_iy0[0] + r, ix = a_ix0[0] + s;
+          if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+            v = to_f<TI>(x[((size_t)(a_n[0] * p.H + iy) * p.W + ix) * p.Cin + ci]);
+        }
+        As[kk][a_pix[0]] = v;
+      }
+      for (int id = tid; id < BK * BN; id += 256) {
+        int kk = id / BN, nn = id - kk * BN;
+        int k = k0 + kk, n = n0 + nn;
+        Bs[kk][nn] = (k < p.K && n < p.Cout) ? to_f<TW>(w[(size_t)k * p.Cout + n]) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        float4 v = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+        a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        float4 v = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN + j]);
+        b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: y = relu?( gelu?(acc + bias) + residual ) ---------------------------------------------
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; j += 4) {
+      int n = n0 + tx * TN + j;
+      if (n >= p.Cout) continue;
+      float v[4] = {acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]};
+      size_t off = (size_t)m * p.Cout + n;
+      if (VEC) {
+        if (bias) {
+          float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+          v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+        }
+        if (p.act == CAPF_ACT_GELU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = gelu_erf(v[e]);
+        }
+        if (res) {
+          float4 r4 = ld4<TO>(res + off);
+          v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+        }
+        if (p.act == CAPF_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        st4<TO>(y + off, make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (n + e >= p.Cout) break;
+          float t = v[e] + (bias ? bias[n + e] : 0.f);
+          if (p.act == CAPF_ACT_GELU) t = gelu_erf(t);
+          if (res) t += to_f<TO>(res[off + e]);
+          if (p.act == CAPF_ACT_RELU) t = fmaxf(t, 0.f);
+          y[off + e] = from_f<TO>(t);
+        }
+      }
+    }
+  }
+}
+
+template <typename TI, typename TW, typename TO>
+static int conv_dispatch(const ConvP& p, const capf_op& op, cudaStream_t st) {
+  const TI* x = (const TI*)op.in[0];
+  const TW* w = (const TW*)op.in[1];
+  const float* bias = (const float*)op.in[2];
+  const TO* res = (const TO*)op.in[3];
+  TO* y = (TO*)op.out[0];
+  bool vec = (p.Cin % 16 == 0) && (p.Cout % 4 == 0);
+  if (!vec) {
+    dim3 g((p.M + 127) / 128, (p.Cout + 31) / 32);
+    conv_nhwc_simt<TI, TW, TO, 128, 32, 4, 4, false><<<g, 256, 0, st>>>(p, x, w, bias, res, y);
+  } else if (p.Cout <= 32 || (p.Cout % 64 != 0 && p.Cout % 32 == 0 && p.Cout < 128)) {
+    dim3 g((p.M + 127) / 128, (p.Cout + 31) / 32);
+    conv_nhwc_simt<TI, TW, TO, 128, 32, 4, 4, true><<<g, 256, 0, st>>>(p, x, w, bias, res, y);
+  } else {
+    dim3 g((p.M + 127) / 128, (p.Cout + 63) / 64);
+    conv_nhwc_simt<TI, TW, TO, 128, 64, 8, 4, true><<<g, 256, 0, st>>>(p, x, w, bias, res, y);
+  }
+  return check_launch("conv_nhwc_simt");
+}
+
+int launch_conv_simt(const capf_op& op, cudaStream_t st) {
+  ConvP p;
+  p.N = op.i[0]; p.H = op.i[1]; p.W = op.i[2]; p.Cin = op.i[3]; p.Cout = op.i[4];
+  p.KH = op.i[5]; p.KW = op.i[6]; p.stride = op.i[7]; p.pad = op.i[8]; p.Ho = op.i[9]; p.Wo = op.i[10];
+  p.act = op.i[11];
+  long long M = (long long)p.N * p.Ho * p.Wo;
+  if (M <= 0 || M >= (1ll << 31) || p.Cin <= 0 || p.Cout <= 0) return set_error(CAPF_ERR_ARG, "conv2d: bad shape");
+  if (p.Ho != (p.H + 2 * p.pad - p.KH) / p.stride + 1 || p.Wo != (p.W + 2 * p.pad - p.KW) / p.stride + 1)
+    return set_error(CAPF_ERR_ARG, "conv2d: Ho/Wo inconsistent with H,W,k,stride,pad");
+  p.M = (int)M;
+  p.K = p.KH * p.KW * p.Cin;
+  if (!op.in[0] || !op.in[1] || !op.out[0]) return set_error(CAPF_ERR_ARG, "conv2d: null pointer");
+  int di = op.dtype_in, dd = op.dtype_out;
+  if (di == CAPF_F32 && dd == CAPF_F32) return conv_dispatch<float, float, float>(p, op, st);
+  if (di == CAPF_F32 && dd == CAPF_F16) return conv_dispatch<float, float, __half>(p, op, st);
+  if (di == CAPF_F32 && dd == CAPF_BF16) return conv_dispatch<float, float, __nv_bfloat16>(p, op, st);
+  if (di == CAPF_F16 && dd == CAPF_F16) return conv_dispatch<__half, __half, __half>(p, op, st);
+  if (di == CAPF_F16 && dd == CAPF_F32) return conv_dispatch<__half, __half, float>(p, op, st);
+  if (di == CAPF_BF16 && dd == CAPF_BF16) return conv_dispatch<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(p, op, st);
+  if (di == CAPF_BF16 && dd == CAPF_F32) return conv_dispatch<__nv_bfloat16, __nv_bfloat16, float>(p, op, st);
+  return set_error(CAPF_ERR_UNSUPPORTED, "conv2d: dtype combination");
+}
+
+// =======================================================================================================
+// HRNet fuse: y = relu(sum_t up_{2^s_t}(term_t))   (pose_hrnet.py:294-301, nearest upsample :244)
+// =======================================================================================================
+struct FuseP {
+  int N, H, W, C, nt, relu;
+  int sh[4];
+  const void* t[4];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) fuse_sum_kernel(FuseP p, T* __restrict__ y) {
+  const int C4 = p.C >> 2;
+  size_t total = (size_t)p.N * p.H * p.W * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    size_t pix = i / C4;
+    int xx = (int)(pix % p.W);
+    size_t t2 = pix / p.W;
+    int yy = (int)(t2 % p.H), n = (int)(t2 / p.H);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (t < p.nt) {
+        int s = p.sh[t];
+        size_t off = (((size_t)n * (p.H >> s) + (yy >> s)) * (p.W >> s) + (xx >> s)) * p.C + c4 * 4;
+        float4 v = ld4<T>((const T*)p.t[t] + off);
+        // first term initialises (reference: y = x[0] ... then y = y + term)
+        if (t == 0) a = v;
+        else { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+      }
+    }
+    if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    st4<T>(y + i * 4, a);
+  }
+}
+
+int launch_fuse_sum(const capf_op& op, cudaStream_t st) {
+  FuseP p;
+  p.N = op.i[0]; p.H = op.i[1]; p.W = op.i[2]; p.C = op.i[3]; p.nt = op.i[4]; p.relu = op.i[9];
+  if (p.nt < 1 || p.nt > 4 || (p.C & 3)) return set_error(CAPF_ERR_ARG, "fuse_sum: 1..4 terms, C%4==0");
+  for (int t = 0; t < 4; ++t) {
+    p.sh[t] = op.i[5 + t];
+    p.t[t] = t < p.nt ? op.in[t] : nullptr;
+    if (t < p.nt && (!p.t[t] || p.sh[t] < 0 || (p.H & ((1 << p.sh[t]) - 1)) || (p.W & ((1 << p.sh[t]) - 1))))
+      return set_error(CAPF_ERR_ARG, "fuse_sum: bad term");
+  }
+  if (op.dtype_in != op.dtype_out) return set_error(CAPF_ERR_UNSUPPORTED, "fuse_sum: dtype_in != dtype_out");
+  size_t total = (size_t)p.N * p.H * p.W * (p.C / 4);
+  int blocks = (int)((total + 255) / 256 < (size_t)g_num_sms * 16 ? (total + 255) / 256 : (size_t)g_num_sms * 16);
+  if (blocks < 1) blocks = 1;
+  switch (op.dtype_out) {
+    case CAPF_F32: fuse_sum_kernel<float><<<blocks, 256, 0, st>>>(p, (float*)op.out[0]); break;
+    case CAPF_F16: fuse_sum_kernel<__half><<<blocks, 256, 0, st>>>(p, (__half*)op.out[0]); break;
+    case CAPF_BF16: fuse_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p, (__nv_bfloat16*)op.out[0]); break;
+    default: return set_error(CAPF_ERR_UNSUPPORTED, "fuse_sum: dtype");
+  }
+  return check_launch("fuse_sum");
+}
+
+// =======================================================================================================
+// CPN helpers: MaxPool2d(3,2,1) (networks/resnet.py:105), bilinear align_corners=True resize
+// (networks/globalNet.py:40, networks/refineNet.py:61; ATen UpSample.h area_pixel_compute_source_index)
+// =======================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(int N, int H, int W, int C, int Ho, int Wo,
+                                                           const T* __restrict__ x, T* __restrict__ y) {
+  const int C4 = C >> 2;
+  size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    size_t pix = i / C4;
+    int ox = (int)(pix % Wo);
+    size_t t2 = pix / Wo;
+    int oy = (int)(t2 % Ho), n = (int)(t2 / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int iy = oy * 2 - 1 + r;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int ix = ox * 2 - 1 + s;
+        if (ix < 0 || ix >= W) continue;
+        float4 v = ld4<T>(x + (((size_t)n * H + iy) * W + ix) * C + c4 * 4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    st4<T>(y + i * 4, m);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear_ac_kernel(int N, int H, int W, int C, int Ho, int Wo, float sy, float sx,
+                                                          const T* __restrict__ x, T* __restrict__ y) {
+  const int C4 = C >> 2;
+  size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    size_t pix = i / C4;
+    int ox = (int)(pix % Wo);
+    size_t t2 = pix / Wo;
+    int oy = (int)(t2 % Ho), n = (int)(t2 / Ho);
+    float fy = __fmul_rn(sy, (float)oy), fx = __fmul_rn(sx, (float)ox);
+    int y0 = (int)fy, x0 = (int)fx;
+    int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    float ly = fy - (float)y0, lx = fx - (float)x0;
+    float hy = 1.f - ly, hx = 1.f - lx;
+    const T* b = x + (size_t)n * H * W * C + c4 * 4;
+    float4 v00 = ld4<T>(b + ((size_t)y0 * W + x0) * C), v01 = ld4<T>(b + ((size_t)y0 * W + x1) * C);
+    float4 v10 = ld4<T>(b + ((size_t)y1 * W + x0) * C), v11 = ld4<T>(b + ((size_t)y1 * W + x1) * C);
+    float4 o;
+    o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+    o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+    o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+    o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+    st4<T>(y + i * 4, o);
+  }
+}
+
+static int ew_blocks(size_t total) {
+  size_t b = (total + 255) / 256, cap = (size_t)g_num_sms * 16;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : (int)b;
+}
+
+int launch_maxpool(const capf_op& op, cudaStream_t st) {
+  int N = op.i[0], H = op.i[1], W = op.i[2], C = op.i[3], Ho = op.i[4], Wo = op.i[5];
+  if ((C & 3) || Ho != (H + 2 - 3) / 2 + 1 || Wo != (W + 2 - 3) / 2 + 1 || op.dtype_in != op.dtype_out)
+    return set_error(CAPF_ERR_ARG, "maxpool: bad shape/dtype");
+  int blocks = ew_blocks((size_t)N * Ho * Wo * (C / 4));
+  switch (op.dtype_in) {
+    case CAPF_F32: maxpool3x3s2_kernel<float><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, (const float*)op.in[0], (float*)op.out[0]); break;
+    case CAPF_F16: maxpool3x3s2_kernel<__half><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, (const __half*)op.in[0], (__half*)op.out[0]); break;
+    case CAPF_BF16: maxpool3x3s2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0]); break;
+    default: return set_error(CAPF_ERR_UNSUPPORTED, "maxpool: dtype");
+  }
+  return check_launch("maxpool3x3s2");
+}
+
+int launch_bilinear(const capf_op& op, cudaStream_t st) {
+  int N = op.i[0], H = op.i[1], W = op.i[2], C = op.i[3], Ho = op.i[4], Wo = op.i[5];
+  if ((C & 3) || op.dtype_in != op.dtype_out) return set_error(CAPF_ERR_ARG, "bilinear: bad shape/dtype");
+  // ATen area_pixel_compute_scale(align_corners=True): (in-1)/(out-1), 0 when out == 1
+  float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  int blocks = ew_blocks((size_t)N * Ho * Wo * (C / 4));
+  switch (op.dtype_in) {
+    case CAPF_F32: bilinear_ac_kernel<float><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, sy, sx, (const float*)op.in[0], (float*)op.out[0]); break;
+    case CAPF_F16: bilinear_ac_kernel<__half><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, sy, sx, (const __half*)op.in[0], (__half*)op.out[0]); break;
+    case CAPF_BF16: bilinear_ac_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, sy, sx, (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0]); break;
+    default: return set_error(CAPF_ERR_UNSUPPORTED, "bilinear: dtype");
+  }
+  return check_launch("bilinear_ac");
+}
+
+// =======================================================================================================
+// LayerNorm over the last dim, one warp per row (pose_dformer.py:65,72,120,138,206)
+// =======================================================================================================
+template <typename TO, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(int rows, int D, int period, float eps,
+                                                        const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ x0,
+                                                        TO* __restrict__ y) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (size_t)warp * D;
+  const float* ar = period > 0 ? x0 + (size_t)(warp % period) * D : nullptr;
+  const int nv = D >> 7;  // float4 per lane (D % 128 == 0)
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      int c = (i * 32 + lane) * 4;
+      float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+      if (ar) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(ar + c));
+        t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+      }
+      v[i] = t;
+      s += (t.x + t.y) + (t.z + t.w);
+    }
+  }
+  float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      int c = (i * 32 + lane) * 4;
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      st4<TO>(y + (size_t)warp * D + c, o);
+    }
+  }
+}
+
+int launch_layernorm(const capf_op& op, cudaStream_t st) {
+  int rows = op.i[0], D = op.i[1], period = op.i[2];
+  if (rows <= 0 || D <= 0 || (D & 127) || D > 128 * 8) return set_error(CAPF_ERR_ARG, "layernorm: D must be a multiple of 128, <= 1024");
+  if (op.dtype_in != CAPF_F32) return set_error(CAPF_ERR_UNSUPPORTED, "layernorm: input stream is f32");
+  if (period > 0 && !op.in[3]) return set_error(CAPF_ERR_ARG, "layernorm: period without x0");
+  int blocks = (rows + 7) / 8;
+  const float *x = (const float*)op.in[0], *g = (const float*)op.in[1], *b = (const float*)op.in[2], *x0 = (const float*)op.in[3];
+  switch (op.dtype_out) {
+    case CAPF_F32: layernorm_kernel<float, 8><<<blocks, 256, 0, st>>>(rows, D, period, op.f[0], x, g, b, x0, (float*)op.out[0]); break;
+    case CAPF_F16: layernorm_kernel<__half, 8><<<blocks, 256, 0, st>>>(rows, D, period, op.f[0], x, g, b, x0, (__half*)op.out[0]); break;
+    case CAPF_BF16: layernorm_kernel<__nv_bfloat16, 8><<<blocks, 256, 0, st>>>(rows, D, period, op.f[0], x, g, b, x0, (__nv_bfloat16*)op.out[0]); break;
+    default: return set_error(CAPF_ERR_UNSUPPORTED, "layernorm: dtype_out");
+  }
+  return check_launch("layernorm");
+}
+
+// =======================================================================================================
+// Tiny-sequence attention (pose_dformer.py:47-55): seq 5 (levels of one joint) or 17 (joints of a frame).
+// One lane per query token; a warp packs floor(32/SEQ) (group, head) items; K/V/Q staged in shared memory.
+// =======================================================================================================
+template <typename TI, typename TO, int SEQ>
+__global__ void __launch_bounds__(128) attention_small_kernel(int groups, int heads, int hd, int tok_stride, int grp_stride,
+                                                              float scale, const TI* __restrict__ qkv, TO* __restrict__ out) {
+  constexpr int IPW = 32 / SEQ;  // items per warp
+  extern __shared__ float sm[];
+  const int warp_in_blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hp = hd + 1;  // padded row pitch (bank-conflict free row-strided access)
+  float* base = sm + (size_t)warp_in_blk * (IPW * SEQ * hp * 3);
+  float* sq = base;
+  float* sk = sq + IPW * SEQ * hp;
+  float* sv = sk + IPW * SEQ * hp;
+  const int D = heads * hd;
+  const long long n_items = (long long)groups * heads;
+  const long long item0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp_in_blk) * IPW;
+  if (item0 >= n_items) return;
+
+  // cooperative, coalesced staging of q/k/v rows
+  for (int it = 0; it < IPW; ++it) {
+    long long item = item0 + it;
+    if (item >= n_items) break;
+    int g = (int)(item / heads), h = (int)(item % heads);
+    for (int t = 0; t < SEQ; ++t) {
+      size_t row = (size_t)g * grp_stride + (size_t)t * tok_stride;
+      const TI* src = qkv + row * (size_t)(3 * D) + h * hd;
+      float* dq = sq + (it * SEQ + t) * hp;
+      float* dk = sk + (it * SEQ + t) * hp;
+      float* dv = sv + (it * SEQ + t) * hp;
+      for (int d = lane; d < hd; d += 32) {
+        dq[d] = to_f<TI>(src[d]);
+        dk[d] = to_f<TI>(src[D + d]);
+        dv[d] = to_f<TI>(src[2 * D + d]);
+      }
+    }
+  }
+  __syncwarp();
+
+  const int it = lane / SEQ, i = lane - it * SEQ;
+  const bool active = (it < IPW) && (item0 + it < n_items);
+  if (active) {
+    const float* q = sq + (it * SEQ + i) * hp;
+    const float* kb = sk + it * SEQ * hp;
+    const float* vb = sv + it * SEQ * hp;
+    float sc[SEQ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SEQ; ++j) {
+      float a = 0.f;
+      for (int d = 0; d < hd; ++d) a = fmaf(q[d], kb[j * hp + d], a);
+      a *= scale;
+      sc[j] = a;
+      mx = fmaxf(mx, a);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < SEQ; ++j) {
+      sc[j] = __expf(sc[j] - mx);
+      den += sc[j];
+    }
+    float inv = 1.0f / den;
+    // write the output row over this lane's own q row (no other lane reads it any more)
+    float* o = sq + (it * SEQ + i) * hp;
+    for (int d = 0; d < hd; ++d) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < SEQ; ++j) a = fmaf(sc[j], vb[j * hp + d], a);
+      o[d] = a * inv;
+    }
+  }
+  __syncwarp();
+  for (int it2 = 0; it2 < IPW; ++it2) {
+    long long item = item0 + it2;
+    if (item >= n_items) break;
+    int g = (int)(item / heads), h = (int)(item % heads);
+    for (int t = 0; t < SEQ; ++t) {
+      size_t row = (size_t)g * grp_stride + (size_t)t * tok_stride;
+      TO* dst = out + row * (size_t)D + h * hd;
+      const float* o = sq + (it2 * SEQ + t) * hp;
+      for (int d = lane; d < hd; d += 32) dst[d] = from_f<TO>(o[d]);
+    }
+  }
+}
+
+template <typename TI, typename TO>
+static int attention_dispatch(const capf_op& op, cudaStream_t st) {
+  int groups = op.i[0], seq = op.i[1], heads = op.i[2], hd = op.i[3], ts = op.i[4], gs = op.i[5];
+  int ipw = 32 / seq;
+  long long items = (long long)groups * heads;
+  long long warps = (items + ipw - 1) / ipw;
+  int blocks = (int)((warps + 3) / 4);
+  size_t smem = (size_t)4 * ipw * seq * (hd + 1) * 3 * sizeof(float);
+  const TI* qkv = (const TI*)op.in[0];
+  TO* out = (TO*)op.out[0];
+  if (seq == 5) {
+    cudaFuncSetAttribute(attention_small_kernel<TI, TO, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attention_small_kernel<TI, TO, 5><<<blocks, 128, smem, st>>>(groups, heads, hd, ts, gs, op.f[0], qkv, out);
+  } else {
+    cudaFuncSetAttribute(attention_small_kernel<TI, TO, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attention_small_kernel<TI, TO, 17><<<blocks, 128, smem, st>>>(groups, heads, hd, ts, gs, op.f[0], qkv, out);
+  }
+  return check_launch("attention_small");
+}
+
+int launch_attention(const capf_op& op, cudaStream_t st) {
+  int seq = op.i[1], hd = op.i[3];
+  if (op.i[0] <= 0 || (seq != 5 && seq != 17) || op.i[2] <= 0 || hd <= 0 || hd > 256)
+    return set_error(CAPF_ERR_ARG, "attention: seq must be 5 or 17, head_dim <= 256");
+  if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_F32) return attention_dispatch<float, float>(op, st);
+  if (op.dtype_in == CAPF_F16 && op.dtype_out == CAPF_F16) return attention_dispatch<__half, __half>(op, st);
+  if (op.dtype_in == CAPF_BF16 && op.dtype_out == CAPF_BF16) return attention_dispatch<__nv_bfloat16, __nv_bfloat16>(op, st);
+  return set_error(CAPF_ERR_UNSUPPORTED, "attention: dtype combination");
+}
+
+// =======================================================================================================
+// Joint-context samplers
+// =======================================================================================================
+struct SampP {
+  int B, J, nl;
+  int H[4], W[4], C[4];
+  long long off[4];
+  const void* map[4];
+};
+
+// (a7) reference-point gather, padding_mode='zeros' (pose_dformer.py:216-218).  One warp per (b, j).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) ref_sample_kernel(SampP p, const float* __restrict__ ref, TO* __restrict__ out,
+                                                         int* __restrict__ rec) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int R = p.B * p.J;
+  if (warp >= R) return;
+  int b = warp / p.J;
+  float gx = __ldg(ref + 2 * warp), gy = __ldg(ref + 2 * warp + 1);
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    if (l >= p.nl) break;
+    const int H = p.H[l], W = p.W[l], C = p.C[l];
+    Corners c = make_corners<false>(gx, gy, W, H);
+    if (rec && lane == 0) {
+      int* r = rec + ((size_t)l * R + warp) * 4;
+      r[0] = c.x0; r[1] = c.y0; r[2] = (int)c.mask; r[3] = 0;
+    }
+    const TI* m = (const TI*)p.map[l] + (size_t)b * H * W * C;
+    TO* o = out + p.off[l] + (size_t)warp * C;
+    for (int ch = lane * 4; ch < C; ch += 128) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c.mask & (1u << k)) {
+          int xx = c.x0 + (k & 1), yy = c.y0 + (k >> 1);
+          float4 v = ld4<TI>(m + ((size_t)yy * W + xx) * C + ch);
+          float wk = c.w[k];
+          // ATen accumulates out += val * weight corner by corner (no FMA on the CPU path)
+          a.x = __fadd_rn(a.x, __fmul_rn(v.x, wk));
+          a.y = __fadd_rn(a.y, __fmul_rn(v.y, wk));
+          a.z = __fadd_rn(a.z, __fmul_rn(v.z, wk));
+          a.w = __fadd_rn(a.w, __fmul_rn(v.w, wk));
+        }
+      }
+      st4<TO>(o + ch, a);
+    }
+  }
+}
+
+// (a8) deformable gather, padding_mode='border' (pose_dformer.py:122-135). One warp per (level, b, j, head):
+// softmax over the head's 4 logits, tanh offsets, 4 samples x 4 corners, sample-weighted sum.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) deform_sample_kernel(SampP p, const float* __restrict__ ref,
+                                                            const float* __restrict__ ow, TO* __restrict__ out,
+                                                            int* __restrict__ rec) {
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int R = p.B * p.J;
+  long long total = (long long)p.nl * R * 4;
+  if (warp >= total) return;
+  int h = (int)(warp & 3);
+  long long t = warp >> 2;
+  int rj = (int)(t % R), l = (int)(t / R);
+  int b = rj / p.J;
+  const int H = p.H[l], W = p.W[l], C = p.C[l];
+  const float* row = ow + ((size_t)l * R + rj) * 48;
+  float lg[4], mx = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { lg[s] = __ldg(row + h * 4 + s); mx = fmaxf(mx, lg[s]); }
+  float den = 0.f;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { lg[s] = expf(lg[s] - mx); den += lg[s]; }
+  float gx = __ldg(ref + 2 * rj), gy = __ldg(ref + 2 * rj + 1);
+  Corners c[4];
+  float aw[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    aw[s] = lg[s] / den;
+    float ox = tanhf(__ldg(row + 16 + (h * 4 + s) * 2)), oy = tanhf(__ldg(row + 16 + (h * 4 + s) * 2 + 1));
+    c[s] = make_corners<true>(__fadd_rn(ox, gx), __fadd_rn(oy, gy), W, H);
+    if (rec && lane == 0) {
+      int* r = rec + ((((size_t)l * R + rj) * 16) + h * 4 + s) * 4;
+      r[0] = c[s].x0; r[1] = c[s].y0; r[2] = (int)c[s].mask; r[3] = 0;
+    }
+  }
+  const TI* m = (const TI*)p.map[l] + (size_t)b * H * W * C;
+  TO* o = out + p.off[l] + ((size_t)rj * 4 + h) * C;
+  for (int ch = lane * 4; ch < C; ch += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c[s].mask & (1u << k)) {
+          int xx = c[s].x0 + (k & 1), yy = c[s].y0 + (k >> 1);
+          float4 v = ld4<TI>(m + ((size_t)yy * W + xx) * C + ch);
+          float wk = c[s].w[k];
+          a.x = __fadd_rn(a.x, __fmul_rn(v.x, wk));
+          a.y = __fadd_rn(a.y, __fmul_rn(v.y, wk));
+          a.z = __fadd_rn(a.z, __fmul_rn(v.z, wk));
+          a.w = __fadd_rn(a.w, __fmul_rn(v.w, wk));
+        }
+      }
+      acc.x = fmaf(aw[s], a.x, acc.x);
+      acc.y = fmaf(aw[s], a.y, acc.y);
+      acc.z = fmaf(aw[s], a.z, acc.z);
+      acc.w = fmaf(aw[s], a.w, acc.w);
+    }
+    st4<TO>(o + ch, acc);
+  }
+}
+
+static int fill_samp(const capf_op& op, SampP& p, const char* who) {
+  p.B = op.i[0]; p.J = op.i[1]; p.nl = op.i[2];
+  if (p.B <= 0 || p.J <= 0 || p.nl < 1 || p.nl > 4) return set_error(CAPF_ERR_ARG, who);
+  for (int l = 0; l < 4; ++l) {
+    p.H[l] = p.W[l] = p.C[l] = 0; p.off[l] = 0; p.map[l] = nullptr;
+    if (l < p.nl) {
+      p.H[l] = op.i[3 + 3 * l]; p.W[l] = op.i[4 + 3 * l]; p.C[l] = op.i[5 + 3 * l];
+      p.off[l] = op.i[15 + l];
+      p.map[l] = op.in[1 + l];
+      if (p.H[l] <= 0 || p.W[l] <= 0 || p.C[l] <= 0 || (p.C[l] & 3) || !p.map[l] || (p.off[l] & 3))
+        return set_error(CAPF_ERR_ARG, who);
+    }
+  }
+  if (!op.in[0] || !op.out[0]) return set_error(CAPF_ERR_ARG, who);
+  return 0;
+}
+
+template <typename TI, typename TO>
+static int sample_dispatch(const capf_op& op, const SampP& p, cudaStream_t st) {
+  if (op.kind == CAPF_OP_REF_SAMPLE) {
+    int R = p.B * p.J;
+    ref_sample_kernel<TI, TO><<<(R + 7) / 8, 256, 0, st>>>(p, (const float*)op.in[0], (TO*)op.out[0], (int*)op.out[1]);
+    return check_launch("ref_sample");
+  }
+  long long warps = (long long)p.nl * p.B * p.J * 4;
+  deform_sample_kernel<TI, TO><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(p, (const float*)op.in[0], (const float*)op.in[5],
+                                                                           (TO*)op.out[0], (int*)op.out[1]);
+  return check_launch("deform_sample");
+}
+
+int launch_sample(const capf_op& op, cudaStream_t st) {
+  SampP p;
+  int e = fill_samp(op, p, op.kind == CAPF_OP_REF_SAMPLE ? "ref_sample: bad arguments" : "deform_sample: bad arguments");
+  if (e) return e;
+  if (op.kind == CAPF_OP_DEFORM_SAMPLE && !op.in[5]) return set_error(CAPF_ERR_ARG, "deform_sample: ow is null");
+  int di = op.dtype_in, dd = op.dtype_out;
+  if (di == CAPF_F32 && dd == CAPF_F32) return sample_dispatch<float, float>(op, p, st);
+  if (di == CAPF_F16 && dd == CAPF_F16) return sample_dispatch<__half, __half>(op, p, st);
+  if (di == CAPF_F16 && dd == CAPF_F32) return sample_dispatch<__half, float>(op, p, st);
+  if (di == CAPF_BF16 && dd == CAPF_BF16) return sample_dispatch<__nv_bfloat16, __nv_bfloat16>(op, p, st);
+  if (di == CAPF_BF16 && dd == CAPF_F32) return sample_dispatch<__nv_bfloat16, float>(op, p, st);
+  return set_error(CAPF_ERR_UNSUPPORTED, "sample: dtype combination");
+}
+
+// =======================================================================================================
+// Token-stream glue
+// =======================================================================================================
+// coord_embed + Spatial_pos_embed (pose_dformer.py:214,223-225) into the level-major stream X[slab][b*J+j][D]
+__global__ void __launch_bounds__(256) embed_coord_kernel(int R, int J, int D, int slabs, const float* __restrict__ kp,
+                                                          const float* __restrict__ Wc, const float* __restrict__ bc,
+                                                          const float* __restrict__ pos, float* __restrict__ X) {
+  size_t total = (size_t)slabs * R * D;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int d = (int)(i % D);
+    size_t t = i / D;
+    int r = (int)(t % R), s = (int)(t / R);
+    int j = r % J;
+    float v = __ldg(pos + ((size_t)s * J + j) * D + d);
+    if (s == 0) {
+      float kx = __ldg(kp + 2 * r), ky = __ldg(kp + 2 * r + 1);
+      // nn.Linear(2, D): x @ W^T + b, accumulated in k order like a GEMM
+      float e = fmaf(ky, __ldg(Wc + 2 * d + 1), __fmul_rn(kx, __ldg(Wc + 2 * d)));
+      v = __fadd_rn(__fadd_rn(e, __ldg(bc + d)), v);
+    }
+    X[i] = v;
+  }
+}
+
+// '(b p) l c -> b p (l c)' (pose_dformer.py:235)
+__global__ void __launch_bounds__(256) levels_to_joint_kernel(int R, int slabs, int D, const float* __restrict__ X,
+                                                              float* __restrict__ Y) {
+  const int D4 = D >> 2;
+  size_t total = (size_t)R * slabs * D4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int d4 = (int)(i % D4);
+    size_t t = i / D4;
+    int s = (int)(t % slabs), r = (int)(t / slabs);
+    float4 v = __ldg(reinterpret_cast<const float4*>(X + ((size_t)s * R + r) * D + d4 * 4));
+    *reinterpret_cast<float4*>(Y + i * 4) = v;
+  }
+}
+
+// keypoints_2d_cpn_crop[..., :2] /= (96, 128);  -= (1, 1)   (conpose.py:34-35), in place
+__global__ void crop_normalize_kernel(int n, float* __restrict__ c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float2 v = reinterpret_cast<float2*>(c)[i];
+    v.x = __fsub_rn(__fdiv_rn(v.x, 96.0f), 1.0f);
+    v.y = __fsub_rn(__fdiv_rn(v.y, 128.0f), 1.0f);
+    reinterpret_cast<float2*>(c)[i] = v;
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(size_t n, const TI* __restrict__ x, TO* __restrict__ y) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = from_f<TO>(to_f<TI>(x[i]));
+}
+
+int launch_embed_coord(const capf_op& op, cudaStream_t st) {
+  int B = op.i[0], J = op.i[1], D = op.i[2], slabs = op.i[3];
+  if (B <= 0 || J <= 0 || D <= 0 || slabs <= 0 || !op.in[0] || !op.in[1] || !op.in[2] || !op.in[3] || !op.out[0])
+    return set_error(CAPF_ERR_ARG, "embed_coord: bad arguments");
+  size_t total = (size_t)slabs * B * J * D;
+  embed_coord_kernel<<<ew_blocks(total), 256, 0, st>>>(B * J, J, D, slabs, (const float*)op.in[0], (const float*)op.in[1],
+                                                       (const float*)op.in[2], (const float*)op.in[3], (float*)op.out[0]);
+  return check_launch("embed_coord");
+}
+
+int launch_levels_to_joint(const capf_op& op, cudaStream_t st) {
+  int R = op.i[0], slabs = op.i[1], D = op.i[2];
+  if (R <= 0 || slabs <= 0 || D <= 0 || (D & 3)) return set_error(CAPF_ERR_ARG, "levels_to_joint: bad arguments");
+  levels_to_joint_kernel<<<ew_blocks((size_t)R * slabs * (D / 4)), 256, 0, st>>>(R, slabs, D, (const float*)op.in[0], (float*)op.out[0]);
+  return check_launch("levels_to_joint");
+}
+
+int launch_crop_normalize(const capf_op& op, cudaStream_t st) {
+  int n = op.i[0];
+  if (n <= 0 || !op.out[0]) return set_error(CAPF_ERR_ARG, "crop_normalize: bad arguments");
+  crop_normalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (float*)op.out[0]);
+  return check_launch("crop_normalize");
+}
+
+int launch_cast(const capf_op& op, cudaStream_t st) {
+  size_t n = (size_t)(uint32_t)op.i[0] | ((size_t)(uint32_t)op.i[1] << 31);
+  if (!n || !op.in[0] || !op.out[0]) return set_error(CAPF_ERR_ARG, "cast: bad arguments");
+  int blocks = ew_blocks(n);
+  if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_F16)
+    cast_kernel<float, __half><<<blocks, 256, 0, st>>>(n, (const float*)op.in[0], (__half*)op.out[0]);
+  else if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_BF16)
+    cast_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>(n, (const float*)op.in[0], (__nv_bfloat16*)op.out[0]);
+  else if (op.dtype_in == CAPF_F16 && op.dtype_out == CAPF_F32)
+    cast_kernel<__half, float><<<blocks, 256, 0, st>>>(n, (const __half*)op.in[0], (float*)op.out[0]);
+  else if (op.dtype_in == CAPF_BF16 && op.dtype_out == CAPF_F32)
+    cast_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>(n, (const __nv_bfloat16*)op.in[0], (float*)op.out[0]);
+  else if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_F32)
+    cast_kernel<float, float><<<blocks, 256, 0, st>>>(n, (const float*)op.in[0], (float*)op.out[0]);
+  else
+    return set_error(CAPF_ERR_UNSUPPORTED, "cast: dtype combination");
+  return check_launch("cast");
+}
+
+}  // namespace capf

@@ -1,0 +1,53 @@
+"""Plan caching shared by the backbone modules and CA_PF."""
+import os
+
+import torch
+
+from ... import lib, program
+
+
+def default_precision():
+    return os.environ.get("CAPF_PRECISION", "fp32")
+
+
+def default_use_tc():
+    return os.environ.get("CAPF_TCGEN05", "1") != "0"
+
+
+def state_version(module: torch.nn.Module):
+    """Cheap change detector: sum of tensor version counters + storage pointers of the first/last tensors."""
+    v = 0
+    for t in module.parameters():
+        v += t._version
+    for t in module.buffers():
+        v += t._version
+    return v
+
+
+class BackboneRuntimeMixin:
+    """Lets a backbone be called on its own: NCHW in -> list of 4 NCHW maps (reference signature)."""
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise lib.CapfError("the backbone runs on a B200 through libcapf_b200; got a CPU tensor (no CPU path)")
+        B, C, H, W = x.shape
+        prec = getattr(self, "precision", None) or default_precision()
+        key = (B, H, W, prec, x.device.index)
+        cache = self.__dict__.setdefault("_plans", {})
+        state = {"backbone." + k: v for k, v in self.state_dict().items()}
+        ver = state_version(self)
+        ent = cache.get(key)
+        if ent is None:
+            shapes = {k: tuple(v.shape) for k, v in state.items()}
+            bb = "cpn" if self.kind == "cpn" else "hrnet_32"
+            prog = program.build_forward_program(bb, getattr(self, "cfg", None), None, shapes, B, H, W, prec,
+                                                 use_tc=default_use_tc(), backbone_only=True)
+            ent = [program.Plan(prog, state, x.device), ver]
+            cache[key] = ent
+        elif ent[1] != ver:
+            ent[0].repack(state)
+            ent[1] = ver
+        plan = ent[0]
+        plan.tensor(plan.prog.inputs["images"]).copy_(x.permute(0, 2, 3, 1))
+        plan.run()
+        return [plan.tensor(m).permute(0, 3, 1, 2).float() for m in plan.prog.feature_maps]

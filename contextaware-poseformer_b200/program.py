@@ -1,0 +1,544 @@
+"""Forward programs: the flat op list libcapf_b200 executes for one (backbone, precision, B, H, W).
+
+``ProgramBuilder`` is the visitor that arch.walk_* drive; ``build_forward_program`` appends the sampler and
+lifter (PoseTransformer.forward, pose_dformer.py:210-241).  A ``Program`` is pure description (shapes, buffer
+liveness, weight-packing recipes) and needs neither a GPU nor the shared library, so the CPU test-suite can
+check it against the oracle with a reference interpreter (tests/interp.py).  ``Plan`` binds a program to
+device memory + packed weights and runs it through the C ABI.
+
+Precision policies
+  fp32 : every tensor f32, CUDA-core kernels                        (parity mode, <=1e-5 of the oracle)
+  fp16 : backbone activations/weights f16 (f32 accumulate), lifter token stream f32 with f16 GEMM operands
+  bf16 : same with bfloat16
+"""
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from . import arch, lib
+
+J = 17  # joints (pose_dformer.py:145)
+
+_TORCH_DT = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16, "i32": torch.int32}
+_ITEMSIZE = {"f32": 4, "f16": 2, "bf16": 2, "i32": 4}
+
+
+@dataclass(eq=False)
+class Buf:
+    name: str
+    shape: tuple
+    dtype: str
+    role: str = "act"            # act | input | output
+    base: Optional["Buf"] = None  # views share storage with base at `offset` elements
+    offset: int = 0
+
+    @property
+    def root(self):
+        return self.base.root if self.base is not None else self
+
+    @property
+    def root_offset(self):
+        return self.offset + (self.base.root_offset if self.base is not None else 0)
+
+    @property
+    def numel(self):
+        return int(np.prod(self.shape))
+
+    @property
+    def nbytes(self):
+        return self.numel * _ITEMSIZE[self.dtype]
+
+    def view(self, offset, shape, name=None):
+        return Buf(name or f"{self.name}[{offset}:]", tuple(shape), self.dtype, self.role, self, int(offset))
+
+
+@dataclass(eq=False)
+class WSlot:
+    """A packed parameter blob; ``pack(state_dict) -> cpu tensor`` of `shape`/`dtype`."""
+    name: str
+    shape: tuple
+    dtype: str
+    pack: Callable
+
+
+@dataclass(eq=False)
+class Op:
+    kind: int
+    dtype_in: str
+    dtype_out: str
+    i: List[int]
+    f: List[float]
+    ins: list
+    outs: list
+    tag: str = ""
+    flops: int = 0
+
+
+@dataclass
+class Program:
+    backbone: str
+    precision: str
+    B: int
+    H: int
+    W: int
+    ops: List[Op] = field(default_factory=list)
+    inputs: dict = field(default_factory=dict)
+    outputs: dict = field(default_factory=dict)
+    feature_maps: list = field(default_factory=list)
+    n_backbone_ops: int = 0
+
+    def flops(self):
+        return sum(o.flops for o in self.ops)
+
+
+# ------------------------------------------------------------------------------------------------------
+# weight packing (host side, float64 folding so the fold itself adds no error)
+# ------------------------------------------------------------------------------------------------------
+BN_EPS = 1e-5  # nn.BatchNorm2d default, used throughout the reference
+
+
+def _fold(state, wkey, bnkey):
+    w = state[wkey].detach().to("cpu", torch.float64)
+    cout = w.shape[0]
+    if bnkey is None:
+        return w, torch.zeros(cout, dtype=torch.float64)
+    g = state[bnkey + ".weight"].detach().to("cpu", torch.float64)
+    b = state[bnkey + ".bias"].detach().to("cpu", torch.float64)
+    m = state[bnkey + ".running_mean"].detach().to("cpu", torch.float64)
+    v = state[bnkey + ".running_var"].detach().to("cpu", torch.float64)
+    s = g / torch.sqrt(v + BN_EPS)
+    return w * s.view(-1, 1, 1, 1), b - m * s
+
+
+def conv_weight_packer(wkey, bnkey, dtype, layout):
+    def pack(state):
+        w, _ = _fold(state, wkey, bnkey)
+        cout = w.shape[0]
+        if layout == "kc":      # SIMT kernel: [KH*KW*Cin][Cout], k = (r*KW+s)*Cin+ci
+            wp = w.permute(2, 3, 1, 0).reshape(-1, cout)
+        else:                   # tcgen05 kernel: [Cout][KH*KW*Cin]  (K-major B operand)
+            wp = w.permute(0, 2, 3, 1).reshape(cout, -1)
+        return wp.contiguous().to(_TORCH_DT[dtype])
+    return pack
+
+
+def conv_bias_packer(wkey, bnkey):
+    def pack(state):
+        return _fold(state, wkey, bnkey)[1].to(torch.float32)
+    return pack
+
+
+def linear_weight_packer(wkeys, dtype, layout):
+    def pack(state):
+        w = torch.cat([state[k].detach().to("cpu", torch.float32) for k in wkeys], dim=0)   # [out, in]
+        wp = w.t() if layout == "kc" else w
+        return wp.contiguous().to(_TORCH_DT[dtype])
+    return pack
+
+
+def vec_packer(keys):
+    def pack(state):
+        return torch.cat([state[k].detach().to("cpu", torch.float32).reshape(-1) for k in keys]).contiguous()
+    return pack
+
+
+# ------------------------------------------------------------------------------------------------------
+# builder
+# ------------------------------------------------------------------------------------------------------
+class ProgramBuilder:
+    def __init__(self, program: Program, shapes: dict, use_tc: bool = False):
+        self.p = program
+        self.shapes = shapes          # state_dict key -> shape (for channel counts)
+        self.prefix = "backbone."
+        prec = program.precision
+        self.act_dt = {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[prec]
+        self.use_tc = use_tc and prec != "fp32"
+        self._n = 0
+
+    # -- helpers ---------------------------------------------------------------------------------------
+    def _buf(self, name, shape, dtype, role="act"):
+        self._n += 1
+        return Buf(f"{name}#{self._n}", tuple(int(s) for s in shape), dtype, role)
+
+    def _emit(self, *a, **k):
+        op = Op(*a, **k)
+        self.p.ops.append(op)
+        return op
+
+    def _conv_impl(self, cin, cout, k, stride, dt_in):
+        """Kernel family for a conv/linear.  tcgen05 needs 16-bit operands and TMA-friendly channel counts."""
+        if not self.use_tc or dt_in == "f32":
+            return lib.IMPL_SIMT
+        if cin % 16 or cout % 16 or cout > 256 and cout % 128:
+            return lib.IMPL_SIMT
+        return lib.IMPL_TCGEN05
+
+    # -- visitor API used by arch.walk_* -----------------------------------------------------------------
+    def conv(self, cname, bname, x, cout, k=1, stride=1, act=arch.NONE, residual=None):
+        B = self.p.B
+        wkey = self.prefix + cname + ".weight"
+        bnkey = self.prefix + bname
+        pad = k // 2
+        Ho = (x.H + 2 * pad - k) // stride + 1
+        Wo = (x.W + 2 * pad - k) // stride + 1
+        src: Buf = x.ref
+        dt_in = src.dtype
+        dt_out = self.act_dt
+        impl = self._conv_impl(x.C, cout, k, stride, dt_in)
+        wdt = "f32" if dt_in == "f32" else dt_in
+        layout = "ck" if impl == lib.IMPL_TCGEN05 else "kc"
+        K = k * k * x.C
+        w = WSlot(f"w:{cname}", (K, cout) if layout == "kc" else (cout, K), wdt, conv_weight_packer(wkey, bnkey, wdt, layout))
+        b = WSlot(f"b:{cname}", (cout,), "f32", conv_bias_packer(wkey, bnkey))
+        out = self._buf(cname, (B, Ho, Wo, cout), dt_out)
+        acode = {arch.NONE: lib.ACT_NONE, arch.RELU: lib.ACT_RELU, arch.GELU: lib.ACT_GELU}[act]
+        self._emit(lib.OP_CONV2D, dt_in, dt_out,
+                   [B, x.H, x.W, x.C, cout, k, k, stride, pad, Ho, Wo, acode, impl], [],
+                   [src, w, b, residual.ref if residual is not None else None], [out],
+                   tag=self.prefix + cname, flops=2 * B * Ho * Wo * cout * K)
+        return arch.T(Ho, Wo, cout, out)
+
+    def fuse(self, terms, relu=True):
+        B = self.p.B
+        t0 = terms[0][0]
+        assert terms[0][1] == 0 or True
+        # output resolution = resolution of the shift-0 term
+        ref_t = next(t for t, s in terms if s == 0)
+        H, W, Cc = ref_t.H, ref_t.W, ref_t.C
+        out = self._buf("fuse", (B, H, W, Cc), self.act_dt)
+        shifts = [s for _, s in terms] + [0] * (4 - len(terms))
+        self._emit(lib.OP_FUSE_SUM, self.act_dt, self.act_dt, [B, H, W, Cc, len(terms)] + shifts + [1 if relu else 0], [],
+                   [t.ref for t, _ in terms], [out], tag="fuse")
+        return arch.T(H, W, Cc, out)
+
+    def maxpool(self, x):
+        B = self.p.B
+        Ho, Wo = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
+        out = self._buf("maxpool", (B, Ho, Wo, x.C), x.ref.dtype)
+        self._emit(lib.OP_MAXPOOL, x.ref.dtype, x.ref.dtype, [B, x.H, x.W, x.C, Ho, Wo], [], [x.ref], [out], tag="maxpool")
+        return arch.T(Ho, Wo, x.C, out)
+
+    def bilinear(self, x, Ho, Wo):
+        B = self.p.B
+        out = self._buf("bilinear", (B, Ho, Wo, x.C), x.ref.dtype)
+        self._emit(lib.OP_BILINEAR, x.ref.dtype, x.ref.dtype, [B, x.H, x.W, x.C, Ho, Wo], [], [x.ref], [out], tag="bilinear")
+        return arch.T(Ho, Wo, x.C, out)
+
+    def dead_conv(self, *a):
+        pass
+
+    def dead_bn(self, *a):
+        pass
+
+    # -- token-matrix ops for the lifter -------------------------------------------------------------------
+    def linear(self, x: Buf, rows, cin, wkeys, bkeys, cout, act=arch.NONE, residual: Buf = None, out: Buf = None,
+               out_dtype=None, tag=""):
+        dt_in = x.dtype
+        dt_out = out_dtype or (out.dtype if out is not None else self.act_dt)
+        impl = self._conv_impl(cin, cout, 1, 1, dt_in)
+        wdt = "f32" if dt_in == "f32" else dt_in
+        layout = "ck" if impl == lib.IMPL_TCGEN05 else "kc"
+        w = WSlot(f"w:{tag}", (cin, cout) if layout == "kc" else (cout, cin), wdt, linear_weight_packer(wkeys, wdt, layout))
+        b = WSlot(f"b:{tag}", (cout,), "f32", vec_packer(bkeys)) if bkeys else None
+        if out is None:
+            out = self._buf(tag, (rows, cout), dt_out)
+        acode = {arch.NONE: lib.ACT_NONE, arch.RELU: lib.ACT_RELU, arch.GELU: lib.ACT_GELU}[act]
+        self._emit(lib.OP_CONV2D, dt_in, dt_out, [rows, 1, 1, cin, cout, 1, 1, 1, 0, 1, 1, acode, impl], [],
+                   [x, w, b, residual], [out], tag=tag, flops=2 * rows * cin * cout)
+        return out
+
+    def layernorm(self, x: Buf, rows, D, prefix, eps, out_dtype, x0: Buf = None, period=0, tag=""):
+        g = WSlot(f"g:{tag}", (D,), "f32", vec_packer([prefix + ".weight"]))
+        b = WSlot(f"b:{tag}", (D,), "f32", vec_packer([prefix + ".bias"]))
+        out = self._buf(tag, (rows, D), out_dtype)
+        self._emit(lib.OP_LAYERNORM, "f32", out_dtype, [rows, D, period], [eps], [x, g, b, x0], [out], tag=tag)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole-forward program
+# ------------------------------------------------------------------------------------------------------
+def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H: int, W: int, precision: str = "fp32",
+                          use_tc: bool = False, debug_records: bool = False, backbone_only: bool = False) -> Program:
+    """CA_PF.forward (conpose.py:30-42) after the crop normalisation, as a Program.
+
+    inputs : images [B,H,W,3] f32 (NHWC as the caller passes them -- no permute is needed, conpose.py:32),
+             kp2d [B*17,2] f32, ref [B*17,2] f32 (already normalised, conpose.py:34-35)
+    output : out [B*17,3] f32  (== [B,1,17,3])
+    """
+    if precision not in ("fp32", "fp16", "bf16"):
+        raise ValueError(f"precision {precision!r}")
+    prog = Program(backbone, precision, B, H, W)
+    pb = ProgramBuilder(prog, shapes, use_tc)
+    images = Buf("images", (B, H, W, 3), "f32", "input")
+    prog.inputs["images"] = images
+    x = arch.T(H, W, 3, images)
+    if backbone in ("hrnet_32", "hrnet_48"):
+        maps = arch.walk_hrnet(pb, x, bb_cfg)
+    elif backbone == "cpn":
+        maps = arch.walk_cpn(pb, x)
+    else:
+        raise ValueError(backbone)
+    prog.feature_maps = [m.ref for m in maps]
+    prog.n_backbone_ops = len(prog.ops)
+    if backbone_only:
+        for k, m in enumerate(maps):
+            m.ref.role = "output"
+            prog.outputs[f"map{k}"] = m.ref
+        return prog
+
+    D = int(pf_cfg["embed_dim_ratio"])
+    levels = int(pf_cfg["levels"])
+    if levels != 4:
+        raise NotImplementedError("the sampler kernels are specialised for the reference's 4 feature levels")
+    dims = arch.feature_dims(backbone, int(pf_cfg["base_dim"]))
+    for l in range(levels):
+        assert maps[l].C == dims[l], (maps[l].C, dims[l])
+    R = B * J
+    S = levels + 1
+    E = D * S
+    adt = pb.act_dt                     # GEMM operand dtype in the lifter
+    vn = "volume_net."
+    kp2d = Buf("kp2d", (R, 2), "f32", "input")
+    ref = Buf("ref", (R, 2), "f32", "input")
+    prog.inputs["kp2d"], prog.inputs["ref"] = kp2d, ref
+
+    # ---- token stream X[slab][b*17+j][D] f32, level-major ------------------------------------------------
+    X = pb._buf("X", (S, R, D), "f32")
+    pb._emit(lib.OP_EMBED_COORD, "f32", "f32", [B, J, D, S], [],
+             [kp2d, WSlot("w:coord_embed", (D, 2), "f32", vec_packer([vn + "coord_embed.weight"])),
+              WSlot("b:coord_embed", (D,), "f32", vec_packer([vn + "coord_embed.bias"])),
+              WSlot("pos", (S, J, D), "f32", vec_packer([vn + "Spatial_pos_embed"]))], [X], tag="embed_coord")
+
+    map_geo = []
+    for l in range(levels):
+        map_geo += [maps[l].H, maps[l].W, maps[l].C]
+    map_geo += [0] * (12 - len(map_geo))
+
+    # ---- (a7) reference-point gather + feat_embed ---------------------------------------------------------
+    offs = [0]
+    for l in range(levels):
+        offs.append(offs[-1] + R * dims[l])
+    samp = pb._buf("ref_sampled", (offs[-1],), adt)
+    rec0 = pb._buf("ref_corners", (levels, R, 4), "i32") if debug_records else None
+    if rec0 is not None:
+        rec0.role = "output"
+        prog.outputs["ref_corners"] = rec0
+    pb._emit(lib.OP_REF_SAMPLE, maps[0].ref.dtype, adt, [B, J, levels] + map_geo + offs[:4], [],
+             [ref] + [m.ref for m in maps], [samp, rec0], tag="ref_sample")
+    for l in range(levels):
+        slab = X.view((1 + l) * R * D, (R, D), f"X[{1 + l}]")
+        pb.linear(samp.view(offs[l], (R, dims[l])), R, dims[l], [f"{vn}feat_embed.{l}.weight"], [f"{vn}feat_embed.{l}.bias"],
+                  D, residual=slab, out=slab, tag=f"{vn}feat_embed.{l}")
+
+    # ---- (a8) 4 x DeformableBlock -------------------------------------------------------------------------
+    X0 = X.view(0, (R, D), "X[0]")
+    Xl = X.view(R * D, (levels * R, D), "X[1:]")
+    goffs = [0]
+    for l in range(levels):
+        goffs.append(goffs[-1] + R * 4 * dims[l])
+    for i in range(levels):
+        q = f"{vn}context_blocks.{i}"
+        t = pb.layernorm(Xl, levels * R, D, q + ".norm1", 1e-5, adt, x0=X0, period=R, tag=q + ".norm1")
+        ow = pb.linear(t, levels * R, D, [q + ".attention_weights.weight", q + ".sampling_offsets.weight"],
+                       [q + ".attention_weights.bias", q + ".sampling_offsets.bias"], 48, out_dtype="f32", tag=q + ".ow")
+        g = pb._buf("deform_sampled", (goffs[-1],), adt)
+        rec = pb._buf("deform_corners", (levels, R, 16, 4), "i32") if (debug_records and i == 0) else None
+        if rec is not None:
+            rec.role = "output"
+            prog.outputs["deform_corners"] = rec
+        pb._emit(lib.OP_DEFORM_SAMPLE, maps[0].ref.dtype, adt, [B, J, levels] + map_geo + goffs[:4], [],
+                 [ref] + [m.ref for m in maps] + [ow], [g, rec], tag=q + ".sample")
+        for l in range(levels):
+            slab4 = X.view((1 + l) * R * D, (R * 4, D // 4), f"X[{1 + l}] as heads")
+            pb.linear(g.view(goffs[l], (R * 4, dims[l])), R * 4, dims[l], [f"{q}.embed_proj.{l}.weight"],
+                      [f"{q}.embed_proj.{l}.bias"], D // 4, residual=slab4, out=slab4, tag=f"{q}.embed_proj.{l}")
+        t = pb.layernorm(Xl, levels * R, D, q + ".norm2", 1e-5, adt, tag=q + ".norm2")
+        hdn = pb.linear(t, levels * R, D, [q + ".mlp.fc1.weight"], [q + ".mlp.fc1.bias"], 2 * D, act=arch.GELU, tag=q + ".mlp.fc1")
+        pb.linear(hdn, levels * R, 2 * D, [q + ".mlp.fc2.weight"], [q + ".mlp.fc2.bias"], D, residual=Xl, out=Xl, tag=q + ".mlp.fc2")
+
+    # ---- (a9) transformer blocks ---------------------------------------------------------------------------
+    def block(q, x: Buf, rows, dim, heads, groups, seq, tok_stride, grp_stride):
+        t = pb.layernorm(x, rows, dim, q + ".norm1", 1e-6, adt, tag=q + ".norm1")
+        qkv = pb.linear(t, rows, dim, [q + ".attn.qkv.weight"], [q + ".attn.qkv.bias"], 3 * dim, tag=q + ".attn.qkv")
+        att = pb._buf(q + ".attn", (rows, dim), adt)
+        hd = dim // heads
+        pb._emit(lib.OP_ATTENTION, adt, adt, [groups, seq, heads, hd, tok_stride, grp_stride], [float(hd) ** -0.5],
+                 [qkv], [att], tag=q + ".attn", flops=4 * groups * heads * seq * seq * hd)
+        pb.linear(att, rows, dim, [q + ".attn.proj.weight"], [q + ".attn.proj.bias"], dim, residual=x, out=x, tag=q + ".attn.proj")
+        t = pb.layernorm(x, rows, dim, q + ".norm2", 1e-6, adt, tag=q + ".norm2")
+        hdn = pb.linear(t, rows, dim, [q + ".mlp.fc1.weight"], [q + ".mlp.fc1.bias"], 2 * dim, act=arch.GELU, tag=q + ".mlp.fc1")
+        pb.linear(hdn, rows, 2 * dim, [q + ".mlp.fc2.weight"], [q + ".mlp.fc2.bias"], dim, residual=x, out=x, tag=q + ".mlp.fc2")
+
+    Xall = X.view(0, (S * R, D), "X[:]")
+    for i in range(levels):    # res_blocks: attention over the S level-tokens of one joint (:231-234)
+        block(f"{vn}res_blocks.{i}", Xall, S * R, D, 8, R, S, R, 1)
+    Y = pb._buf("Y", (R, E), "f32")
+    pb._emit(lib.OP_LEVELS_TO_JOINT, "f32", "f32", [R, S, D], [], [X], [Y], tag="levels_to_joint")
+    for i in range(levels):    # joint_blocks: attention over the 17 joints of a frame (:235-238)
+        block(f"{vn}joint_blocks.{i}", Y, R, E, 8, B, J, 1, J)
+
+    # ---- (a10) head ----------------------------------------------------------------------------------------
+    t = pb.layernorm(Y, R, E, vn + "head.0", 1e-5, adt, tag=vn + "head.0")
+    out = Buf("out", (R, 3), "f32", "output")
+    pb.linear(t, R, E, [vn + "head.1.weight"], [vn + "head.1.bias"], 3, out=out, tag=vn + "head.1")
+    prog.outputs["out"] = out
+    return prog
+
+
+# ------------------------------------------------------------------------------------------------------
+# memory planning: greedy reuse of dead activation buffers (exact-size pools)
+# ------------------------------------------------------------------------------------------------------
+def plan_memory(prog: Program):
+    """Returns (assignment: root Buf -> pool slot id, slots: list of (nbytes))."""
+    last_use = {}
+    for k, op in enumerate(prog.ops):
+        for b in list(op.ins) + list(op.outs):
+            if isinstance(b, Buf):
+                last_use[b.root] = k
+    keep_alive = {b.root for b in prog.inputs.values()} | {b.root for b in prog.outputs.values()}
+    assign, slots, free = {}, [], {}
+    for k, op in enumerate(prog.ops):
+        for b in op.outs:
+            if isinstance(b, Buf) and b.root not in assign:
+                r = b.root
+                pool = free.get(r.nbytes)
+                if pool and r not in keep_alive:
+                    assign[r] = pool.pop()
+                else:
+                    slots.append(r.nbytes)
+                    assign[r] = len(slots) - 1
+        for b in op.ins:
+            if isinstance(b, Buf) and b.root not in assign:   # program inputs
+                slots.append(b.root.nbytes)
+                assign[b.root] = len(slots) - 1
+        for b in set(x.root for x in list(op.ins) + list(op.outs) if isinstance(x, Buf)):
+            if last_use[b] == k and b not in keep_alive:
+                free.setdefault(b.nbytes, []).append(assign[b])
+    return assign, slots
+
+
+# ------------------------------------------------------------------------------------------------------
+# device plan
+# ------------------------------------------------------------------------------------------------------
+class BufferStore:
+    """Storage for every program buffer according to plan_memory (shared by Plan and tests/interp.py so the
+    CPU test-suite exercises the same aliasing the GPU sees)."""
+
+    def __init__(self, prog: Program, device):
+        self.assign, slots = plan_memory(prog)
+        self.slots = [torch.empty(max(n, 16), dtype=torch.uint8, device=device) for n in slots]
+        self.nbytes = sum(slots)
+
+    def tensor(self, b: Buf) -> torch.Tensor:
+        raw = self.slots[self.assign[b.root]]
+        it = _ITEMSIZE[b.dtype]
+        start = b.root_offset * it
+        return raw[start:start + b.numel * it].view(_TORCH_DT[b.dtype]).view(b.shape)
+
+    def ptr(self, b: Buf) -> int:
+        return self.slots[self.assign[b.root]].data_ptr() + b.root_offset * _ITEMSIZE[b.dtype]
+
+
+def weight_slots(prog: Program):
+    out = {}
+    for op in prog.ops:
+        for w in op.ins:
+            if isinstance(w, WSlot):
+                out.setdefault(id(w), w)
+    return out
+
+
+class Plan:
+    """A Program bound to device buffers and packed weights, executed through libcapf_b200."""
+
+    def __init__(self, prog: Program, state: dict, device):
+        import ctypes as C
+        self.prog = prog
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise lib.CapfError("Plan needs a CUDA device: libcapf_b200 has no CPU path")
+        L = lib.load()
+        self.mem = BufferStore(prog, self.device)
+        self.workspace_bytes = self.mem.nbytes
+        self._wslots = weight_slots(prog)
+        self._wtensors = {}
+        self.repack(state)
+        arr = (lib.CapfOp * len(prog.ops))()
+        for k, op in enumerate(prog.ops):
+            c = arr[k]
+            c.kind = op.kind
+            c.dtype_in = lib.DTYPE_CODE[op.dtype_in]
+            c.dtype_out = lib.DTYPE_CODE[op.dtype_out]
+            for n, v in enumerate(op.i):
+                c.i[n] = int(v)
+            for n, v in enumerate(op.f):
+                c.f[n] = float(v)
+            for n, b in enumerate(op.ins):
+                c.inp[n] = self._ptr(b)
+            for n, b in enumerate(op.outs):
+                c.out[n] = self._ptr(b)
+        self._ops = arr
+        h = C.c_void_p()
+        lib.check(L.capf_plan_create(arr, len(prog.ops), self.device.index or 0, C.byref(h)), "capf_plan_create")
+        self._h = h
+        self._L = L
+        self._graph = None
+
+    def _ptr(self, b):
+        if b is None:
+            return None
+        if isinstance(b, WSlot):
+            return self._wtensors[id(b)].data_ptr()
+        return self.mem.ptr(b)
+
+    def tensor(self, b: Buf) -> torch.Tensor:
+        """Typed torch view of a program buffer (inputs/outputs/feature maps)."""
+        return self.mem.tensor(b)
+
+    def repack(self, state):
+        """(Re)pack every weight blob from `state` into its fixed device tensor (pointers stay valid)."""
+        for k, w in self._wslots.items():
+            t = w.pack(state)
+            assert tuple(t.shape) == tuple(w.shape) or t.numel() == int(np.prod(w.shape)), (w.name, t.shape, w.shape)
+            if k in self._wtensors:
+                self._wtensors[k].copy_(t.reshape(self._wtensors[k].shape), non_blocking=False)
+            else:
+                self._wtensors[k] = t.to(self.device)
+
+    def run(self, first=0, count=-1, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        lib.check(self._L.capf_plan_run(self._h, first, count, s), "capf_plan_run")
+
+    @property
+    def num_launches(self):
+        return len(self.prog.ops)
+
+    # ---- CUDA graph ---------------------------------------------------------------------------------
+    def capture(self):
+        """Capture one full run into a CUDA graph (replayed by run_graph)."""
+        torch.cuda.synchronize(self.device)
+        side = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(side):
+            self.run()                      # warm-up outside capture (lazy module load, func attributes)
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            self.run(stream=side.cuda_stream)
+        self._graph = g
+        return g
+
+    def run_graph(self):
+        if self._graph is None:
+            self.capture()
+        self._graph.replay()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.capf_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -1,0 +1,171 @@
+/*
+ * capf_b200.h -- C ABI of libcapf_b200.so: the B200 (sm_100a) implementation of the
+ * ContextAware-PoseFormer single-frame lifting path  (CA_PF.forward, conpose.py:30-42).
+ *
+ * The reference exposes no FFI: all arithmetic is delegated to PyTorch (cuDNN / cuBLAS / ATen).
+ * This header is the boundary a maintainer binds instead (ctypes stub: see INTEGRATION.md and
+ * contextaware-poseformer_b200/lib.py).  Every entry point cites the reference call it replaces
+ * as  file:line  relative to /root/reference/ContextPose/mvn/models/.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every data pointer is a *device* pointer owned by the caller
+ *     (the PyTorch caching allocator in practice).  The library allocates no device memory.
+ *   - every call is asynchronous and ordered on the cudaStream_t passed as `void* stream`
+ *     (pass torch.cuda.current_stream().cuda_stream); all calls are CUDA-graph capturable.
+ *   - return value: 0 = ok, <0 = capf_status; capf_last_error() gives a thread-local message.
+ *     Nothing throws or exits across the ABI.
+ *   - activations are NHWC (channels innermost); token matrices are row-major [rows][cols].
+ *   - there is no CPU path: with no usable device every compute call returns CAPF_ERR_CUDA.
+ */
+#ifndef CAPF_B200_H_
+#define CAPF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAPF_ABI_VERSION 3
+
+typedef enum capf_status {
+  CAPF_OK = 0,
+  CAPF_ERR_ARG = -1,      /* bad shape / dtype / null pointer                       */
+  CAPF_ERR_UNSUPPORTED = -2, /* valid request, no kernel variant for it              */
+  CAPF_ERR_CUDA = -3      /* CUDA runtime / driver error (message has the detail)   */
+} capf_status;
+
+typedef enum capf_dtype { CAPF_F32 = 0, CAPF_F16 = 1, CAPF_BF16 = 2 } capf_dtype;
+
+typedef enum capf_act { CAPF_ACT_NONE = 0, CAPF_ACT_RELU = 1, CAPF_ACT_GELU = 2 } capf_act;
+
+/* Kernel family selector for CAPF_OP_CONV2D. */
+typedef enum capf_impl {
+  CAPF_IMPL_SIMT = 0,     /* fp32-accumulate CUDA-core implicit GEMM (any shape/dtype) */
+  CAPF_IMPL_TCGEN05 = 1   /* TMA -> smem -> tcgen05.mma (TMEM accumulators), f16/bf16  */
+} capf_impl;
+
+typedef enum capf_op_kind {
+  CAPF_OP_CONV2D = 1,
+  CAPF_OP_FUSE_SUM = 2,
+  CAPF_OP_MAXPOOL3X3S2 = 3,
+  CAPF_OP_BILINEAR = 4,
+  CAPF_OP_LAYERNORM = 5,
+  CAPF_OP_ATTENTION = 6,
+  CAPF_OP_REF_SAMPLE = 7,
+  CAPF_OP_DEFORM_SAMPLE = 8,
+  CAPF_OP_EMBED_COORD = 9,
+  CAPF_OP_LEVELS_TO_JOINT = 10,
+  CAPF_OP_CROP_NORMALIZE = 11,
+  CAPF_OP_CAST = 12
+} capf_op_kind;
+
+/*
+ * One step of a forward "program".  The Python host (program.py) emits a flat array of these from the
+ * reference's config keys (STAGE2..4, poseformer.*) and hands it to capf_plan_create().
+ * Field meaning per kind (unused fields must be 0 / NULL):
+ *
+ * CAPF_OP_CONV2D  -- nn.Conv2d(bias=False)+BatchNorm2d(eval) [+residual] [+ReLU]  (pose_hrnet.py:79-136,
+ *                    235-277, 382-408; networks/resnet.py:62-85; networks/refineNet.py:26-45) and
+ *                    nn.Linear [+GELU] [+residual] (pose_dformer.py:25-31,49,56,132,214,221,240) as a
+ *                    1x1 convolution over rows.
+ *     i[0..10] = N,H,W,Cin,Cout,KH,KW,stride,pad,Ho,Wo   i[11]=act  i[12]=impl
+ *     in[0]=x  [N,H,W,Cin]        dtype_in
+ *     in[1]=w  SIMT: [KH*KW*Cin][Cout] (tap-major rows, Cout contiguous); TCGEN05: [Cout][KH*KW*Cin];
+ *              dtype_in, except x f32 -> w f32.  BatchNorm scale is pre-folded into w by the host.
+ *     in[2]=bias[Cout] f32 (folded BN shift or Linear bias; may be NULL)
+ *     in[3]=residual [N,Ho,Wo,Cout] dtype_out or NULL (may alias out[0])
+ *     out[0]=y [N,Ho,Wo,Cout] dtype_out.    y = relu?( gelu?(conv+bias) + residual )
+ *
+ * CAPF_OP_FUSE_SUM -- HighResolutionModule fuse  y_i = ReLU(sum_j f_ij(x_j))  (pose_hrnet.py:294-301) with the
+ *                    nn.Upsample(mode='nearest') of the j>i terms (:244) applied on the fly.
+ *     i[0..3]=N,H,W,C  i[4]=n_terms(1..4)  i[5..8]=log2 upsample factor per term  i[9]=relu
+ *     in[t]=term t, [N,H>>s,W>>s,C] dtype_in (summed in order t=0,1,..)   out[0]=[N,H,W,C] dtype_out
+ *
+ * CAPF_OP_MAXPOOL3X3S2 -- nn.MaxPool2d(3,2,1) (networks/resnet.py:105).  i[0..5]=N,H,W,C,Ho,Wo
+ *
+ * CAPF_OP_BILINEAR -- nn.Upsample(mode='bilinear', align_corners=True) (networks/globalNet.py:40,
+ *                    networks/refineNet.py:61).   i[0..5]=N,H,W,C,Ho,Wo   in[0]=x  out[0]=y
+ *
+ * CAPF_OP_LAYERNORM -- nn.LayerNorm over the last dim (pose_dformer.py:65,72,120,138,206), optionally of
+ *                    (x + x0) with x0 broadcast every `period` rows (the `x + x_0` of :120).
+ *     i[0]=rows i[1]=D i[2]=period(0 = no x0)   f[0]=eps
+ *     in[0]=x [rows][D] f32  in[1]=gamma f32  in[2]=beta f32  in[3]=x0 [period][D] f32 or NULL
+ *     out[0]=y [rows][D] dtype_out
+ *
+ * CAPF_OP_ATTENTION -- Attention.forward softmax(q k^T * scale) v  (pose_dformer.py:47-55) for the two tiny
+ *                    sequence shapes of the model: 5 levels of one joint (:231-234) or 17 joints (:235-238).
+ *     i[0]=groups i[1]=seq(5|17) i[2]=heads i[3]=head_dim i[4]=token_stride_rows i[5]=group_stride_rows
+ *     f[0]=scale   in[0]=qkv [rows][3*heads*head_dim] dtype_in, columns ordered (3,heads,head_dim) (:49)
+ *     out[0]=[rows][heads*head_dim] dtype_out.  Row of token t of group g = g*group_stride + t*token_stride.
+ *
+ * CAPF_OP_REF_SAMPLE -- F.grid_sample(features, ref[B,17,1,2], bilinear, zeros, align_corners=True)
+ *                    (pose_dformer.py:216-218) on up to 4 NHWC maps.
+ *     i[0]=B i[1]=J i[2]=n_levels  i[3+3l..5+3l]=H_l,W_l,C_l
+ *     in[0]=ref [B*J][2] f32 (x,y in [-1,1])  in[1+l]=map l [B,H_l,W_l,C_l] dtype_in
+ *     out... see i/o below: out[0]=packed output base dtype_out; level l written at element offset i[15+l]
+ *     as a dense [B*J][C_l] matrix.   out[1] (optional, int32 [n_levels][B*J][4]) = x_nw, y_nw, valid-mask
+ *     (bit0 nw, bit1 ne, bit2 sw, bit3 se), 0 -- the integer part of the gather, exposed for bit-exact tests.
+ *
+ * CAPF_OP_DEFORM_SAMPLE -- DeformableBlock sampling (pose_dformer.py:122-135): softmax over the 4 samples of
+ *                    each head, tanh offsets + ref, F.grid_sample(..., padding_mode='border',
+ *                    align_corners=True), and the sample-weighted sum.  The sum is taken *before*
+ *                    embed_proj (legal: the weights sum to 1; changes rounding order only).
+ *     i[0]=B i[1]=J i[2]=n_levels i[3+3l..]=H_l,W_l,C_l  i[15+l]=element offset of level l in out[0]
+ *     in[0]=ref [B*J][2] f32   in[1+l]=map l dtype_in
+ *     in[5]=ow [n_levels*B*J][48] f32: cols 0..15 attention_weights logits (head*4+sample),
+ *           cols 16..47 sampling_offsets pre-tanh ((head*4+sample)*2+xy)
+ *     out[0]: level l = dense [B*J*4][C_l] dtype_out (row = (b*J+j)*4+head)
+ *     out[1] optional int32 [n_levels][B*J][16][4] corner record as above.
+ *
+ * CAPF_OP_EMBED_COORD -- coord_embed(kp2d) + Spatial_pos_embed[0], and Spatial_pos_embed[1+l] broadcast
+ *                    into the level slabs ready for the feat_embed GEMMs to accumulate onto
+ *                    (pose_dformer.py:214,223-225).   i[0]=B i[1]=J i[2]=D i[3]=n_slabs(=levels+1)
+ *     in[0]=kp2d [B*J][2] f32  in[1]=W [D][2] f32  in[2]=b [D] f32  in[3]=pos [n_slabs][J][D] f32
+ *     out[0]=X [n_slabs][B*J][D] f32 (level-major token stream)
+ *
+ * CAPF_OP_LEVELS_TO_JOINT -- rearrange '(b p) l c -> b p (l c)' (pose_dformer.py:235) from the level-major
+ *                    stream.  i[0]=rows(B*J) i[1]=n_slabs i[2]=D   in[0]=[n_slabs][rows][D] f32  out[0]=[rows][n_slabs*D] f32
+ *
+ * CAPF_OP_CROP_NORMALIZE -- keypoints_2d_cpn_crop /= (96,128); -= 1  in place (conpose.py:34-35).
+ *     i[0]=n_points   out[0]=crop [n][2] f32
+ *
+ * CAPF_OP_CAST -- dtype conversion of a dense array.  i[0],i[1]=element count (lo,hi 31-bit words) in[0] out[0]
+ */
+typedef struct capf_op {
+  int32_t kind;
+  int32_t dtype_in;
+  int32_t dtype_out;
+  int32_t reserved;
+  int32_t i[24];
+  float f[4];
+  const void* in[6];
+  void* out[2];
+} capf_op;
+
+typedef struct capf_plan capf_plan;
+
+/* Library / device ------------------------------------------------------------------------------------- */
+int capf_abi_version(void);
+const char* capf_last_error(void);
+/* SM count, cc major/minor, global memory bytes of `device` (out[4] as int64). */
+int capf_device_info(int device, int64_t* out4);
+
+/* Programs ---------------------------------------------------------------------------------------------- */
+/* Validates `ops`, selects kernel variants, encodes TMA descriptors for the pointers given.  Pointers are
+ * baked in: the host keeps every referenced buffer alive and at the same address for the plan's lifetime. */
+int capf_plan_create(const capf_op* ops, int n_ops, int device, capf_plan** out_plan);
+/* Enqueue ops [first, first+count) on `stream`; count < 0 means "to the end". */
+int capf_plan_run(const capf_plan* plan, int first, int count, void* stream);
+int capf_plan_num_launches(const capf_plan* plan);   /* kernels one full run enqueues */
+int capf_plan_destroy(capf_plan* plan);
+/* One-off execution of a single op (builds a throw-away plan): used by the per-operator parity tests. */
+int capf_op_run(const capf_op* op, int device, void* stream);
+
+/* Convenience wrappers over capf_op_run mirroring the reference call sites ------------------------------ */
+int capf_crop_normalize(float* crop_xy, int n_points, void* stream);          /* conpose.py:34-35 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPF_B200_H_ */

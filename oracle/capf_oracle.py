@@ -1,0 +1,298 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference lifting path (the parity oracle).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / --impl reference legs may import
+this module, and only as the checker / reported baseline.  The product (contextaware-poseformer_b200) never does.
+
+What is restated: ``CA_PF.forward`` of /root/reference/ContextPose/mvn/models/conpose.py:30-42 and everything
+under it, as plain functions over a ``state_dict`` (fp32, torch-CPU arithmetic = the same ATen kernels the
+reference itself calls; the reference has no native code of its own).  Each function cites
+the reference lines it follows.  The bilinear gather is additionally restated element-by-element in numpy
+(``grid_sample_records``) so that the *integer* part of the sampler (corner indices, in-bounds masks) can be
+compared bit-exactly with the CUDA kernels.
+
+Pinning: the reference ships no tests or golden vectors, so this oracle is pinned to
+outputs of the *reference itself* run in the authoring container: ``oracle/gen_golden.py`` imports the
+unmodified reference, feeds it the seeded protocol of ``oracle/protocol.py`` and commits the results under
+``tests/golden/``; ``tests/test_oracle.py`` checks this file against them (and against the live reference when
+/root/reference is present).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------
+# building blocks
+# ------------------------------------------------------------------------------------------------------
+def conv_bn(sd, x, conv, bn, stride=1, relu=False):
+    """nn.Conv2d(bias=False) -> nn.BatchNorm2d in eval mode [-> ReLU] (e.g. pose_hrnet.py:82-84)."""
+    w = sd[conv + ".weight"]
+    y = F.conv2d(x, w, None, stride, w.shape[-1] // 2)
+    y = F.batch_norm(y, sd[bn + ".running_mean"], sd[bn + ".running_var"], sd[bn + ".weight"], sd[bn + ".bias"],
+                     False, 0.0, BN_EPS)
+    return F.relu(y) if relu else y
+
+
+def basic_block(sd, x, p):
+    """BasicBlock.forward, pose_hrnet.py:79-95 (no downsample inside HRNet branches)."""
+    y = conv_bn(sd, x, p + ".conv1", p + ".bn1", relu=True)
+    y = conv_bn(sd, y, p + ".conv2", p + ".bn2")
+    return F.relu(y + x)
+
+
+def bottleneck(sd, x, p, stride=1, expansion_conv3=True):
+    """Bottleneck.forward, pose_hrnet.py:116-136 / networks/resnet.py:73-93 / networks/refineNet.py:26-45."""
+    y = conv_bn(sd, x, p + ".conv1", p + ".bn1", relu=True)
+    y = conv_bn(sd, y, p + ".conv2", p + ".bn2", stride=stride, relu=True)
+    y = conv_bn(sd, y, p + ".conv3", p + ".bn3")
+    r = x
+    if (p + ".downsample.0.weight") in sd:
+        r = conv_bn(sd, x, p + ".downsample.0", p + ".downsample.1", stride=stride)
+    return F.relu(y + r)
+
+
+# ------------------------------------------------------------------------------------------------------
+# HRNet (pose_hrnet.py)
+# ------------------------------------------------------------------------------------------------------
+def _hr_module(sd, xs, p, n_br, n_blocks, multi_scale_output):
+    """HighResolutionModule.forward, pose_hrnet.py:285-303.  Returns (branch outputs, fused outputs)."""
+    br = []
+    for i in range(n_br):
+        t = xs[i]
+        for b in range(n_blocks[i]):
+            t = basic_block(sd, t, f"{p}.branches.{i}.{b}")
+        br.append(t)
+    fused = []
+    for i in range(n_br if multi_scale_output else 1):
+        y = None
+        for j in range(n_br):
+            f = f"{p}.fuse_layers.{i}.{j}"
+            if j == i:
+                t = br[j]
+            elif j > i:     # 1x1 conv + BN + nearest upsample (:235-246)
+                t = conv_bn(sd, br[j], f + ".0", f + ".1")
+                t = F.interpolate(t, scale_factor=2 ** (j - i), mode="nearest")
+            else:           # chain of stride-2 3x3 convs, ReLU on all but the last (:250-277)
+                t = br[j]
+                for k in range(i - j):
+                    t = conv_bn(sd, t, f"{f}.{k}.0", f"{f}.{k}.1", stride=2, relu=(k != i - j - 1))
+            y = t if y is None else y + t
+        fused.append(F.relu(y))
+    return br, fused
+
+
+def hrnet_forward(sd, x, cfg, prefix="backbone."):
+    """PoseHighResolutionNet.forward, pose_hrnet.py:464-501.  x: [B,3,H,W] -> 4 NCHW maps.
+
+    Levels 1..3 are the *branch outputs of stage4's first module before fusion*: the module overwrites the list it
+    is given (:289-290) and forward returns entries of that same list (:501)."""
+    S = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    x = conv_bn(S, x, "conv1", "bn1", stride=2, relu=True)
+    x = conv_bn(S, x, "conv2", "bn2", stride=2, relu=True)
+    for b in range(4):
+        x = bottleneck(S, x, f"layer1.{b}")
+    ys = [x]
+    kept = None
+    for si, key in enumerate(("STAGE2", "STAGE3", "STAGE4")):
+        st = cfg[key]
+        n_br, chans = st["NUM_BRANCHES"], st["NUM_CHANNELS"]
+        xs = []
+        for i in range(n_br):       # transitions (:372-411; applied in forward :473-495)
+            tn = f"transition{si + 1}.{i}"
+            if (tn + ".0.weight") in S:                       # same-resolution 3x3 conv
+                xs.append(conv_bn(S, ys[-1], tn + ".0", tn + ".1", relu=True))
+            elif (tn + ".0.0.weight") in S:                   # new branch: stride-2 chain from the last map
+                t = ys[-1]
+                j = 0
+                while (f"{tn}.{j}.0.weight") in S:
+                    t = conv_bn(S, t, f"{tn}.{j}.0", f"{tn}.{j}.1", stride=2, relu=True)
+                    j += 1
+                xs.append(t)
+            else:
+                xs.append(ys[i])
+        for m in range(st["NUM_MODULES"]):
+            multi = not (key == "STAGE4" and m == st["NUM_MODULES"] - 1)
+            br, xs = _hr_module(S, xs, f"stage{si + 2}.{m}", n_br, st["NUM_BLOCKS"], multi)
+            if key == "STAGE4" and m == 0:
+                kept = br
+        ys = xs
+    return [ys[0], kept[1], kept[2], kept[3]]
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPN-50 (networks/*.py)
+# ------------------------------------------------------------------------------------------------------
+def cpn_forward(sd, x, output_shape=(64, 48), prefix="backbone."):
+    """CPN.forward, networks/network.py:16-22 -> 4 maps [B,256,64,48]."""
+    S = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    # ResNet.forward, networks/resnet.py:136-147
+    x = conv_bn(S, x, "resnet.conv1", "resnet.bn1", stride=2, relu=True)
+    x = F.max_pool2d(x, 3, 2, 1)
+    feats = []
+    for li, (blocks, stride) in enumerate(((3, 1), (4, 2), (6, 2), (3, 2))):
+        for b in range(blocks):
+            x = bottleneck(S, x, f"resnet.layer{li + 1}.{b}", stride=stride if b == 0 else 1)
+        feats.append(x)
+    res_out = feats[::-1]
+    # globalNet.forward, networks/globalNet.py:61-83 (predict heads are computed and discarded there: skipped)
+    fms, up = [], None
+    for i in range(4):
+        lat = conv_bn(S, res_out[i], f"global_net.laterals.{i}.0", f"global_net.laterals.{i}.1", relu=True)
+        feature = lat if i == 0 else lat + up
+        fms.append(feature)
+        if i != 3:
+            u = F.interpolate(feature, scale_factor=2, mode="bilinear", align_corners=True)
+            up = conv_bn(S, u, f"global_net.upsamples.{i}.1", f"global_net.upsamples.{i}.2")
+    # refineNet.forward, networks/refineNet.py:72-88
+    outs = []
+    for i in range(4):
+        t = fms[i]
+        for k in range(3 - i):
+            t = bottleneck(S, t, f"refine_net.cascade.{i}.{k}")
+        outs.append(F.interpolate(t, size=tuple(output_shape), mode="bilinear", align_corners=True))
+    return outs
+
+
+# ------------------------------------------------------------------------------------------------------
+# bilinear gather, restated element-wise (ATen/native/GridSampler.h:27-36 + cuda/GridSampler.cu bilinear branch)
+# ------------------------------------------------------------------------------------------------------
+def grid_sample_records(grid_xy: np.ndarray, H: int, W: int, border: bool):
+    """grid_xy [...,2] f32 in normalised coords -> (x_nw, y_nw int32, mask uint8 bit0..3 = nw,ne,sw,se in-bounds,
+    weights [...,4] f32).  align_corners=True.  All arithmetic in float32, one rounding per operation."""
+    f = np.float32
+    g = grid_xy.astype(np.float32)
+    ix = ((g[..., 0] + f(1)) / f(2)) * f(W - 1)
+    iy = ((g[..., 1] + f(1)) / f(2)) * f(H - 1)
+    if border:     # clip_coordinates
+        ix = np.minimum(f(W - 1), np.maximum(ix, f(0)))
+        iy = np.minimum(f(H - 1), np.maximum(iy, f(0)))
+    fx, fy = np.floor(ix), np.floor(iy)
+    x1, y1 = fx + f(1), fy + f(1)
+    w = np.stack([(x1 - ix) * (y1 - iy), (ix - fx) * (y1 - iy), (x1 - ix) * (iy - fy), (ix - fx) * (iy - fy)], -1).astype(np.float32)
+    x0 = np.clip(fx, -1e6, 1e6).astype(np.int32)
+    y0 = np.clip(fy, -1e6, 1e6).astype(np.int32)
+    xl, xr = (x0 >= 0) & (x0 < W), (x0 + 1 >= 0) & (x0 + 1 < W)
+    yt, yb = (y0 >= 0) & (y0 < H), (y0 + 1 >= 0) & (y0 + 1 < H)
+    mask = (xl & yt).astype(np.uint8) | ((xr & yt).astype(np.uint8) << 1) | ((xl & yb).astype(np.uint8) << 2) | ((xr & yb).astype(np.uint8) << 3)
+    return x0, y0, mask, w
+
+
+def grid_sample_gather(feat_nchw: torch.Tensor, grid_xy: np.ndarray, border: bool):
+    """Pure-numpy bilinear gather for feat [B,C,H,W] and grid [B,P,2] -> [B,P,C] (used on small cases to pin
+    F.grid_sample and the CUDA samplers to the same corner set)."""
+    B, C, H, W = feat_nchw.shape
+    x0, y0, mask, w = grid_sample_records(grid_xy, H, W, border)
+    fm = feat_nchw.numpy()
+    out = np.zeros(grid_xy.shape[:-1] + (C,), np.float32)
+    for k, (dx, dy) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
+        ok = (mask >> k) & 1
+        xx = np.clip(x0 + dx, 0, W - 1)
+        yy = np.clip(y0 + dy, 0, H - 1)
+        b_idx = np.arange(B).reshape(B, *([1] * (x0.ndim - 1)))
+        vals = fm[b_idx, :, yy, xx]                       # [..., C]
+        out = out + (vals * w[..., k:k + 1]).astype(np.float32) * ok[..., None].astype(np.float32)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# PoseTransformer (pose_dformer.py)
+# ------------------------------------------------------------------------------------------------------
+def _lin(sd, x, p):
+    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
+
+
+def _ln(sd, x, p, eps):
+    return F.layer_norm(x, x.shape[-1:], sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+def _mlp(sd, x, p):
+    """Mlp.forward, pose_dformer.py:25-31 (dropout p=0)."""
+    return _lin(sd, F.gelu(_lin(sd, x, p + ".fc1")), p + ".fc2")
+
+
+def _attention(sd, x, p, heads):
+    """Attention.forward, pose_dformer.py:47-59."""
+    B, N, C = x.shape
+    qkv = _lin(sd, x, p + ".qkv").reshape(B, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    a = (q @ k.transpose(-2, -1)) * ((C // heads) ** -0.5)
+    a = a.softmax(dim=-1)
+    return _lin(sd, (a @ v).transpose(1, 2).reshape(B, N, C), p + ".proj")
+
+
+def _block(sd, x, p, heads=8):
+    """Block.forward, pose_dformer.py:76-79 with LayerNorm eps 1e-6 (:166); DropPath is identity in eval."""
+    x = x + _attention(sd, _ln(sd, x, p + ".norm1", 1e-6), p + ".attn", heads)
+    return x + _mlp(sd, _ln(sd, x, p + ".norm2", 1e-6), p + ".mlp")
+
+
+def _context_block(sd, x, ref, feats, p, heads=4, samples=4):
+    """DeformableBlock.forward, pose_dformer.py:115-141 (LayerNorm eps 1e-5: default nn.LayerNorm, :89,:95)."""
+    x0, xl = x[:, :1], x[:, 1:]
+    b, l, pj, c = xl.shape
+    t = _ln(sd, xl + x0, p + ".norm1", 1e-5)
+    w = _lin(sd, t, p + ".attention_weights").view(b, l, pj, heads, samples).softmax(-1).unsqueeze(-1)
+    off = _lin(sd, t, p + ".sampling_offsets").reshape(b, l, pj, heads * samples, 2).tanh()
+    pos = off + ref.view(b, 1, pj, 1, -1)
+    sampled = []
+    for idx, fm in enumerate(feats):
+        s = F.grid_sample(fm, pos[:, idx], padding_mode="border", align_corners=True).permute(0, 2, 3, 1)
+        sampled.append(_lin(sd, s, f"{p}.embed_proj.{idx}"))
+    s = torch.stack(sampled, 1)
+    s = (w * s.view(b, l, pj, heads, samples, -1)).sum(-2).view(b, l, pj, -1)
+    xl = xl + s
+    xl = xl + _mlp(sd, _ln(sd, xl, p + ".norm2", 1e-5), p + ".mlp")
+    return torch.cat([x0, xl], 1), pos
+
+
+def lifter_forward(sd, kp2d, ref, feats, levels=4, prefix="volume_net.", trace=None):
+    """PoseTransformer.forward, pose_dformer.py:210-241.  kp2d, ref: [B,17,2]; feats: 4 NCHW maps -> [B,1,17,3]."""
+    S = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    b, p, _ = kp2d.shape
+    x = _lin(S, kp2d, "coord_embed")
+    fr = [F.grid_sample(fm, ref.unsqueeze(-2), align_corners=True).squeeze(-1).permute(0, 2, 1) for fm in feats]
+    fr = [_lin(S, fr[i], f"feat_embed.{i}") for i in range(len(feats))]
+    x = torch.stack([x, *fr], 1) + S["Spatial_pos_embed"]
+    if trace is not None:
+        trace["tokens_embed"] = x.clone()
+    for i in range(levels):
+        x, pos = _context_block(S, x, ref, feats, f"context_blocks.{i}")
+        if trace is not None and i == 0:
+            trace["deform_pos0"] = pos.clone()
+    if trace is not None:
+        trace["tokens_context"] = x.clone()
+    x = x.permute(0, 2, 1, 3).reshape(b * p, levels + 1, -1)          # 'b l p c -> (b p) l c'
+    for i in range(levels):
+        x = _block(S, x, f"res_blocks.{i}")
+    if trace is not None:
+        trace["tokens_res"] = x.clone()
+    x = x.reshape(b, p, -1)                                           # '(b p) l c -> b p (l c)'
+    for i in range(levels):
+        x = _block(S, x, f"joint_blocks.{i}")
+    if trace is not None:
+        trace["tokens_joint"] = x.clone()
+    x = _lin(S, _ln(S, x, "head.0", 1e-5), "head.1")
+    return x.view(b, 1, p, -1)
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole path
+# ------------------------------------------------------------------------------------------------------
+def normalize_crop_(crop: torch.Tensor):
+    """conpose.py:34-35, in place on the caller's tensor (hard-coded 192x256 crop)."""
+    crop[..., :2] /= torch.tensor([192 // 2, 256 // 2], device=crop.device)
+    crop[..., :2] -= torch.tensor([1, 1], device=crop.device)
+    return crop
+
+
+def ca_pf_forward(sd, backbone, bb_cfg, images, kp2d, crop, trace=None):
+    """CA_PF.forward, conpose.py:30-42.  images [B,H,W,3]; mutates `crop` like the reference.  fp32."""
+    with torch.no_grad():
+        x = images.permute(0, 3, 1, 2).contiguous()
+        ref = normalize_crop_(crop)
+        feats = cpn_forward(sd, x) if backbone == "cpn" else hrnet_forward(sd, x, bb_cfg)
+        if trace is not None:
+            trace["features"] = feats
+        return lifter_forward(sd, kp2d, ref, feats, trace=trace)

@@ -1,0 +1,163 @@
+"""TEST-ONLY reference interpreter for ``Program``s (torch-CPU semantics of every op in include/capf_b200.h).
+
+It executes exactly the op list, packed weights and *memory plan* the GPU executes, so the CPU suite can prove
+host logic (graph construction, BN folding, weight layouts, buffer aliasing) against the oracle without a GPU.
+It is not part of the product and is never imported by it.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from capf_b200 import lib, program
+from capf_b200.program import Buf, WSlot
+
+import capf_oracle
+
+
+class Interp:
+    def __init__(self, prog, state):
+        self.prog = prog
+        self.mem = program.BufferStore(prog, "cpu")
+        self.w = {k: w.pack(state) for k, w in program.weight_slots(prog).items()}
+
+    def t(self, b):
+        if b is None:
+            return None
+        if isinstance(b, WSlot):
+            return self.w[id(b)]
+        return self.mem.tensor(b)
+
+    def run(self):
+        for op in self.prog.ops:
+            getattr(self, "_op%d" % op.kind)(op)
+
+    # ---- ops -------------------------------------------------------------------------------------------
+    def _op1(self, op):   # CONV2D
+        N, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, act, impl = op.i[:13]
+        x = self.t(op.ins[0]).reshape(N, H, W, Cin).float().permute(0, 3, 1, 2)
+        w = self.t(op.ins[1]).float()
+        if impl == lib.IMPL_TCGEN05:
+            w = w.reshape(Cout, KH, KW, Cin).permute(0, 3, 1, 2)
+        else:
+            w = w.reshape(KH, KW, Cin, Cout).permute(3, 2, 0, 1)
+        y = F.conv2d(x, w.contiguous(), None, stride, pad).permute(0, 2, 3, 1)
+        if op.ins[2] is not None:
+            y = y + self.t(op.ins[2])
+        if act == lib.ACT_GELU:
+            y = F.gelu(y)
+        if op.ins[3] is not None:
+            y = y + self.t(op.ins[3]).reshape(N, Ho, Wo, Cout).float()
+        if act == lib.ACT_RELU:
+            y = F.relu(y)
+        out = self.t(op.outs[0])
+        out.copy_(y.reshape(out.shape).to(out.dtype))
+
+    def _op2(self, op):   # FUSE_SUM
+        N, H, W, C, nt = op.i[:5]
+        acc = None
+        for k in range(nt):
+            s = op.i[5 + k]
+            t = self.t(op.ins[k]).reshape(N, H >> s, W >> s, C).float()
+            if s:
+                t = t.repeat_interleave(1 << s, 1).repeat_interleave(1 << s, 2)
+            acc = t if acc is None else acc + t
+        if op.i[9]:
+            acc = F.relu(acc)
+        out = self.t(op.outs[0])
+        out.copy_(acc.to(out.dtype))
+
+    def _op3(self, op):   # MAXPOOL
+        N, H, W, C, Ho, Wo = op.i[:6]
+        x = self.t(op.ins[0]).float().permute(0, 3, 1, 2)
+        out = self.t(op.outs[0])
+        out.copy_(F.max_pool2d(x, 3, 2, 1).permute(0, 2, 3, 1).to(out.dtype))
+
+    def _op4(self, op):   # BILINEAR
+        N, H, W, C, Ho, Wo = op.i[:6]
+        x = self.t(op.ins[0]).float().permute(0, 3, 1, 2)
+        out = self.t(op.outs[0])
+        out.copy_(F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1).to(out.dtype))
+
+    def _op5(self, op):   # LAYERNORM
+        rows, D, period = op.i[:3]
+        x = self.t(op.ins[0]).reshape(rows, D)
+        if period:
+            x = x + self.t(op.ins[3]).reshape(period, D).repeat(rows // period, 1)
+        y = F.layer_norm(x, (D,), self.t(op.ins[1]), self.t(op.ins[2]), op.f[0])
+        out = self.t(op.outs[0])
+        out.copy_(y.to(out.dtype))
+
+    def _op6(self, op):   # ATTENTION
+        groups, seq, heads, hd, ts, gs = op.i[:6]
+        D = heads * hd
+        qkv = self.t(op.ins[0]).float()
+        rows = (torch.arange(groups).view(-1, 1) * gs + torch.arange(seq).view(1, -1) * ts)      # [G, seq]
+        x = qkv[rows.reshape(-1)].view(groups, seq, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        a = ((x[0] @ x[1].transpose(-2, -1)) * op.f[0]).softmax(-1)
+        y = (a @ x[2]).transpose(1, 2).reshape(groups * seq, D)
+        out = self.t(op.outs[0])
+        out[rows.reshape(-1)] = y.to(out.dtype)
+
+    def _maps(self, op):
+        B, Jn, nl = op.i[:3]
+        geo = [(op.i[3 + 3 * l], op.i[4 + 3 * l], op.i[5 + 3 * l]) for l in range(nl)]
+        maps = [self.t(op.ins[1 + l]).float().permute(0, 3, 1, 2) for l in range(nl)]
+        return B, Jn, nl, geo, maps, [op.i[15 + l] for l in range(nl)]
+
+    def _op7(self, op):   # REF_SAMPLE
+        B, Jn, nl, geo, maps, offs = self._maps(op)
+        ref = self.t(op.ins[0]).view(B, Jn, 2)
+        out = self.t(op.outs[0])
+        for l in range(nl):
+            s = F.grid_sample(maps[l], ref.unsqueeze(-2), align_corners=True).squeeze(-1).permute(0, 2, 1)
+            C = geo[l][2]
+            out[offs[l]:offs[l] + B * Jn * C] = s.reshape(-1).to(out.dtype)
+            if op.outs[1] is not None:
+                x0, y0, m, _ = capf_oracle.grid_sample_records(ref.numpy(), geo[l][0], geo[l][1], border=False)
+                rec = self.t(op.outs[1])
+                rec[l, :, 0] = torch.from_numpy(x0.reshape(-1))
+                rec[l, :, 1] = torch.from_numpy(y0.reshape(-1))
+                rec[l, :, 2] = torch.from_numpy(m.reshape(-1).astype(np.int32))
+                rec[l, :, 3] = 0
+
+    def _op8(self, op):   # DEFORM_SAMPLE
+        B, Jn, nl, geo, maps, offs = self._maps(op)
+        R = B * Jn
+        ref = self.t(op.ins[0]).view(B, 1, Jn, 1, 2)
+        ow = self.t(op.ins[5]).view(nl, B, Jn, 48)
+        wts = ow[..., :16].reshape(nl, B, Jn, 4, 4).softmax(-1)
+        pos = ow[..., 16:].reshape(nl, B, Jn, 16, 2).tanh().permute(1, 0, 2, 3, 4) + ref      # [B,nl,J,16,2]
+        out = self.t(op.outs[0])
+        for l in range(nl):
+            C = geo[l][2]
+            s = F.grid_sample(maps[l], pos[:, l], padding_mode="border", align_corners=True).permute(0, 2, 3, 1)  # [B,J,16,C]
+            g = (s.reshape(B, Jn, 4, 4, C) * wts[l].unsqueeze(-1)).sum(-2)                                      # [B,J,4,C]
+            out[offs[l]:offs[l] + R * 4 * C] = g.reshape(-1).to(out.dtype)
+            if op.outs[1] is not None:
+                x0, y0, m, _ = capf_oracle.grid_sample_records(pos[:, l].numpy(), geo[l][0], geo[l][1], border=True)
+                rec = self.t(op.outs[1])
+                rec[l, :, :, 0] = torch.from_numpy(x0.reshape(R, 16))
+                rec[l, :, :, 1] = torch.from_numpy(y0.reshape(R, 16))
+                rec[l, :, :, 2] = torch.from_numpy(m.reshape(R, 16).astype(np.int32))
+                rec[l, :, :, 3] = 0
+
+    def _op9(self, op):   # EMBED_COORD
+        B, Jn, D, S = op.i[:4]
+        kp = self.t(op.ins[0]).view(B * Jn, 2)
+        W, b, pos = self.t(op.ins[1]).view(D, 2), self.t(op.ins[2]), self.t(op.ins[3]).view(S, Jn, D)
+        X = self.t(op.outs[0])
+        X.copy_(pos.unsqueeze(1).expand(S, B, Jn, D).reshape(S, B * Jn, D))
+        X[0] += F.linear(kp, W, b)
+
+    def _op10(self, op):  # LEVELS_TO_JOINT
+        R, S, D = op.i[:3]
+        self.t(op.outs[0]).copy_(self.t(op.ins[0]).view(S, R, D).permute(1, 0, 2).reshape(R, S * D))
+
+    def _op11(self, op):  # CROP_NORMALIZE
+        c = self.t(op.outs[0]).view(-1, 2)
+        c /= torch.tensor([96.0, 128.0])
+        c -= 1.0
+
+    def _op12(self, op):  # CAST
+        out = self.t(op.outs[0])
+        out.copy_(self.t(op.ins[0]).to(out.dtype))
