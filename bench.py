@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the CA_PF lifting path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5                 # this arm (libcapf_b200)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W                  # N GPUs, one rank per GPU, NCCL
+  python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # the reference's CPU forward (oracle port)
+
+A step is one CA_PF.forward over one batch of synthetic input.  Workload at N=1 = BASELINE.json configs[1]:
+HRNet-32 + 4-level PoseFormer, 17 joints, bs=256, 256x256, fp16 storage / fp32 accumulate.  With N GPUs every rank
+runs its own 256-frame shard (frames are independent, weak scaling) and the step ends with the NCCL all-gather of
+the [256,1,17,3] outputs -- the only collective of the path (reference train.py:216-226).
+
+One JSON line on stdout (rank 0).  `value`: device-resident inputs, CUDA-graph replay, CUDA events, max over ranks.
+`e2e`: same metric through the public API with pinned HOST inputs: H2D copies + D2H of the result inside the timed
+region.  `roofline`: the dominant kernel family (conv / linear implicit GEMM) -- algorithmic FLOPs of its launches
+divided by their summed device time (per-op CUDA events on the launching stream, one in-order pass), against the
+measured bf16 tensor peak of MEASURED_PEAKS.json.  `cpu_baseline`: the oracle (CPU restatement of the reference,
+kind "port") timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "frames/sec (17-joint, 256x256, bs=256)"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx = float(c[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(backbone, precision, device, graph):
+    import capf_b200
+    cfg = capf_b200.make_config(backbone)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = capf_b200.CA_PF(cfg, precision=precision, use_cuda_graph=graph).eval()
+    w = capf_b200.synth.make_weights([(k, tuple(v.shape)) for k, v in model.state_dict().items()], 0)
+    model.load_state_dict(w, strict=True)
+    return model.to(device), w, cfg
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU forward (oracle port) on this box's host cores
+# ------------------------------------------------------------------------------------------------------
+def time_cpu_reference(backbone, H, W, sample_frames, steps, warmup, threads=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import capf_b200
+    import capf_oracle
+    threads = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    cfg = capf_b200.make_config(backbone)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = capf_b200.CA_PF(cfg)
+    w = capf_b200.synth.make_weights([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 0)
+    images, kp2d, crop = capf_b200.synth.make_inputs(sample_frames, H, W, 1234)
+    times = []
+    for it in range(warmup + steps):
+        c = crop.clone()
+        t0 = time.perf_counter()
+        capf_oracle.ca_pf_forward(w, backbone, cfg.model.backbone, images, kp2d, c)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.ref_sample
+    times, threads = time_cpu_reference(args.backbone, args.height, args.width, sample, args.steps, args.warmup)
+    total = sum(times)
+    fps = sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.backbone} + 4-level PoseFormer, 17 joints, bs={args.batch}, {args.height}x{args.width}",
+                   "sample": f"{sample} frames per step"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"oracle/capf_oracle.py (CPU restatement of the reference forward, torch-CPU fp32), "
+                                   f"{sample}-frame batches of the same workload, {len(times)} timed steps, all host threads"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# this arm
+# ------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch.distributed as dist
+    import capf_b200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libcapf_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, H, W = args.batch, args.height, args.width
+    model, weights, cfg = build_model(args.backbone, args.precision, dev, graph=not args.no_graph)
+    images, kp2d, crop = capf_b200.synth.make_inputs(B, H, W, 1234 + rank)
+    static = model.static_inputs(B, H, W, dev)
+    plan = model.plan_for(B, H, W, dev)
+    gather = capf_b200.dist.OutputGatherer([B] * world, (1, 17, 3), dev) if world > 1 else None
+
+    static["images"].copy_(images.to(dev))
+    kp_d, crop_pristine = kp2d.to(dev), crop.to(dev)
+    crop_work = crop_pristine.clone()
+
+    def step_resident():
+        crop_work.copy_(crop_pristine)                 # forward normalises it in place (conpose.py:34-35)
+        out = model(static["images"], kp_d, crop_work)
+        return gather(out) if gather is not None else out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = step_resident()
+        barrier()
+        # ---- timed region 1: device-resident inputs ------------------------------------------------------
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = step_resident()
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = e0.elapsed_time(e1)
+
+        # ---- timed region 2: end to end from pinned host memory ------------------------------------------
+        h_img, h_kp, h_crop = images.pin_memory(), kp2d.pin_memory(), crop.pin_memory()
+        h_out = torch.empty(B, 1, 17, 3).pin_memory()
+        copy_stream = torch.cuda.Stream(dev)
+        stage = [dict(kp=torch.empty_like(kp_d), crop=torch.empty_like(crop_work), img=torch.empty_like(static["images"]),
+                      ev=torch.cuda.Event()) for _ in range(2)]
+
+        def upload(slot):
+            with torch.cuda.stream(copy_stream):
+                s = stage[slot]
+                s["img"].copy_(h_img, non_blocking=True)
+                s["kp"].copy_(h_kp, non_blocking=True)
+                s["crop"].copy_(h_crop, non_blocking=True)
+                s["ev"].record(copy_stream)
+
+        def e2e_loop(n):
+            upload(0)
+            for i in range(n):
+                s = stage[i & 1]
+                torch.cuda.current_stream(dev).wait_event(s["ev"])
+                o = model(s["img"], s["kp"], s["crop"])
+                if i + 1 < n:
+                    copy_stream.wait_stream(torch.cuda.current_stream(dev))   # do not overwrite a slot still being read
+                    upload((i + 1) & 1)
+                if gather is not None:
+                    o = gather(o)[rank * B:(rank + 1) * B]
+                h_out.copy_(o, non_blocking=False)                            # D2H of the step's result (synchronises)
+            return h_out
+
+        e2e_loop(2)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        e2e_loop(args.steps)
+        t1.record()
+        barrier()
+        ms_e2e = t0.elapsed_time(t1)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = t.tolist()
+
+    frames = B * world * args.steps
+    value = frames / (ms_total / 1e3)
+    e2e_value = frames / (ms_e2e / 1e3)
+    h2d = h_img.numel() * 4 + h_kp.numel() * 4 + h_crop.numel() * 4
+    d2h = h_out.numel() * 4
+
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        # ---- roofline of the dominant kernel family (live per-op timing) -----------------------------------
+        with torch.no_grad():
+            op_ms = plan.time_ops(passes=2)
+        fam = {}
+        for op, ms in zip(plan.prog.ops, op_ms):
+            if op.kind == capf_b200.lib.OP_CONV2D:
+                name = "conv/linear implicit GEMM (tcgen05)" if op.i[12] == capf_b200.lib.IMPL_TCGEN05 else "conv/linear implicit GEMM (SIMT fp32-accumulate)"
+            else:
+                name = {2: "fuse_sum", 5: "layernorm", 6: "attention", 7: "ref_sample", 8: "deform_sample"}.get(op.kind, "other")
+            d = fam.setdefault(name, {"ms": 0.0, "flops": 0, "launches": 0})
+            d["ms"] += ms
+            d["flops"] += op.flops
+            d["launches"] += 1
+        dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        dom_tflops = dom[1]["flops"] / (dom[1]["ms"] * 1e-3) / 1e12
+        peak_tf = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
+        qkv = [(op, ms) for op, ms in zip(plan.prog.ops, op_ms) if "joint_blocks" in op.tag and op.tag.endswith("attn.qkv")]
+        qkv_tf = sum(o.flops for o, _ in qkv) / (sum(m for _, m in qkv) * 1e-3) / 1e12 if qkv else None
+        step_ms_sum = sum(op_ms)
+        roofline = {
+            "bound": "tensor", "kernel": dom[0], "achieved": dom_tflops, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": dom_tflops / peak_tf, "traffic": None, "peak_source": f"{peaks['_source']} bf16_tflops_sustained",
+            "launches_per_step": dom[1]["launches"], "flops_per_step": dom[1]["flops"],
+            "kernel_ms_per_step": dom[1]["ms"], "share_of_step": dom[1]["ms"] / step_ms_sum,
+            "qkv_gemm": {"achieved": qkv_tf, "peak": peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]), "unit": "TFLOP/s",
+                         "frac": (qkv_tf / peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"])) if qkv_tf else None,
+                         "shape": f"M={B * 17} K=640 N=1920 x4 blocks"},
+            "whole_step": {"achieved": plan.prog.flops() / (ms_total / args.steps * 1e-3) / 1e12, "unit": "TFLOP/s",
+                           "flops_per_frame": plan.prog.flops() / B},
+            "families_ms": {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+        }
+        # ---- MPJPE vs reference on a small slice (parity carried with the number) ---------------------------
+        cpu_base, parity = None, None
+        if world == 1 and not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import capf_oracle
+            n = args.cpu_sample
+            times, threads = time_cpu_reference(args.backbone, H, W, n, args.cpu_steps, 1)
+            fps_cpu = n * len(times) / sum(times)
+            cpu_base = {"value": fps_cpu, "unit": "frames/s", "cores": threads, "kind": "port",
+                        "sample": f"oracle/capf_oracle.py (CPU restatement of the reference forward, fp32) on BASELINE configs[0]: "
+                                  f"{args.backbone}, bs={n}, {H}x{W}; {len(times)} timed forwards after 1 warm-up, all host threads",
+                        "best_fps": n / min(times)}
+            c = crop[:n].clone()
+            want = capf_oracle.ca_pf_forward(weights, args.backbone, cfg.model.backbone, images[:n], kp2d[:n], c)
+            got = out[:n].cpu() if gather is None else out[:n].cpu()
+            parity = {"frames": n, "rel_l2": float((got - want).norm() / want.norm()),
+                      "mpjpe_vs_ref_mm": float((got - want).norm(dim=-1).mean()) * 1000.0}
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision] + " storage, f32 accumulate",
+            "data": "synthetic (seeded randn images, random-init weights of the named architecture)",
+            "config": {"workload": f"{args.backbone} + 4-level PoseFormer, 17 joints, bs={B} per GPU, {H}x{W} (BASELINE configs[1])",
+                       "global_batch": B * world, "parallelism": f"frame-sharded x{world}, NCCL all-gather of outputs" if world > 1 else "single GPU",
+                       "l2": f"inputs larger than L2: {h_img.numel() * 4 / 1e6:.0f} MB of images per step (L2 = 126 MB); activations ~{plan.workspace_bytes / 1e9:.1f} GB",
+                       "cuda_graph": not args.no_graph, "precision": args.precision},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "note": "pinned host f32 images -> H2D on a copy stream (double-buffered) -> CA_PF.forward -> D2H of [B,1,17,3]"},
+            "gpu_launches": args.steps * (plan.num_launches + 1),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--backbone", default="hrnet_32")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--height", type=int, default=256)
+    ap.add_argument("--width", type=int, default=256)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="frames per CPU-baseline forward (BASELINE configs[0] uses 4)")
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--ref-sample", type=int, default=32, help="frames per step of the --impl reference arm")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -539,11 +539,20 @@ static int attention_dispatch(const capf_op& op, cudaStream_t st) {
   size_t smem = (size_t)4 * ipw * seq * (hd + 1) * 3 * sizeof(float);
   const TI* qkv = (const TI*)op.in[0];
   TO* out = (TO*)op.out[0];
+  // opt in to > 48 KB dynamic smem once per instantiation (not a stream operation; done outside graph capture
+  // because Plan.capture() always runs one eager warm-up pass first)
+  static size_t max5 = 0, max17 = 0;
   if (seq == 5) {
-    cudaFuncSetAttribute(attention_small_kernel<TI, TO, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > max5) {
+      cudaFuncSetAttribute(attention_small_kernel<TI, TO, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      max5 = smem;
+    }
     attention_small_kernel<TI, TO, 5><<<blocks, 128, smem, st>>>(groups, heads, hd, ts, gs, op.f[0], qkv, out);
   } else {
-    cudaFuncSetAttribute(attention_small_kernel<TI, TO, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > max17) {
+      cudaFuncSetAttribute(attention_small_kernel<TI, TO, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      max17 = smem;
+    }
     attention_small_kernel<TI, TO, 17><<<blocks, 128, smem, st>>>(groups, heads, hd, ts, gs, op.f[0], qkv, out);
   }
   return check_launch("attention_small");
@@ -584,8 +593,9 @@ __global__ void __launch_bounds__(256) ref_sample_kernel(SampP p, const float* _
     const int H = p.H[l], W = p.W[l], C = p.C[l];
     Corners c = make_corners<false>(gx, gy, W, H);
     if (rec && lane == 0) {
-      int* r = rec + ((size_t)l * R + warp) * 4;
+      int* r = rec + ((size_t)l * R + warp) * 8;
       r[0] = c.x0; r[1] = c.y0; r[2] = (int)c.mask; r[3] = 0;
+      r[4] = __float_as_int(gx); r[5] = __float_as_int(gy); r[6] = 0; r[7] = 0;
     }
     const TI* m = (const TI*)p.map[l] + (size_t)b * H * W * C;
     TO* o = out + p.off[l] + (size_t)warp * C;
@@ -639,10 +649,12 @@ __global__ void __launch_bounds__(256) deform_sample_kernel(SampP p, const float
   for (int s = 0; s < 4; ++s) {
     aw[s] = lg[s] / den;
     float ox = tanhf(__ldg(row + 16 + (h * 4 + s) * 2)), oy = tanhf(__ldg(row + 16 + (h * 4 + s) * 2 + 1));
-    c[s] = make_corners<true>(__fadd_rn(ox, gx), __fadd_rn(oy, gy), W, H);
+    const float px = __fadd_rn(ox, gx), py = __fadd_rn(oy, gy);
+    c[s] = make_corners<true>(px, py, W, H);
     if (rec && lane == 0) {
-      int* r = rec + ((((size_t)l * R + rj) * 16) + h * 4 + s) * 4;
+      int* r = rec + ((((size_t)l * R + rj) * 16) + h * 4 + s) * 8;
       r[0] = c[s].x0; r[1] = c[s].y0; r[2] = (int)c[s].mask; r[3] = 0;
+      r[4] = __float_as_int(px); r[5] = __float_as_int(py); r[6] = 0; r[7] = 0;
     }
   }
   const TI* m = (const TI*)p.map[l] + (size_t)b * H * W * C;

@@ -11,7 +11,7 @@ def default_precision():
 
 
 def default_use_tc():
-    return os.environ.get("CAPF_TCGEN05", "1") != "0"
+    return os.environ.get("CAPF_TCGEN05", "0") != "0"
 
 
 def state_version(module: torch.nn.Module):

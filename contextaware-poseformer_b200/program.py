@@ -322,7 +322,7 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
     for l in range(levels):
         offs.append(offs[-1] + R * dims[l])
     samp = pb._buf("ref_sampled", (offs[-1],), adt)
-    rec0 = pb._buf("ref_corners", (levels, R, 4), "i32") if debug_records else None
+    rec0 = pb._buf("ref_corners", (levels, R, 8), "i32") if debug_records else None
     if rec0 is not None:
         rec0.role = "output"
         prog.outputs["ref_corners"] = rec0
@@ -345,7 +345,7 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
         ow = pb.linear(t, levels * R, D, [q + ".attention_weights.weight", q + ".sampling_offsets.weight"],
                        [q + ".attention_weights.bias", q + ".sampling_offsets.bias"], 48, out_dtype="f32", tag=q + ".ow")
         g = pb._buf("deform_sampled", (goffs[-1],), adt)
-        rec = pb._buf("deform_corners", (levels, R, 16, 4), "i32") if (debug_records and i == 0) else None
+        rec = pb._buf("deform_corners", (levels, R, 16, 8), "i32") if (debug_records and i == 0) else None
         if rec is not None:
             rec.role = "output"
             prog.outputs["deform_corners"] = rec
@@ -515,6 +515,22 @@ class Plan:
     @property
     def num_launches(self):
         return len(self.prog.ops)
+
+    def time_ops(self, passes: int = 2):
+        """Per-op device time (ms) of one in-order pass, CUDA events on the launching stream around every op.
+        The last of `passes` passes is returned, so caches are in their steady in-step state (not warm per op)."""
+        st = torch.cuda.current_stream(self.device)
+        n = len(self.prog.ops)
+        ms = [0.0] * n
+        for _ in range(passes):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            ev[0].record(st)
+            for k in range(n):
+                lib.check(self._L.capf_plan_run(self._h, k, 1, st.cuda_stream), "capf_plan_run")
+                ev[k + 1].record(st)
+            st.synchronize()
+            ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(n)]
+        return ms
 
     # ---- CUDA graph ---------------------------------------------------------------------------------
     def capture(self):

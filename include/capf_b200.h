@@ -104,8 +104,9 @@ typedef enum capf_op_kind {
  *     i[0]=B i[1]=J i[2]=n_levels  i[3+3l..5+3l]=H_l,W_l,C_l
  *     in[0]=ref [B*J][2] f32 (x,y in [-1,1])  in[1+l]=map l [B,H_l,W_l,C_l] dtype_in
  *     out... see i/o below: out[0]=packed output base dtype_out; level l written at element offset i[15+l]
- *     as a dense [B*J][C_l] matrix.   out[1] (optional, int32 [n_levels][B*J][4]) = x_nw, y_nw, valid-mask
- *     (bit0 nw, bit1 ne, bit2 sw, bit3 se), 0 -- the integer part of the gather, exposed for bit-exact tests.
+ *     as a dense [B*J][C_l] matrix.   out[1] (optional, int32 [n_levels][B*J][8]) = x_nw, y_nw, valid-mask
+ *     (bit0 nw, bit1 ne, bit2 sw, bit3 se), 0, float bits of the sampled (x,y), 0, 0 -- the integer part of the
+ *     gather and the exact position it was derived from, exposed for bit-exact tests.
  *
  * CAPF_OP_DEFORM_SAMPLE -- DeformableBlock sampling (pose_dformer.py:122-135): softmax over the 4 samples of
  *                    each head, tanh offsets + ref, F.grid_sample(..., padding_mode='border',
@@ -116,7 +117,7 @@ typedef enum capf_op_kind {
  *     in[5]=ow [n_levels*B*J][48] f32: cols 0..15 attention_weights logits (head*4+sample),
  *           cols 16..47 sampling_offsets pre-tanh ((head*4+sample)*2+xy)
  *     out[0]: level l = dense [B*J*4][C_l] dtype_out (row = (b*J+j)*4+head)
- *     out[1] optional int32 [n_levels][B*J][16][4] corner record as above.
+ *     out[1] optional int32 [n_levels][B*J][16][8] corner record as above.
  *
  * CAPF_OP_EMBED_COORD -- coord_embed(kp2d) + Spatial_pos_embed[0], and Spatial_pos_embed[1+l] broadcast
  *                    into the level slabs ready for the feat_embed GEMMs to accumulate onto

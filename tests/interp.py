@@ -118,7 +118,8 @@ class Interp:
                 rec[l, :, 0] = torch.from_numpy(x0.reshape(-1))
                 rec[l, :, 1] = torch.from_numpy(y0.reshape(-1))
                 rec[l, :, 2] = torch.from_numpy(m.reshape(-1).astype(np.int32))
-                rec[l, :, 3] = 0
+                rec[l, :, 3:] = 0
+                rec[l, :, 4:6] = torch.from_numpy(ref.numpy().reshape(-1, 2).view(np.int32))
 
     def _op8(self, op):   # DEFORM_SAMPLE
         B, Jn, nl, geo, maps, offs = self._maps(op)
@@ -139,7 +140,8 @@ class Interp:
                 rec[l, :, :, 0] = torch.from_numpy(x0.reshape(R, 16))
                 rec[l, :, :, 1] = torch.from_numpy(y0.reshape(R, 16))
                 rec[l, :, :, 2] = torch.from_numpy(m.reshape(R, 16).astype(np.int32))
-                rec[l, :, :, 3] = 0
+                rec[l, :, :, 3:] = 0
+                rec[l, :, :, 4:6] = torch.from_numpy(np.ascontiguousarray(pos[:, l].numpy()).reshape(R, 16, 2).view(np.int32))
 
     def _op9(self, op):   # EMBED_COORD
         B, Jn, D, S = op.i[:4]

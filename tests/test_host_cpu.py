@@ -1,0 +1,118 @@
+"""CPU: host-side logic -- state_dict layout, config mirror, op programs (through the reference interpreter,
+with the real memory plan), frame sharding.  No GPU, no compute calls into the shared library."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import capf_oracle
+import interp
+import protocol
+from capf_b200 import program
+from capf_b200.mvn.utils import cfg as cfgmod
+from conftest import build_case_model, golden_cases, load_golden, rel_l2, ROOT
+
+
+@pytest.mark.parametrize("backbone", ["hrnet_32", "hrnet_48", "cpn"])
+def test_state_dict_layout_matches_reference(backbone, manifest):
+    m, _, _ = build_case_model(backbone, 0)
+    ours = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    assert sorted(ours) == sorted(manifest[backbone])          # same keys, same shapes (train.py:307-314 strict=True)
+    assert all(not p.requires_grad for p in m.backbone.parameters())      # conpose.py:22-25
+    assert all(p.requires_grad for p in m.volume_net.parameters())
+
+
+def test_default_init_matches_reference_quirks():
+    """pose_dformer.py:103-113,184: zero attention/offset weights, directional offset bias, zero pos-embed."""
+    import capf_b200
+    m = capf_b200.CA_PF(capf_b200.make_config("hrnet_32"))
+    cb = m.volume_net.context_blocks[0]
+    assert cb.attention_weights.weight.abs().sum() == 0 and cb.sampling_offsets.weight.abs().sum() == 0
+    assert m.volume_net.Spatial_pos_embed.abs().sum() == 0
+    b = cb.sampling_offsets.bias.view(4, 4, 2)
+    assert torch.allclose(b[0, :, 0], torch.tensor([0.01, 0.02, 0.03, 0.04])) and b[0, :, 1].abs().max() < 1e-8
+    assert m.volume_net.head[0].eps == 1e-5 and m.volume_net.res_blocks[0].norm1.eps == 1e-6
+
+
+def test_config_mirror(tmp_path):
+    c = copy.deepcopy(cfgmod.config)
+    assert c.model.backbone.STAGE3.NUM_CHANNELS == [32, 64, 128] and c["model"]["poseformer"]["levels"] == 4
+    y = tmp_path / "ok.yaml"
+    y.write_text("model:\n  backbone:\n    type: cpn\n    fix_weights: true\n  poseformer:\n    embed_dim_ratio: 128\n")
+    saved = copy.deepcopy(dict(cfgmod.config))
+    try:
+        cfgmod.update_config(str(y))
+        assert cfgmod.config.model.backbone.type == "cpn" and cfgmod.config.model.backbone.fix_weights is True
+        bad = tmp_path / "bad.yaml"
+        bad.write_text("model:\n  not_a_key: 1\n")
+        with pytest.raises(ValueError, match="not exist in cfg.py"):       # cfg.py:173-174
+            cfgmod.update_config(str(bad))
+    finally:
+        cfgmod.config.clear()
+        cfgmod.config.update(cfgmod.AttrDict(saved))
+    ref_yaml = "/root/reference/ContextPose/experiments/human36m/human36m.yaml"
+    if os.path.isfile(ref_yaml):                                           # the reference's own YAML loads unchanged
+        import capf_b200
+        c = capf_b200.make_config("hrnet_48", ref_yaml)
+        assert c.model.backbone.STAGE4.NUM_CHANNELS == [48, 96, 192, 384] and c.model.poseformer.base_dim == 48
+        assert c.train.batch_size == 512 and c.model.backbone.fix_weights is True
+
+
+CASES = [c for c in golden_cases() if c["name"] in ("hrnet32_b2_128x96", "hrnet48_b1_384x288", "cpn_b2_256x256")]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_program_matches_golden(case, precision):
+    """The op program (as the GPU will run it, including buffer aliasing) reproduces the reference output."""
+    g = load_golden(case["name"])
+    m, w, cfg = build_case_model(case["backbone"], case["weight_seed"])
+    B, H, W = case["B"], case["H"], case["W"]
+    images, kp2d, crop = protocol.make_inputs(B, H, W, case["input_seed"])
+    prog = program.build_forward_program(case["backbone"], getattr(m.backbone, "cfg", None), m._pf_cfg,
+                                         {k: tuple(v.shape) for k, v in w.items()}, B, H, W, precision, debug_records=True)
+    it = interp.Interp(prog, w)
+    it.t(prog.inputs["images"]).copy_(images)
+    it.t(prog.inputs["kp2d"]).copy_(kp2d.reshape(-1, 2))
+    it.t(prog.inputs["ref"]).copy_(torch.from_numpy(g["crop_after"]).reshape(-1, 2))
+    it.run()
+    out = it.t(prog.outputs["out"]).view(B, 1, 17, 3)
+    tol = 1e-5 if precision == "fp32" else 2.5e-3      # fp16 storage: ~7e-4 HRNet, ~1.3e-3 CPN (documented in DESIGN.md)
+    assert rel_l2(out, g["out"]) < tol
+    for l, f in enumerate(prog.feature_maps):
+        nchw = it.t(f).float().permute(0, 3, 1, 2).reshape(-1)
+        assert rel_l2(nchw[torch.from_numpy(g[f"feat{l}_idx"])], g[f"feat{l}_val"]) < (1e-5 if precision == "fp32" else 3e-3)
+
+
+def test_memory_plan_reuses_and_never_aliases_live_buffers():
+    m, w, _ = build_case_model("hrnet_32", 0)
+    prog = program.build_forward_program("hrnet_32", m.backbone.cfg, m._pf_cfg, {k: tuple(v.shape) for k, v in w.items()},
+                                         2, 64, 64, "fp32")
+    assign, slots = program.plan_memory(prog)
+    roots = {b.root for op in prog.ops for b in list(op.ins) + list(op.outs) if isinstance(b, program.Buf)}
+    assert sum(slots) < 0.25 * sum(r.nbytes for r in roots)          # reuse happens
+    # liveness check: two roots sharing a slot must have disjoint [first def, last use] ranges
+    first, last = {}, {}
+    for k, op in enumerate(prog.ops):
+        for b in list(op.ins) + list(op.outs):
+            if isinstance(b, program.Buf):
+                first.setdefault(b.root, k)
+                last[b.root] = k
+    by_slot = {}
+    for r, s in assign.items():
+        by_slot.setdefault(s, []).append((first[r], last[r]))
+    for s, iv in by_slot.items():
+        iv.sort()
+        for (a0, a1), (b0, b1) in zip(iv, iv[1:]):
+            assert a1 < b0 or (a1 == b0 and False), f"slot {s}: live ranges {a0, a1} and {b0, b1} overlap"
+
+
+def test_flop_accounting_matches_survey():
+    m, w, _ = build_case_model("hrnet_32", 0)
+    prog = program.build_forward_program("hrnet_32", m.backbone.cfg, m._pf_cfg, {k: tuple(v.shape) for k, v in w.items()},
+                                         1, 256, 256, "fp32")
+    assert abs(prog.flops() / 1e9 - 20.995) < 0.05        # SURVEY.md section 6 / BASELINE.md section 2
+    qkv = sum(o.flops for o in prog.ops if "joint_blocks" in o.tag and o.tag.endswith("attn.qkv"))
+    assert abs(qkv / 1e9 - 0.1671) < 1e-3
