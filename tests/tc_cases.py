@@ -1,0 +1,81 @@
+"""Shape list + runner shared by tests/test_gpu_tc.py and tools/tc_probe.py: the tcgen05 implicit-GEMM kernel
+(csrc/capf_tc.cu) against a plain PyTorch fp32 reference of the same operator on 16-bit-rounded inputs."""
+import zlib
+
+import torch
+import torch.nn.functional as F
+
+from capf_b200 import lib
+from gpu_util import run_op
+
+DEV = "cuda:0"
+
+# name, (N, H, W, Cin, Cout, k, stride), act, use_res, out_f32
+TC_CASES = [
+    ("rows_sw128_exact", (384, 1, 1, 64, 64, 1, 1), lib.ACT_NONE, False, False),
+    ("rows_ow_ragged_f32", (37, 1, 1, 128, 48, 1, 1), lib.ACT_NONE, False, True),
+    ("rows_qkv", (4352, 1, 1, 640, 1920, 1, 1), lib.ACT_NONE, False, False),
+    ("rows_sw64_k32", (300, 1, 1, 32, 128, 1, 1), lib.ACT_NONE, True, True),
+    ("rows_sw64_k96", (300, 1, 1, 96, 128, 1, 1), lib.ACT_GELU, False, False),
+    ("rows_sw32_k48", (260, 1, 1, 48, 32, 1, 1), lib.ACT_NONE, True, True),
+    ("rows_sw32_k16", (129, 1, 1, 16, 16, 1, 1), lib.ACT_RELU, False, False),
+    ("rows_fc2_res_f32", (1000, 1, 1, 1280, 640, 1, 1), lib.ACT_NONE, True, True),
+    ("rows_fc1_gelu", (1000, 1, 1, 640, 1280, 1, 1), lib.ACT_GELU, False, False),
+    ("rows_fuse1x1", (2, 8, 8, 256, 32, 1, 1), lib.ACT_NONE, False, False),
+    ("rows_resnet_expand", (2, 8, 6, 512, 2048, 1, 1), lib.ACT_RELU, True, False),
+    ("conv3_c32_small", (3, 16, 12, 32, 32, 3, 1), lib.ACT_RELU, True, False),
+    ("conv3_c64_64x64", (2, 64, 64, 64, 64, 3, 1), lib.ACT_RELU, True, False),
+    ("conv3_c32_many_tiles", (8, 64, 64, 32, 32, 3, 1), lib.ACT_RELU, False, False),
+    ("conv3_c128_16x16", (4, 16, 16, 128, 128, 3, 1), lib.ACT_RELU, True, False),
+    ("conv3_c256_8x8_n5", (5, 8, 8, 256, 256, 3, 1), lib.ACT_RELU, True, False),
+    ("conv3_c48_9x7", (2, 9, 7, 48, 48, 3, 1), lib.ACT_RELU, True, False),
+    ("conv3s2_64_128", (2, 16, 16, 64, 128, 3, 2), lib.ACT_NONE, False, False),
+    ("conv3s2_256_64_64x64", (2, 64, 64, 256, 64, 3, 2), lib.ACT_RELU, False, False),
+    ("conv3s2_48_96_odd", (1, 9, 7, 48, 96, 3, 2), lib.ACT_NONE, False, False),
+    ("conv1s2_64_64", (2, 8, 8, 64, 64, 1, 2), lib.ACT_NONE, False, False),
+    ("conv3_c96_48x36", (2, 48, 36, 96, 96, 3, 1), lib.ACT_RELU, True, False),
+    ("conv3_c32_64x48", (2, 64, 48, 32, 32, 3, 1), lib.ACT_RELU, True, False),
+]
+
+
+def run_tc_case(case, dt=torch.float16, impl=None):
+    """Returns (rel_l2, max_abs, frac_bad_rows) of the tcgen05 kernel against the fp32 reference."""
+    name, (N, H, W, Cin, Cout, k, stride), act, use_res, out_f32 = case
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % (1 << 31))
+    pad = k // 2
+    x = torch.randn(N, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    odt = torch.float32 if out_f32 else dt
+    res = torch.randn(N, Ho, Wo, Cout, generator=g) if use_res else None
+    xq, wq = x.to(dt).float().to(DEV), w.to(dt).float().to(DEV)
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        y = F.conv2d(xq.permute(0, 3, 1, 2), wq, bias.to(DEV), stride, pad).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    if act == lib.ACT_GELU:
+        y = F.gelu(y)
+    if use_res:
+        y = y + res.to(odt).float().to(DEV)
+    if act == lib.ACT_RELU:
+        y = F.relu(y)
+    impl = lib.IMPL_TCGEN05 if impl is None else impl
+    if impl == lib.IMPL_TCGEN05:
+        wp = w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().to(dt).to(DEV)      # [Cout][(r,s,ci)]
+    else:
+        wp = w.permute(2, 3, 1, 0).reshape(-1, Cout).contiguous().to(dt).to(DEV)
+    out = torch.full((N, Ho, Wo, Cout), float("nan"), dtype=odt, device=DEV)
+    run_op(lib.OP_CONV2D, dt, odt, [N, H, W, Cin, Cout, k, k, stride, pad, Ho, Wo, act, impl], [],
+           [x.to(dt).to(DEV), wp, bias.to(DEV), res.to(odt).to(DEV) if use_res else None], [out])
+    o = out.float()
+    diff = (o - y)
+    bad = ~torch.isfinite(o)
+    diff = torch.where(bad, torch.full_like(diff, 1e3), diff)
+    rel = float(diff.double().norm() / y.double().norm().clamp_min(1e-30))
+    tol_row = 0.05 * float(y.abs().mean()) + 0.02
+    bad_rows = float((diff.abs().reshape(-1, Cout).amax(dim=1) > tol_row).float().mean())
+    return rel, float(diff.abs().max()), bad_rows
