@@ -271,6 +271,14 @@ def run_native(args):
             d["ms"] += ms
             d["flops"] += op.flops
             d["launches"] += 1
+        if args.ops_csv:
+            os.makedirs(os.path.dirname(os.path.abspath(args.ops_csv)), exist_ok=True)
+            with open(args.ops_csv, "w") as f:
+                f.write("idx,kind,impl,tag,shape,ms,gflop,tflops\n")
+                for k, (op, ms) in enumerate(zip(plan.prog.ops, op_ms)):
+                    shape = "x".join(str(v) for v in op.i[:11]) if op.kind == capf_b200.lib.OP_CONV2D else "x".join(str(v) for v in op.i[:6])
+                    impl = op.i[12] if op.kind == capf_b200.lib.OP_CONV2D else -1
+                    f.write(f"{k},{op.kind},{impl},{op.tag},{shape},{ms:.5f},{op.flops / 1e9:.4f},{op.flops / max(ms, 1e-9) / 1e9:.2f}\n")
         dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
         dom_tflops = dom[1]["flops"] / (dom[1]["ms"] * 1e-3) / 1e12
         peak_tf = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
@@ -341,6 +349,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-sample", type=int, default=4, help="frames per CPU-baseline forward (BASELINE configs[0] uses 4)")
     ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--ops-csv", default=None, help="write the per-op device-time table (one in-order pass) to this CSV")
     ap.add_argument("--ref-sample", type=int, default=32, help="frames per step of the --impl reference arm")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -11,7 +11,8 @@ def default_precision():
 
 
 def default_use_tc():
-    return os.environ.get("CAPF_TCGEN05", "0") != "0"
+    """tcgen05/TMA kernels for every 16-bit GEMM-shaped op (CAPF_TCGEN05=0 forces the CUDA-core kernels)."""
+    return os.environ.get("CAPF_TCGEN05", "1") != "0"
 
 
 def state_version(module: torch.nn.Module):

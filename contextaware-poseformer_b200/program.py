@@ -171,7 +171,7 @@ class ProgramBuilder:
         """Kernel family for a conv/linear.  tcgen05 needs 16-bit operands and TMA-friendly channel counts."""
         if not self.use_tc or dt_in == "f32":
             return lib.IMPL_SIMT
-        if cin % 16 or cout % 16 or cout > 256 and cout % 128:
+        if cin % 16 or cout % 16 or stride > 2 or k > 7:
             return lib.IMPL_SIMT
         return lib.IMPL_TCGEN05
 
