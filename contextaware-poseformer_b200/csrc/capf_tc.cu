@@ -9,120 +9,22 @@
 //     row-major [M][K] matrix.
 // D[128 x BN] (fp32, TMEM) += A[128 x 16] (smem, K-major, swizzled) * B[BN x 16]^T (smem, K-major, swizzled).
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (tcgen05.ld -> bias/GELU/residual/ReLU -> global).  Two TMEM accumulator stages let the
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator,
+// warps 4..11 = epilogue (tcgen05.ld -> bias/GELU/residual/ReLU -> global).  Two TMEM accumulator stages let the
 // epilogue of tile i overlap the MMAs of tile i+1; a ring of smem stages decouples TMA from the tensor pipe.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
 #include <new>
 
-#include "capf_common.cuh"
-#include "capf_internal.h"
+#include "capf_tc.cuh"
 
 namespace capf {
 
 // =======================================================================================================
-// device-side PTX wrappers
-// =======================================================================================================
-namespace ptx {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (((++spins) & 0x3ff) == 0 && clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread for the CTA.
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives once every tcgen05 op previously issued by this thread has completed.
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives row (lane base + t).
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-}  // namespace ptx
-
-// =======================================================================================================
 // kernel parameters
 // =======================================================================================================
+constexpr int TC_THREADS = 384;          // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_HEADER_BYTES = 1024;       // barriers + TMEM base pointer
 constexpr int TC_A_STAGE_BYTES = 128 * 128; // 128 rows x 64 elements x 2 B
-constexpr int TC_SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA
 
 struct TcP {
   int mode;                 // 0 = rows ([M][K] matrix), 1 = conv (NHWC, 4-D boxes)
@@ -149,10 +51,7 @@ struct TcP {
   void* out;
 };
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t hi) {
-  // bits [0,14) start address >> 4, bits [16,30) leading byte offset >> 4 (ignored for swizzled K-major; canonical 1)
-  return ((uint64_t)hi << 32) | (uint64_t)(((smem_addr >> 4) & 0x3fffu) | (1u << 16));
-}
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t hi) { return tc_make_desc(smem_addr, 1u, hi); }
 
 struct TileCoord {
   int n_tile;      // column tile
@@ -174,74 +73,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TcP& p, int tile) {
   return t;
 }
 
-template <typename TO> struct Pack16;
-template <> struct Pack16<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&r)[16]) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
-      r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-    }
-  }
-  static __device__ __forceinline__ void store(float* p, const float (&r)[16]) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-  }
-};
-template <> struct Pack16<__half> {
-  static __device__ __forceinline__ void load(const __half* p, float (&r)[16]) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint4 v = *reinterpret_cast<const uint4*>(p + 8 * q);
-      const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __half22float2(h[e]);
-        r[8 * q + 2 * e] = f.x; r[8 * q + 2 * e + 1] = f.y;
-      }
-    }
-  }
-  static __device__ __forceinline__ void store(__half* p, const float (&r)[16]) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint4 v;
-      __half2* h = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(r[8 * q + 2 * e], r[8 * q + 2 * e + 1]);
-      *reinterpret_cast<uint4*>(p + 8 * q) = v;
-    }
-  }
-};
-template <> struct Pack16<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[16]) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint4 v = *reinterpret_cast<const uint4*>(p + 8 * q);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __bfloat1622float2(h[e]);
-        r[8 * q + 2 * e] = f.x; r[8 * q + 2 * e + 1] = f.y;
-      }
-    }
-  }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&r)[16]) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint4 v;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(r[8 * q + 2 * e], r[8 * q + 2 * e + 1]);
-      *reinterpret_cast<uint4*>(p + 8 * q) = v;
-    }
-  }
-};
-
 // =======================================================================================================
 // the kernel
 // =======================================================================================================
 template <typename TO>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -267,7 +103,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);
-      ptx::mbar_init(bar_tempty + 8 * a, 128);
+      ptx::mbar_init(bar_tempty + 8 * a, TC_THREADS - 128);
     }
     ptx::fence_mbar_init();
   }
@@ -344,8 +180,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =========================================
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int row = q * 32 + lane;          // accumulator row == tile row
+    // 8 warps: quadrant q = warp & 3 owns TMEM lanes [32q, 32q+32) (= tile rows); the two warps of a quadrant split
+    // the BN accumulator columns.  Per group of 32 columns: two tcgen05.ld in flight, the residual of the NEXT group
+    // already requested, one wait, then bias/GELU/residual/ReLU and 16-byte stores.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int split = ((p.BN / 16 + 1) / 2) * 16;
+    const int cbeg = half ? split : 0, cend = half ? p.BN : split;
+    const int ngroups = (cend - cbeg + 31) / 32;
     const TO* res = reinterpret_cast<const TO*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
     uint32_t it = 0;
@@ -363,46 +206,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       } else {
         orow = (t.m0 + row < p.M) ? (long long)(t.m0 + row) : -1;
       }
+      const bool live = orow >= 0;
+      const bool has_res = live && res != nullptr;
+      const int ncol0 = t.n_tile * p.BN;
+      const size_t off0 = (size_t)(live ? orow : 0) * p.Cout + ncol0;
+      const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
+
+      Vec16<TO> r0[2], r1[2];
+      auto fetch = [&](int g, Vec16<TO> (&r)[2]) {
+        if (has_res) {
+          const int c = cbeg + 32 * g;
+          r[0].load(res + off0 + c);
+          if (c + 16 < cend) r[1].load(res + off0 + c + 16);
+        }
+      };
+      auto group = [&](int g, const Vec16<TO> (&r)[2], Vec16<TO> (&rnext)[2]) {
+        const int c = cbeg + 32 * g;
+        const bool two = c + 16 < cend;
+        uint32_t a0[16], a1[16];
+        ptx::tmem_ld16(taddr + (uint32_t)c, a0);
+        if (two) ptx::tmem_ld16(taddr + (uint32_t)(c + 16), a1);
+        if (g + 1 < ngroups) fetch(g + 1, rnext);
+        ptx::tmem_ld_wait();
+        if (live) {
+          finish16<TO>(p.bias, p.act, a0, r[0], has_res, ncol0 + c, out + off0 + c);
+          if (two) finish16<TO>(p.bias, p.act, a1, r[1], has_res, ncol0 + c + 16, out + off0 + c + 16);
+        }
+      };
+      fetch(0, r0);                                  // independent of the MMAs: issue before waiting for them
       ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      const int ncol0 = t.n_tile * p.BN;
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t raw16[16];
-        ptx::tmem_ld16(taddr + (uint32_t)c, raw16);
-        ptx::tmem_ld_wait();
-        if (orow >= 0) {
-          float v[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw16[e]);
-          const int n = ncol0 + c;
-          if (p.bias) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q4);
-              v[4 * q4] += b4.x; v[4 * q4 + 1] += b4.y; v[4 * q4 + 2] += b4.z; v[4 * q4 + 3] += b4.w;
-            }
-          }
-          if (p.act == CAPF_ACT_GELU) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
-          }
-          const size_t off = (size_t)orow * p.Cout + n;
-          if (res) {
-            float r16[16];
-            Pack16<TO>::load(res + off, r16);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] += r16[e];
-          }
-          if (p.act == CAPF_ACT_RELU) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-          }
-          Pack16<TO>::store(out + off, v);
-        }
+      for (int g = 0; g < ngroups; g += 2) {
+        group(g, r0, r1);
+        if (g + 1 < ngroups) group(g + 1, r1, r0);
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(bar_tempty + 8 * acc);   // 128 arrivals free this accumulator stage
+      ptx::mbar_arrive(bar_tempty + 8 * acc);   // 256 arrivals free this accumulator stage
     }
   }
 
@@ -415,6 +254,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // host side: tensor maps + launch geometry
 // =======================================================================================================
 struct TcConvState {
+  TcHaloState* halo = nullptr;   // non-null: the op runs on the halo-band kernel instead of tc_gemm_kernel
   CUtensorMap mapA, mapB;
   TcP p;
   int grid;
@@ -424,7 +264,7 @@ struct TcConvState {
 
 static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
 
-static int get_encoder() {
+int tc_get_encoder() {
   if (g_encode) return CAPF_OK;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -484,7 +324,7 @@ static void choose_box(const ConvGeo& g, int max_w, int& bw, int& bh, int& bn) {
   }
 }
 
-static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims,
+int tc_encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims,
                       const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, int swz_bytes, const char* what) {
   CUtensorMapSwizzle sw = swz_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swz_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = g_encode(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
@@ -495,11 +335,19 @@ static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const vo
 
 int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   *out = nullptr;
-  int e = get_encoder();
+  int e = tc_get_encoder();
   if (e) return e;
   const ConvGeo g = geo_of(op);
   TcConvState* s = new (std::nothrow) TcConvState();
   if (!s) return set_error(CAPF_ERR_ARG, "tc_conv_prepare: out of host memory");
+  // i[13]: kernel variant hint (0 = automatic, 1 = per-tap TMA GEMM, 2 = halo band); tests use it for A/B parity
+  if (op.i[13] != 1 && tc_halo_supported(op)) {
+    e = tc_halo_prepare(op, &s->halo);
+    if (e) { delete s; return e; }
+    *out = s;
+    return CAPF_OK;
+  }
+  if (op.i[13] == 2) { delete s; return set_error(CAPF_ERR_UNSUPPORTED, "tc conv: halo variant requested but not applicable"); }
   TcP& p = s->p;
   memset(&p, 0, sizeof(p));
   const bool rows = (g.KH == 1 && g.KW == 1 && g.stride == 1 && g.pad == 0);
@@ -563,11 +411,8 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   int cols = 32;
   while (cols < 2 * p.BN) cols <<= 1;
   p.tmem_cols = cols;
-  const uint32_t fmt = op.dtype_in == CAPF_BF16 ? 1u : 0u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;   // UMMA LayoutType: SWIZZLE_128B / 64B / 32B
-  const uint32_t sbo = (uint32_t)(8 * swz) >> 4;                    // byte distance between 8-row groups, >> 4
-  p.desc_hi = sbo | (1u << 14) | (layout << 29);                    // version = 1 at bit 46, layout at bits 61..63
+  p.idesc = tc_idesc(op.dtype_in == CAPF_BF16, p.BN);
+  p.desc_hi = tc_desc_hi(swz, 8 * swz);
   s->grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   s->dtype_out = op.dtype_out;
 
@@ -579,20 +424,20 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
     cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.kb, 128};
     cuuint32_t es[2] = {1, 1};
-    e = encode_map(&s->mapA, dt, 2, op.in[0], dims, strides, box, es, swz, "A rows");
+    e = tc_encode_map(&s->mapA, dt, 2, op.in[0], dims, strides, box, es, swz, "A rows");
   } else {
     cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
     cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.W * g.Cin * 2, (cuuint64_t)g.H * g.W * g.Cin * 2};
     cuuint32_t box[4] = {(cuuint32_t)p.kb, (cuuint32_t)(p.bw * g.stride), (cuuint32_t)(p.bh * g.stride), (cuuint32_t)p.bn};
     cuuint32_t es[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
-    e = encode_map(&s->mapA, dt, 4, op.in[0], dims, strides, box, es, swz, "A conv");
+    e = tc_encode_map(&s->mapA, dt, 4, op.in[0], dims, strides, box, es, swz, "A conv");
   }
   if (!e) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)g.Cout};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.kb, (cuuint32_t)p.BN};
     cuuint32_t es[2] = {1, 1};
-    e = encode_map(&s->mapB, dt, 2, op.in[1], dims, strides, box, es, swz, "B weights");
+    e = tc_encode_map(&s->mapB, dt, 2, op.in[1], dims, strides, box, es, swz, "B weights");
   }
   if (e) { delete s; return e; }
   *out = s;
@@ -607,12 +452,13 @@ static int tc_launch_typed(const TcConvState* s, cudaStream_t st) {
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_gemm_kernel smem opt-in: %s", cudaGetErrorString(e));
     max_smem = TC_SMEM_LIMIT;
   }
-  tc_gemm_kernel<TO><<<s->grid, 256, s->smem_bytes, st>>>(s->mapA, s->mapB, s->p);
+  tc_gemm_kernel<TO><<<s->grid, TC_THREADS, s->smem_bytes, st>>>(s->mapA, s->mapB, s->p);
   return check_launch("tc_gemm_kernel");
 }
 
 int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
   if (!s) return set_error(CAPF_ERR_ARG, "tc conv: op was not prepared");
+  if (s->halo) return tc_halo_launch(s->halo, st);
   switch (s->dtype_out) {
     case CAPF_F32: return tc_launch_typed<float>(s, st);
     case CAPF_F16: return tc_launch_typed<__half>(s, st);
@@ -621,6 +467,9 @@ int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
   }
 }
 
-void tc_conv_release(TcConvState* s) { delete s; }
+void tc_conv_release(TcConvState* s) {
+  if (s && s->halo) tc_halo_release(s->halo);
+  delete s;
+}
 
 }  // namespace capf

@@ -1,0 +1,237 @@
+// Device-side building blocks shared by the tcgen05 kernels of libcapf_b200 (capf_tc.cu, capf_tc_halo.cu):
+// PTX wrappers (mbarrier, TMA, TMEM, tcgen05.mma/ld/commit), smem matrix descriptors, and the fused epilogue.
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "capf_common.cuh"
+#include "capf_internal.h"
+
+namespace capf {
+
+// =======================================================================================================
+// device-side PTX wrappers
+// =======================================================================================================
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (((++spins) & 0x3ff) == 0 && clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread for the CTA.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every tcgen05 op previously issued by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives row (lane base + t).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace ptx
+
+constexpr int TC_SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA
+
+// High word of a K-major shared-memory matrix descriptor: stride byte offset (distance between 8-row groups) >> 4 in
+// bits [32,46), descriptor version 1 in [46,48), swizzle mode in [61,64) (0 none, 2 = 128 B, 4 = 64 B, 6 = 32 B).
+__host__ __device__ inline uint32_t tc_desc_hi(int swizzle_bytes, int sbo_bytes) {
+  const uint32_t layout = swizzle_bytes == 128 ? 2u : swizzle_bytes == 64 ? 4u : swizzle_bytes == 32 ? 6u : 0u;
+  return ((uint32_t)sbo_bytes >> 4) | (1u << 14) | (layout << 29);
+}
+// Low word: start address >> 4 in [0,14), leading byte offset >> 4 in [16,30) (distance between the two 16-byte
+// K slices of one MMA in the un-swizzled layout; ignored, canonical value 1, in the swizzled K-major layouts).
+__device__ __forceinline__ uint64_t tc_make_desc(uint32_t smem_addr, uint32_t lbo_field, uint32_t hi) {
+  return ((uint64_t)hi << 32) | (uint64_t)(((smem_addr >> 4) & 0x3fffu) | (lbo_field << 16));
+}
+// tcgen05 instruction descriptor: kind::f16, fp32 accumulate, A and B K-major, M = 128, N = n.
+__host__ __device__ inline uint32_t tc_idesc(bool bf16, int n) {
+  const uint32_t fmt = bf16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// 16 consecutive output elements as raw 16-byte vectors: loads are issued early and converted late so that the
+// global-memory latency of the residual overlaps the TMEM read of the accumulator.
+template <typename TO> struct Vec16;
+template <> struct Vec16<float> {
+  float4 v[4];
+  __device__ __forceinline__ void load(const float* p) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const float4*>(p + 4 * q);
+  }
+  __device__ __forceinline__ void add_to(float (&r)[16]) const {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { r[4 * q] += v[q].x; r[4 * q + 1] += v[q].y; r[4 * q + 2] += v[q].z; r[4 * q + 3] += v[q].w; }
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&r)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+  }
+};
+template <> struct Vec16<__half> {
+  uint4 v[2];
+  __device__ __forceinline__ void load(const __half* p) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) v[q] = *reinterpret_cast<const uint4*>(p + 8 * q);
+  }
+  __device__ __forceinline__ void add_to(float (&r)[16]) const {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[q]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h[e]);
+        r[8 * q + 2 * e] += f.x; r[8 * q + 2 * e + 1] += f.y;
+      }
+    }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&r)[16]) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint4 o;
+      __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(r[8 * q + 2 * e], r[8 * q + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(p + 8 * q) = o;
+    }
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  uint4 v[2];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) v[q] = *reinterpret_cast<const uint4*>(p + 8 * q);
+  }
+  __device__ __forceinline__ void add_to(float (&r)[16]) const {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[q]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __bfloat1622float2(h[e]);
+        r[8 * q + 2 * e] += f.x; r[8 * q + 2 * e + 1] += f.y;
+      }
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&r)[16]) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint4 o;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(r[8 * q + 2 * e], r[8 * q + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(p + 8 * q) = o;
+    }
+  }
+};
+
+// bias + GELU + residual + ReLU on 16 accumulator columns of one output row, then the store.
+template <typename TO>
+__device__ __forceinline__ void finish16(const float* __restrict__ bias, int act, const uint32_t (&raw)[16], const Vec16<TO>& rv, bool has_res, int n, TO* dst) {
+  float v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
+  if (bias) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n) + q4);
+      v[4 * q4] += b4.x; v[4 * q4 + 1] += b4.y; v[4 * q4 + 2] += b4.z; v[4 * q4 + 3] += b4.w;
+    }
+  }
+  if (act == CAPF_ACT_GELU) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
+  }
+  if (has_res) rv.add_to(v);
+  if (act == CAPF_ACT_RELU) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+  }
+  Vec16<TO>::store(dst, v);
+}
+
+// halo-band 3x3 convolution (capf_tc_halo.cu)
+struct TcHaloState;
+int tc_halo_supported(const capf_op& op);
+int tc_halo_prepare(const capf_op& op, TcHaloState** out);
+int tc_halo_launch(const TcHaloState* s, cudaStream_t st);
+void tc_halo_release(TcHaloState* s);
+
+// host helpers (capf_tc.cu)
+int tc_get_encoder();
+int tc_encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box, const cuuint32_t* estr, int swz_bytes, const char* what);
+
+}  // namespace capf

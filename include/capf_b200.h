@@ -70,6 +70,8 @@ typedef enum capf_op_kind {
  *                    nn.Linear [+GELU] [+residual] (pose_dformer.py:25-31,49,56,132,214,221,240) as a
  *                    1x1 convolution over rows.
  *     i[0..10] = N,H,W,Cin,Cout,KH,KW,stride,pad,Ho,Wo   i[11]=act  i[12]=impl
+ *     i[13] = tcgen05 kernel variant hint: 0 automatic, 1 per-tap TMA implicit GEMM, 2 shared-memory halo band
+ *             (3x3 / stride 1 / pad 1 whose folded weights fit in shared memory); used by the A/B parity tests
  *     in[0]=x  [N,H,W,Cin]        dtype_in
  *     in[1]=w  SIMT: [KH*KW*Cin][Cout] (tap-major rows, Cout contiguous); TCGEN05: [Cout][KH*KW*Cin];
  *              dtype_in, except x f32 -> w f32.  BatchNorm scale is pre-folded into w by the host.

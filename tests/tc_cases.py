@@ -38,7 +38,22 @@ TC_CASES = [
 ]
 
 
-def run_tc_case(case, dt=torch.float16, impl=None):
+# 3x3 / stride 1 / pad 1 shapes the halo-band kernel (csrc/capf_tc_halo.cu) must take when asked to (variant 2)
+HALO_CASES = [
+    ("halo_c32_64x64", (3, 64, 64, 32, 32, 3, 1), lib.ACT_RELU, True, False),
+    ("halo_c64_32x32", (5, 32, 32, 64, 64, 3, 1), lib.ACT_RELU, True, False),
+    ("halo_c32_many_bands", (40, 64, 64, 32, 32, 3, 1), lib.ACT_RELU, False, False),
+    ("halo_c64_many_bands", (150, 32, 32, 64, 64, 3, 1), lib.ACT_NONE, True, False),
+    ("halo_c48_9x7", (3, 9, 7, 48, 48, 3, 1), lib.ACT_RELU, True, False),
+    ("halo_c32_64x48", (2, 64, 48, 32, 32, 3, 1), lib.ACT_RELU, True, False),
+    ("halo_c64_32x24", (2, 32, 24, 64, 64, 3, 1), lib.ACT_GELU, False, False),
+    ("halo_c16_tiny", (1, 3, 5, 16, 16, 3, 1), lib.ACT_NONE, False, False),
+    ("halo_c64_c32_f32out", (2, 16, 16, 64, 32, 3, 1), lib.ACT_NONE, True, True),
+    ("halo_c32_c64_96x72", (1, 96, 72, 32, 64, 3, 1), lib.ACT_RELU, False, False),
+]
+
+
+def run_tc_case(case, dt=torch.float16, impl=None, variant=0):
     """Returns (rel_l2, max_abs, frac_bad_rows) of the tcgen05 kernel against the fp32 reference."""
     name, (N, H, W, Cin, Cout, k, stride), act, use_res, out_f32 = case
     g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % (1 << 31))
@@ -69,7 +84,7 @@ def run_tc_case(case, dt=torch.float16, impl=None):
     else:
         wp = w.permute(2, 3, 1, 0).reshape(-1, Cout).contiguous().to(dt).to(DEV)
     out = torch.full((N, Ho, Wo, Cout), float("nan"), dtype=odt, device=DEV)
-    run_op(lib.OP_CONV2D, dt, odt, [N, H, W, Cin, Cout, k, k, stride, pad, Ho, Wo, act, impl], [],
+    run_op(lib.OP_CONV2D, dt, odt, [N, H, W, Cin, Cout, k, k, stride, pad, Ho, Wo, act, impl, variant], [],
            [x.to(dt).to(DEV), wp, bias.to(DEV), res.to(odt).to(DEV) if use_res else None], [out])
     o = out.float()
     diff = (o - y)

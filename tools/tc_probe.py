@@ -11,14 +11,17 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def main():
     import torch
-    from tc_cases import TC_CASES, run_tc_case
+    from tc_cases import HALO_CASES, TC_CASES, run_tc_case
+    if os.environ.get("PROBE_SET", "tc") == "halo":
+        TC_CASES = HALO_CASES
+    variant = int(os.environ.get("PROBE_VARIANT", "0"))
     idx = [int(a) for a in sys.argv[1:]] or list(range(len(TC_CASES)))
     single = len(sys.argv) > 1
     for i in idx:
         c = TC_CASES[i]
         for dt in (torch.float16, torch.bfloat16):
             try:
-                rel, mx, bad = run_tc_case(c, dt)
+                rel, mx, bad = run_tc_case(c, dt, variant=variant)
                 print(f"[{i:2d}] {c[0]:28s} {str(dt)[6:]:9s} rel {rel:.3e} max {mx:.3e} bad_rows {bad:.4f} "
                       f"{'OK' if bad == 0 and rel < 1e-2 else 'WRONG'}", flush=True)
             except Exception as e:  # noqa: BLE001
