@@ -53,24 +53,33 @@ struct TcP {
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t hi) { return tc_make_desc(smem_addr, 1u, hi); }
 
-struct TileCoord {
-  int n_tile;      // column tile
-  int m0;          // rows mode: first row
-  int ox0, oy0, n0;  // conv mode: first output pixel / image of the box
+// Tiles are handed out as one contiguous range per CTA, so every role walks its range with carry-propagating
+// counters instead of integer divisions (the producer and the MMA issuer are single threads: a division costs them
+// more than a TMA or MMA issue).  Order: column tile fastest, then x, y, image box.
+struct TileWalk {
+  int n_tile, tx, ty, tn;
+  __device__ __forceinline__ void init(const TcP& p, int tile) {
+    n_tile = tile % p.n_tiles_n;
+    int mt = tile / p.n_tiles_n;
+    tx = mt % p.tiles_x;
+    int r = mt / p.tiles_x;
+    ty = r % p.tiles_y;
+    tn = r / p.tiles_y;
+  }
+  __device__ __forceinline__ void next(const TcP& p) {
+    if (++n_tile == p.n_tiles_n) {
+      n_tile = 0;
+      if (++tx == p.tiles_x) {
+        tx = 0;
+        if (++ty == p.tiles_y) { ty = 0; ++tn; }
+      }
+    }
+  }
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const TcP& p, int tile) {
-  TileCoord t;
-  t.n_tile = tile % p.n_tiles_n;
-  int mt = tile / p.n_tiles_n;
-  t.m0 = mt * 128;
-  int tx = mt % p.tiles_x;
-  int r = mt / p.tiles_x;
-  int ty = r % p.tiles_y;
-  t.ox0 = tx * p.bw;
-  t.oy0 = ty * p.bh;
-  t.n0 = (r / p.tiles_y) * p.bn;
-  return t;
+__device__ __forceinline__ void tile_range(const TcP& p, int& t0, int& t1) {
+  t0 = (int)(((long long)p.num_tiles * blockIdx.x) / gridDim.x);
+  t1 = (int)(((long long)p.num_tiles * (blockIdx.x + 1)) / gridDim.x);
 }
 
 // =======================================================================================================
@@ -88,7 +97,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t bar_tempty = bar_tfull + 16;                // [2]
   const uint32_t tmem_slot = bar_tempty + 16;                // uint32
   const uint32_t stage0 = base + TC_HEADER_BYTES;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (base - raw) + (tmem_slot - base));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -116,66 +125,86 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1;
+  int t0, t1;
+  tile_range(p, t0, t1);
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // ===================================== TMA producer (one elected thread) ================
+    if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        const int ix_base = t.ox0 * p.stride - p.pad, iy_base = t.oy0 * p.stride - p.pad;
+      TileWalk w;
+      w.init(p, t0);
+      for (int tile = t0; tile < t1; ++tile, w.next(p)) {
+        const int m0 = (w.tx + p.tiles_x * (w.ty + p.tiles_y * w.tn)) * 128;            // rows mode (tiles_y == 1)
+        const int ix_base = w.tx * p.bw * p.stride - p.pad, iy_base = w.ty * p.bh * p.stride - p.pad, n0 = w.tn * p.bn;
+        const int nb0 = w.n_tile * p.BN;
+        int r = 0, sx = 0, cc = 0, kcol = 0;       // filter tap (r, sx), channel chunk inside the tap, B column
         for (int c0 = 0; c0 < p.num_chunks; c0 += p.cps) {
           ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const int nc = min(p.cps, p.num_chunks - c0);
           const uint32_t full = bar_full + 8 * stage;
           ptx::mbar_arrive_expect_tx(full, (uint32_t)(nc * p.tx_bytes_per_chunk));
-          const uint32_t a_dst = stage0 + stage * p.stage_bytes;
-          const uint32_t b_dst = a_dst + TC_A_STAGE_BYTES;
+          uint32_t a_dst = stage0 + stage * p.stage_bytes;
+          uint32_t b_dst = a_dst + TC_A_STAGE_BYTES;
           for (int j = 0; j < nc; ++j) {
-            const int chunk = c0 + j;
-            if (p.mode == 1) {
-              const int tap = chunk / p.cpt;
-              const int ci0 = (chunk - tap * p.cpt) * p.kb;
-              const int r = tap / p.KW, s = tap - r * p.KW;
-              ptx::tma_load_4d(&mapA, full, a_dst + j * p.a_chunk_bytes, ci0, ix_base + s, iy_base + r, t.n0);
-            } else {
-              ptx::tma_load_2d(&mapA, full, a_dst + j * p.a_chunk_bytes, chunk * p.kb, t.m0);
+            if (p.mode == 1) ptx::tma_load_4d(&mapA, full, a_dst, cc * p.kb, ix_base + sx, iy_base + r, n0);
+            else ptx::tma_load_2d(&mapA, full, a_dst, kcol, m0);
+            ptx::tma_load_2d(&mapB, full, b_dst, kcol, nb0);
+            a_dst += p.a_chunk_bytes;
+            b_dst += p.b_chunk_bytes;
+            kcol += p.kb;
+            if (++cc == p.cpt) {
+              cc = 0;
+              if (++sx == p.KW) { sx = 0; ++r; }
             }
-            ptx::tma_load_2d(&mapB, full, b_dst + j * p.b_chunk_bytes, chunk * p.kb, t.n_tile * p.BN);
           }
           if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      uint32_t it = 0;
-      const int ksteps = p.kb >> 4;  // UMMA_K = 16 elements = 32 bytes inside the swizzled row
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-        ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+    // ===================================== MMA issuer ========================================
+    // The whole warp walks the pipeline (uniform control flow); one elected lane issues the tcgen05 ops.
+    // A full stage is always 4 MMAs of K = 16: (64 / kb) chunks x (kb / 16) steps.
+    uint32_t a_off[4], b_off[4];
+    {
+      const int ksteps = p.kb >> 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = i / ksteps, k = i - j * ksteps;
+        a_off[i] = (uint32_t)(j * p.a_chunk_bytes + 32 * k) >> 4;
+        b_off[i] = (uint32_t)(j * p.b_chunk_bytes + 32 * k) >> 4;
+      }
+    }
+    const int mma_per_chunk = p.kb >> 4;
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = t0; tile < t1; ++tile, ++it) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * acc_stride;
+      uint32_t accumulate = 0;
+      for (int c0 = 0; c0 < p.num_chunks; c0 += p.cps) {
+        ptx::mbar_wait(bar_full + 8 * stage, phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * acc_stride;
-        uint32_t accumulate = 0;
-        for (int c0 = 0; c0 < p.num_chunks; c0 += p.cps) {
-          ptx::mbar_wait(bar_full + 8 * stage, phase);
-          ptx::tc_fence_after();
-          const int nc = min(p.cps, p.num_chunks - c0);
+        const int nmma = min(p.cps, p.num_chunks - c0) * mma_per_chunk;
+        const bool last = c0 + p.cps >= p.num_chunks;
+        if (ptx::elect_one()) {
           const uint32_t a_src = stage0 + stage * p.stage_bytes;
-          const uint32_t b_src = a_src + TC_A_STAGE_BYTES;
-          for (int j = 0; j < nc; ++j) {
-            const uint32_t a_addr = a_src + j * p.a_chunk_bytes, b_addr = b_src + j * p.b_chunk_bytes;
-            for (int k = 0; k < ksteps; ++k) {
-              ptx::umma_f16(d_tmem, make_desc(a_addr + 32 * k, p.desc_hi), make_desc(b_addr + 32 * k, p.desc_hi), p.idesc, accumulate);
+          const uint64_t a_desc = make_desc(a_src, p.desc_hi), b_desc = make_desc(a_src + TC_A_STAGE_BYTES, p.desc_hi);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < nmma) {
+              ptx::umma_f16(d_tmem, a_desc + a_off[i], b_desc + b_off[i], p.idesc, accumulate);
               accumulate = 1;
             }
           }
-          ptx::umma_commit(bar_empty + 8 * stage);  // smem slot reusable once these MMAs have read it
-          if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1u; }
+          ptx::umma_commit(bar_empty + 8 * stage);      // smem slot reusable once these MMAs have read it
+          if (last) ptx::umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
         }
-        ptx::umma_commit(bar_tfull + 8 * acc);      // accumulator complete -> epilogue
+        __syncwarp();
+        accumulate = 1;
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
@@ -191,24 +220,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int ngroups = (cend - cbeg + 31) / 32;
     const TO* res = reinterpret_cast<const TO*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
+    // tile-invariant position of this thread's row inside the output-pixel box
+    const int bx = row % p.bw;
+    const int by = (row / p.bw) % p.bh, bi = row / (p.bw * p.bh);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    TileWalk w;
+    w.init(p, t0);
+    for (int tile = t0; tile < t1; ++tile, ++it, w.next(p)) {
       const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-      const TileCoord t = decode_tile(p, tile);
       long long orow;  // output row (pixel) index, -1 when this tile row is padding
       if (p.mode == 1) {
-        const int ix = row % p.bw;
-        const int r2 = row / p.bw;
-        const int iy = r2 % p.bh, in_ = r2 / p.bh;
-        const int ox = t.ox0 + ix, oy = t.oy0 + iy, n = t.n0 + in_;
-        const bool ok = in_ < p.bn && ox < p.Wo && oy < p.Ho && n < p.Nimg;
+        const int ox = w.tx * p.bw + bx, oy = w.ty * p.bh + by, n = w.tn * p.bn + bi;
+        const bool ok = bi < p.bn && ox < p.Wo && oy < p.Ho && n < p.Nimg;
         orow = ok ? ((long long)n * p.Ho + oy) * p.Wo + ox : -1;
       } else {
-        orow = (t.m0 + row < p.M) ? (long long)(t.m0 + row) : -1;
+        const int m = w.tx * 128 + row;
+        orow = m < p.M ? (long long)m : -1;
       }
       const bool live = orow >= 0;
       const bool has_res = live && res != nullptr;
-      const int ncol0 = t.n_tile * p.BN;
+      const int ncol0 = w.n_tile * p.BN;
       const size_t off0 = (size_t)(live ? orow : 0) * p.Cout + ncol0;
       const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
 

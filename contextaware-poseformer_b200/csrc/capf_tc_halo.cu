@@ -29,6 +29,7 @@ struct HaloP {
   int C, Cout;              // Cout == UMMA N (single column tile)
   int H, W, Nimg;           // stride 1, pad 1: output size == input size
   int Wp;                   // padded row pitch in pixels = W + 1
+  uint32_t wp_magic;        // ceil(2^32 / Wp)
   int bh;                   // band height (output rows per band)
   int bands_per_img, num_bands;
   int P_alloc;              // pixels per chunk plane of one halo buffer
@@ -36,7 +37,7 @@ struct HaloP {
   int kb, cpt;              // weight chunk width (elements) and chunks per tap, as in capf_tc.cu
   int b_chunk_bytes, b_bytes;
   int halo_bytes;           // one halo buffer
-  int acc_stages, tmem_cols, acc_stride;
+  int acc_stages, acc_shift, tmem_cols, acc_stride;   // acc_stages = 1 << acc_shift accumulators in flight
   uint32_t idesc, b_desc_hi, a_desc_hi;
   int act;
   const void* x;
@@ -50,9 +51,15 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <typename TI, typename TO>
+// pix / Wp without a divide: magic = ceil(2^32 / Wp), exact for the pixel counts of one band (< 2^16)
+__device__ __forceinline__ int div_wp(int v, uint32_t magic) { return (int)__umulhi((uint32_t)v, magic); }
+
+template <int C, typename TI, typename TO>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
+  constexpr int KSTEPS = C / 16;                                   // 16-channel MMA steps per filter tap
+  constexpr int KB = C % 64 == 0 ? 64 : C % 32 == 0 ? 32 : 16;     // weight chunk width (elements)
+  constexpr int KPC = KB / 16, CPT = C / KB, CHUNKS = C / 8;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -90,80 +97,85 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // contiguous band range of this CTA; (image, band-in-image) advance by carry, never by division
+  const int band0 = (int)(((long long)p.num_bands * blockIdx.x) / gridDim.x);
+  const int band1 = (int)(((long long)p.num_bands * (blockIdx.x + 1)) / gridDim.x);
+  const int img0 = band0 / p.bands_per_img, bin0 = band0 - img0 * p.bands_per_img;
+
   if (warp == 0) {
     // ===================================== resident weights ==================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar_b, (uint32_t)p.b_bytes);
-      const int n_chunks = 9 * p.cpt;
-      for (int c = 0; c < n_chunks; ++c) ptx::tma_load_2d(&mapB, bar_b, smem_b + c * p.b_chunk_bytes, c * p.kb, 0);
+      for (int c = 0; c < 9 * CPT; ++c) ptx::tma_load_2d(&mapB, bar_b, smem_b + c * p.b_chunk_bytes, c * KB, 0);
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      ptx::mbar_wait(bar_b, 0);
+    ptx::mbar_wait(bar_b, 0);
+    ptx::tc_fence_after();
+    const uint32_t lbo_field = (uint32_t)p.P_alloc;      // chunk-plane pitch = P_alloc * 16 bytes, >> 4
+    const uint64_t b_desc0 = tc_make_desc(smem_b, 1u, p.b_desc_hi);
+    const uint32_t b_chunk16 = (uint32_t)p.b_chunk_bytes >> 4;
+    uint32_t it = 0, k = 0;
+    int bin = bin0;
+    for (int band = band0; band < band1; ++band, ++k) {
+      const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
+      const int bh_eff = min(p.bh, p.H - bin * p.bh);
+      const int n_sub = (bh_eff * p.Wp + 127) >> 7;
+      if (++bin == p.bands_per_img) bin = 0;
+      ptx::mbar_wait(bar_hfull + 8 * buf, hph);
       ptx::tc_fence_after();
-      const uint32_t lbo_field = (uint32_t)p.P_alloc;      // chunk-plane pitch = P_alloc * 16 bytes, >> 4
-      const int ksteps = p.C >> 4, kpc = p.kb >> 4;        // 16-channel MMA steps per tap; steps per weight chunk
-      uint32_t it = 0, k = 0;
-      for (int bi = blockIdx.x; bi < p.num_bands; bi += gridDim.x, ++k) {
-        const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
-        const int y0 = (bi % p.bands_per_img) * p.bh;
-        const int bh_eff = min(p.bh, p.H - y0);
-        const int n_sub = (bh_eff * p.Wp + 127) >> 7;
-        ptx::mbar_wait(bar_hfull + 8 * buf, hph);
+      const uint64_t a_desc0 = tc_make_desc(smem_halo + buf * p.halo_bytes, lbo_field, p.a_desc_hi);
+      for (int j = 0; j < n_sub; ++j, ++it) {
+        const uint32_t acc = it & (uint32_t)(p.acc_stages - 1), aph = (it >> p.acc_shift) & 1u;
+        ptx::mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t halo = smem_halo + buf * p.halo_bytes;
-        for (int j = 0; j < n_sub; ++j, ++it) {
-          const uint32_t acc = it % (uint32_t)p.acc_stages, aph = (it / (uint32_t)p.acc_stages) & 1u;
-          ptx::mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
-          ptx::tc_fence_after();
+        if (ptx::elect_one()) {
           const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-          uint32_t accumulate = 0;
-#pragma unroll 1
+          // descriptor start-address field counts 16-byte units == halo pixels
+          const uint64_t a_sub = a_desc0 + (uint32_t)(j * 128);
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int r = tap / 3, s = tap - 3 * r;
-            const uint32_t a_pix = halo + (uint32_t)(j * 128 + r * p.Wp + s) * 16u;
-            for (int kk = 0; kk < ksteps; ++kk) {
-              const uint32_t a_addr = a_pix + (uint32_t)(2 * kk) * (uint32_t)p.P_alloc * 16u;
-              const uint32_t b_addr = smem_b + (uint32_t)(tap * p.cpt + kk / kpc) * p.b_chunk_bytes + (uint32_t)(kk % kpc) * 32u;
-              ptx::umma_f16(d_tmem, tc_make_desc(a_addr, lbo_field, p.a_desc_hi), tc_make_desc(b_addr, 1u, p.b_desc_hi), p.idesc, accumulate);
-              accumulate = 1;
+            const uint64_t a_tap = a_sub + (uint32_t)((tap / 3) * p.Wp + (tap % 3));
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const uint64_t a_d = a_tap + (uint32_t)(2 * kk) * (uint32_t)p.P_alloc;
+              const uint64_t b_d = b_desc0 + (uint32_t)(tap * CPT + kk / KPC) * b_chunk16 + (uint32_t)((kk % KPC) * 2);
+              ptx::umma_f16(d_tmem, a_d, b_d, p.idesc, (tap | kk) ? 1u : 0u);
             }
           }
           ptx::umma_commit(bar_tfull + 8 * acc);
+          if (j == n_sub - 1) ptx::umma_commit(bar_hempty + 8 * buf);   // band fully read -> loaders may refill
         }
-        ptx::umma_commit(bar_hempty + 8 * buf);     // band fully read by the tensor pipe -> loaders may refill
+        __syncwarp();
       }
     }
   } else if (warp >= 12) {
     // ===================================== halo loaders =====================================
     const int tl = threadIdx.x - 12 * 32;            // 0..127
     const TI* x = reinterpret_cast<const TI*>(p.x);
-    const int cshift = p.chunks == 8 ? 3 : p.chunks == 4 ? 2 : p.chunks == 2 ? 1 : -1;
     uint32_t k = 0;
-    for (int bi = blockIdx.x; bi < p.num_bands; bi += gridDim.x, ++k) {
+    int img = img0, bin = bin0;
+    for (int band = band0; band < band1; ++band, ++k) {
       const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
-      const int n = bi / p.bands_per_img;
-      const int y0 = (bi - n * p.bands_per_img) * p.bh;
+      const int y0 = bin * p.bh;
       const int bh_eff = min(p.bh, p.H - y0);
-      const int npix = (bh_eff + 2) * p.Wp + 1;      // + the zero pixel right of the last row
-      const int total = npix * p.chunks;
+      const int total = ((bh_eff + 2) * p.Wp + 1) * CHUNKS;     // + the zero pixel right of the last row
       ptx::mbar_wait(bar_hempty + 8 * buf, hph ^ 1u);
       const uint32_t halo = smem_halo + buf * p.halo_bytes;
-      const TI* img = x + (size_t)n * p.H * p.W * p.C;
+      const TI* imgp = x + (size_t)img * p.H * p.W * C;
+#pragma unroll 4
       for (int t = tl; t < total; t += 128) {
-        int pix, c;
-        if (cshift >= 0) { pix = t >> cshift; c = t & (p.chunks - 1); }
-        else { pix = t / p.chunks; c = t - pix * p.chunks; }
-        const int hy = pix / p.Wp, hx = pix - hy * p.Wp;
+        const int pix = t / CHUNKS, c = t % CHUNKS;              // CHUNKS is a compile-time constant
+        const int hy = div_wp(pix, p.wp_magic), hx = pix - hy * p.Wp;
         const int iy = y0 - 1 + hy, ix = hx - 1;
         const bool ok = hx > 0 && iy >= 0 && iy < p.H && hy < bh_eff + 2;
-        const TI* src = ok ? img + ((size_t)iy * p.W + ix) * p.C + c * 8 : x;
+        const TI* src = ok ? imgp + ((size_t)iy * p.W + ix) * C + c * 8 : x;
         cp_async16_zfill(halo + ((uint32_t)c * (uint32_t)p.P_alloc + (uint32_t)pix) * 16u, src, ok ? 16u : 0u);
       }
       cp_async_wait_all();
       ptx::fence_proxy_async();                       // generic-proxy writes -> visible to the tensor (async) proxy
       ptx::mbar_arrive(bar_hfull + 8 * buf);
+      if (++bin == p.bands_per_img) { bin = 0; ++img; }
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =========================================
@@ -174,19 +186,21 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
     const TO* res = reinterpret_cast<const TO*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
     uint32_t it = 0;
-    for (int bi = blockIdx.x; bi < p.num_bands; bi += gridDim.x) {
-      const int n = bi / p.bands_per_img;
-      const int y0 = (bi - n * p.bands_per_img) * p.bh;
+    int img = img0, bin = bin0;
+    for (int band = band0; band < band1; ++band) {
+      const int y0 = bin * p.bh;
       const int bh_eff = min(p.bh, p.H - y0);
       const int n_sub = (bh_eff * p.Wp + 127) >> 7;
+      const size_t img_row0 = (size_t)img * p.H + y0;
+      if (++bin == p.bands_per_img) { bin = 0; ++img; }
       for (int j = 0; j < n_sub; ++j, ++it) {
         if ((int)(it & 1u) != grp) continue;
-        const uint32_t acc = it % (uint32_t)p.acc_stages, aph = (it / (uint32_t)p.acc_stages) & 1u;
+        const uint32_t acc = it & (uint32_t)(p.acc_stages - 1), aph = (it >> p.acc_shift) & 1u;
         const int mp = j * 128 + row;
-        const int iy = mp / p.Wp, ix = mp - iy * p.Wp;
+        const int iy = div_wp(mp, p.wp_magic), ix = mp - iy * p.Wp;
         const bool live = ix < p.W && iy < bh_eff;
         const bool has_res = live && res != nullptr;
-        const size_t off0 = live ? (((size_t)n * p.H + (y0 + iy)) * p.W + ix) * p.Cout : 0;
+        const size_t off0 = live ? ((img_row0 + iy) * p.W + ix) * p.Cout : 0;
         const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
 
         Vec16<TO> r0[2], r1[2];
@@ -240,9 +254,10 @@ struct TcHaloState {
 static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   const int N = op.i[0], H = op.i[1], W = op.i[2], C = op.i[3], Cout = op.i[4];
   if (op.i[5] != 3 || op.i[6] != 3 || op.i[7] != 1 || op.i[8] != 1) return 0;
-  if (C % 16 || Cout % 16 || Cout > 256 || C > 256) return 0;
+  if ((C != 16 && C != 32 && C != 48 && C != 64) || Cout % 16 || Cout > 256) return 0;   // instantiated widths
   memset(&p, 0, sizeof(p));
   p.C = C; p.Cout = Cout; p.H = H; p.W = W; p.Nimg = N; p.Wp = W + 1;
+  p.wp_magic = (uint32_t)(((1ull << 32) + p.Wp - 1) / p.Wp);
   p.chunks = C / 8;
   p.kb = C % 64 == 0 ? 64 : C % 32 == 0 ? 32 : 16;
   p.cpt = C / p.kb;
@@ -271,8 +286,8 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   const int n_sub_full = (p.bh * p.Wp + 127) / 128;
   p.P_alloc = (n_sub_full * 128 + 2 * p.Wp + 2 + 7) & ~7;
   p.halo_bytes = p.P_alloc * C * 2;
-  p.acc_stages = 512 / Cout < HALO_MAX_ACC ? 512 / Cout : HALO_MAX_ACC;
-  if (p.acc_stages < 2) return 0;
+  p.acc_shift = 4 * Cout <= 512 ? 2 : 1;
+  p.acc_stages = 1 << p.acc_shift;
   int cols = 32;
   while (cols < p.acc_stages * Cout) cols <<= 1;
   p.tmem_cols = cols;
@@ -320,16 +335,27 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
   return CAPF_OK;
 }
 
-template <typename TI, typename TO>
-static int halo_launch_typed(const TcHaloState* s, cudaStream_t st) {
+template <int C, typename TI, typename TO>
+static int halo_launch_c(const TcHaloState* s, cudaStream_t st) {
   static bool opted = false;
   if (!opted) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv3_halo_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv3_halo_kernel<C, TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_conv3_halo_kernel smem opt-in: %s", cudaGetErrorString(e));
     opted = true;
   }
-  tc_conv3_halo_kernel<TI, TO><<<s->grid, HALO_THREADS, s->smem_bytes, st>>>(s->mapB, s->p);
+  tc_conv3_halo_kernel<C, TI, TO><<<s->grid, HALO_THREADS, s->smem_bytes, st>>>(s->mapB, s->p);
   return check_launch("tc_conv3_halo_kernel");
+}
+
+template <typename TI, typename TO>
+static int halo_launch_typed(const TcHaloState* s, cudaStream_t st) {
+  switch (s->p.C) {
+    case 16: return halo_launch_c<16, TI, TO>(s, st);
+    case 32: return halo_launch_c<32, TI, TO>(s, st);
+    case 48: return halo_launch_c<48, TI, TO>(s, st);
+    case 64: return halo_launch_c<64, TI, TO>(s, st);
+    default: return set_error(CAPF_ERR_UNSUPPORTED, "halo conv: channel count not instantiated");
+  }
 }
 
 int tc_halo_launch(const TcHaloState* s, cudaStream_t st) {
