@@ -12,9 +12,9 @@
 // zero column are computed and dropped (1 / Wp of the tensor work).  The folded weights ([Cout][9 * Cin], swizzled
 // K-major chunks exactly as in capf_tc.cu) are fetched once per CTA by TMA and stay resident.
 //
-// Roles (512 threads): warp 0 = weight TMA, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator,
-// warps 4..11 = two 4-warp epilogue groups (alternate 128-row sub-tiles), warps 12..15 = halo loaders (cp.async,
-// zero fill outside the image).  Halo bands are double buffered; up to four TMEM accumulators are in flight.
+// Roles (512 threads): warp 0 = TMA producer (weights once, then one box per 8-channel plane per band; out-of-image
+// elements are zero-filled by TMA), warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4..15 = three 4-warp
+// epilogue groups taking 128-row sub-tiles round-robin.  Halo bands are double buffered; four TMEM accumulators.
 #include <new>
 
 #include "capf_tc.cuh"
@@ -24,6 +24,7 @@ namespace capf {
 constexpr int HALO_THREADS = 512;
 constexpr int HALO_HEADER_BYTES = 1024;
 constexpr int HALO_MAX_ACC = 4;
+constexpr int HALO_EPI_GROUPS = 3;         // warps 4..15
 
 struct HaloP {
   int C, Cout;              // Cout == UMMA N (single column tile)
@@ -37,6 +38,7 @@ struct HaloP {
   int kb, cpt;              // weight chunk width (elements) and chunks per tap, as in capf_tc.cu
   int b_chunk_bytes, b_bytes;
   int halo_bytes;           // one halo buffer
+  int plane_tx_bytes;       // bytes one TMA box (one 8-channel plane of a band) delivers
   int acc_stages, acc_shift, tmem_cols, acc_stride;   // acc_stages = 1 << acc_shift accumulators in flight
   uint32_t idesc, b_desc_hi, a_desc_hi;
   int act;
@@ -46,17 +48,41 @@ struct HaloP {
   void* out;
 };
 
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// pix / Wp without a divide: magic = ceil(2^32 / Wp), exact for the pixel counts of one band (< 2^16)
+// v / Wp without a divide: magic = ceil(2^32 / Wp), exact for the pixel counts of one band (< 2^16)
 __device__ __forceinline__ int div_wp(int v, uint32_t magic) { return (int)__umulhi((uint32_t)v, magic); }
+
+// Walks the (band, 128-row sub-tile) sequence of one CTA in issue order.  Every role steps through the same sequence,
+// which is what keeps the accumulator-stage / phase bookkeeping implicit.
+struct HaloWalk {
+  int band, band_end, img, bin, j, n_sub, bh_eff, y0;
+  uint32_t it;
+  __device__ __forceinline__ void load_band(const HaloP& p) {
+    y0 = bin * p.bh;
+    bh_eff = min(p.bh, p.H - y0);
+    n_sub = (bh_eff * p.Wp + 127) >> 7;
+  }
+  __device__ __forceinline__ void init(const HaloP& p, int b0, int b1) {
+    band = b0; band_end = b1;
+    img = b0 / p.bands_per_img;
+    bin = b0 - img * p.bands_per_img;
+    j = 0; it = 0;
+    load_band(p);
+  }
+  __device__ __forceinline__ bool valid() const { return band < band_end; }
+  __device__ __forceinline__ void step(const HaloP& p) {
+    ++it;
+    if (++j == n_sub) {
+      j = 0;
+      ++band;
+      if (++bin == p.bands_per_img) { bin = 0; ++img; }
+      load_band(p);
+    }
+  }
+};
 
 template <int C, typename TI, typename TO>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
-tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
+tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const HaloP p) {
   constexpr int KSTEPS = C / 16;                                   // 16-channel MMA steps per filter tap
   constexpr int KB = C % 64 == 0 ? 64 : C % 32 == 0 ? 32 : 16;     // weight chunk width (elements)
   constexpr int KPC = KB / 16, CPT = C / KB, CHUNKS = C / 8;
@@ -64,7 +90,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t bar_b = base;                       // weights landed
-  const uint32_t bar_hfull = base + 8;               // [2] halo buffer filled   (128 loader arrivals)
+  const uint32_t bar_hfull = base + 8;               // [2] halo buffer filled   (TMA transaction bytes)
   const uint32_t bar_hempty = base + 24;             // [2] halo buffer consumed (tcgen05.commit)
   const uint32_t bar_tfull = base + 40;              // [HALO_MAX_ACC] accumulator complete
   const uint32_t bar_tempty = base + 40 + 8 * HALO_MAX_ACC;  // [HALO_MAX_ACC] accumulator drained (128 arrivals)
@@ -75,11 +101,14 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&mapB);
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&mapA);
+    ptx::prefetch_tmap(&mapB);
+  }
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(bar_b, 1);
     for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(bar_hfull + 8 * b, 128);
+      ptx::mbar_init(bar_hfull + 8 * b, 1);
       ptx::mbar_init(bar_hempty + 8 * b, 1);
     }
     for (int a = 0; a < HALO_MAX_ACC; ++a) {
@@ -97,16 +126,31 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // contiguous band range of this CTA; (image, band-in-image) advance by carry, never by division
+  // contiguous band range of this CTA
   const int band0 = (int)(((long long)p.num_bands * blockIdx.x) / gridDim.x);
   const int band1 = (int)(((long long)p.num_bands * (blockIdx.x + 1)) / gridDim.x);
-  const int img0 = band0 / p.bands_per_img, bin0 = band0 - img0 * p.bands_per_img;
 
   if (warp == 0) {
-    // ===================================== resident weights ==================================
+    // ===================================== TMA producer ======================================
+    // weights once; then per band one box per 8-channel plane: {8 ch, Wp pixels from x = -1, bh + 3 rows from y0 - 1}.
+    // Out-of-image elements arrive as zeros = the convolution padding (and the shared zero column).
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar_b, (uint32_t)p.b_bytes);
       for (int c = 0; c < 9 * CPT; ++c) ptx::tma_load_2d(&mapB, bar_b, smem_b + c * p.b_chunk_bytes, c * KB, 0);
+      const int img0 = band0 / p.bands_per_img;
+      int img = img0, bin = band0 - img0 * p.bands_per_img;
+      uint32_t k = 0;
+      for (int band = band0; band < band1; ++band, ++k) {
+        const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
+        ptx::mbar_wait(bar_hempty + 8 * buf, hph ^ 1u);
+        const uint32_t full = bar_hfull + 8 * buf;
+        ptx::mbar_arrive_expect_tx(full, (uint32_t)(CHUNKS * p.plane_tx_bytes));
+        const uint32_t halo = smem_halo + buf * p.halo_bytes;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c)
+          ptx::tma_load_4d(&mapA, full, halo + (uint32_t)c * (uint32_t)p.P_alloc * 16u, 8 * c, -1, bin * p.bh - 1, img);
+        if (++bin == p.bands_per_img) { bin = 0; ++img; }
+      }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
@@ -115,18 +159,17 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
     const uint32_t lbo_field = (uint32_t)p.P_alloc;      // chunk-plane pitch = P_alloc * 16 bytes, >> 4
     const uint64_t b_desc0 = tc_make_desc(smem_b, 1u, p.b_desc_hi);
     const uint32_t b_chunk16 = (uint32_t)p.b_chunk_bytes >> 4;
-    uint32_t it = 0, k = 0;
-    int bin = bin0;
-    for (int band = band0; band < band1; ++band, ++k) {
+    HaloWalk w;
+    w.init(p, band0, band1);
+    uint32_t k = 0;
+    while (w.valid()) {
       const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
-      const int bh_eff = min(p.bh, p.H - bin * p.bh);
-      const int n_sub = (bh_eff * p.Wp + 127) >> 7;
-      if (++bin == p.bands_per_img) bin = 0;
       ptx::mbar_wait(bar_hfull + 8 * buf, hph);
       ptx::tc_fence_after();
       const uint64_t a_desc0 = tc_make_desc(smem_halo + buf * p.halo_bytes, lbo_field, p.a_desc_hi);
-      for (int j = 0; j < n_sub; ++j, ++it) {
-        const uint32_t acc = it & (uint32_t)(p.acc_stages - 1), aph = (it >> p.acc_shift) & 1u;
+      const int n_sub = w.n_sub;
+      for (int j = 0; j < n_sub; ++j) {
+        const uint32_t acc = w.it & (uint32_t)(p.acc_stages - 1), aph = (w.it >> p.acc_shift) & 1u;
         ptx::mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -144,96 +187,76 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
             }
           }
           ptx::umma_commit(bar_tfull + 8 * acc);
-          if (j == n_sub - 1) ptx::umma_commit(bar_hempty + 8 * buf);   // band fully read -> loaders may refill
+          if (j == n_sub - 1) ptx::umma_commit(bar_hempty + 8 * buf);   // band fully read -> producer may refill
         }
         __syncwarp();
+        w.step(p);
       }
-    }
-  } else if (warp >= 12) {
-    // ===================================== halo loaders =====================================
-    const int tl = threadIdx.x - 12 * 32;            // 0..127
-    const TI* x = reinterpret_cast<const TI*>(p.x);
-    uint32_t k = 0;
-    int img = img0, bin = bin0;
-    for (int band = band0; band < band1; ++band, ++k) {
-      const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
-      const int y0 = bin * p.bh;
-      const int bh_eff = min(p.bh, p.H - y0);
-      const int total = ((bh_eff + 2) * p.Wp + 1) * CHUNKS;     // + the zero pixel right of the last row
-      ptx::mbar_wait(bar_hempty + 8 * buf, hph ^ 1u);
-      const uint32_t halo = smem_halo + buf * p.halo_bytes;
-      const TI* imgp = x + (size_t)img * p.H * p.W * C;
-#pragma unroll 4
-      for (int t = tl; t < total; t += 128) {
-        const int pix = t / CHUNKS, c = t % CHUNKS;              // CHUNKS is a compile-time constant
-        const int hy = div_wp(pix, p.wp_magic), hx = pix - hy * p.Wp;
-        const int iy = y0 - 1 + hy, ix = hx - 1;
-        const bool ok = hx > 0 && iy >= 0 && iy < p.H && hy < bh_eff + 2;
-        const TI* src = ok ? imgp + ((size_t)iy * p.W + ix) * C + c * 8 : x;
-        cp_async16_zfill(halo + ((uint32_t)c * (uint32_t)p.P_alloc + (uint32_t)pix) * 16u, src, ok ? 16u : 0u);
-      }
-      cp_async_wait_all();
-      ptx::fence_proxy_async();                       // generic-proxy writes -> visible to the tensor (async) proxy
-      ptx::mbar_arrive(bar_hfull + 8 * buf);
-      if (++bin == p.bands_per_img) { bin = 0; ++img; }
+      ++k;
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =========================================
+    // Three 4-warp groups take sub-tiles round-robin.  The residual of a group's NEXT sub-tile is requested before
+    // the current one is finished, so its DRAM latency is covered by a whole sub-tile period.
+    constexpr int NG = HALO_EPI_GROUPS;
     const int q = warp & 3;
-    const int grp = (warp - 4) >> 2;                 // 0 | 1: sub-tiles alternate between the two groups
+    const int grp = (warp - 4) >> 2;
     const int row = q * 32 + lane;
-    const int ngroups = (p.Cout + 31) / 32;
     const TO* res = reinterpret_cast<const TO*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
-    uint32_t it = 0;
-    int img = img0, bin = bin0;
-    for (int band = band0; band < band1; ++band) {
-      const int y0 = bin * p.bh;
-      const int bh_eff = min(p.bh, p.H - y0);
-      const int n_sub = (bh_eff * p.Wp + 127) >> 7;
-      const size_t img_row0 = (size_t)img * p.H + y0;
-      if (++bin == p.bands_per_img) { bin = 0; ++img; }
-      for (int j = 0; j < n_sub; ++j, ++it) {
-        if ((int)(it & 1u) != grp) continue;
-        const uint32_t acc = it & (uint32_t)(p.acc_stages - 1), aph = (it >> p.acc_shift) & 1u;
-        const int mp = j * 128 + row;
-        const int iy = div_wp(mp, p.wp_magic), ix = mp - iy * p.Wp;
-        const bool live = ix < p.W && iy < bh_eff;
-        const bool has_res = live && res != nullptr;
-        const size_t off0 = live ? ((img_row0 + iy) * p.W + ix) * p.Cout : 0;
-        const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
+    const int nv = p.Cout >> 4;                      // 16-column vectors per row (<= 4)
 
-        Vec16<TO> r0[2], r1[2];
-        auto fetch = [&](int g, Vec16<TO> (&r)[2]) {
-          if (has_res) {
-            const int c = 32 * g;
-            r[0].load(res + off0 + c);
-            if (c + 16 < p.Cout) r[1].load(res + off0 + c + 16);
-          }
-        };
-        auto group = [&](int g, const Vec16<TO> (&r)[2], Vec16<TO> (&rnext)[2]) {
-          const int c = 32 * g;
-          const bool two = c + 16 < p.Cout;
+    HaloWalk w;
+    w.init(p, band0, band1);
+    for (int i = 0; i < grp && w.valid(); ++i) w.step(p);
+
+    auto locate = [&](const HaloWalk& t, bool& live, size_t& off0) {
+      const int mp = t.j * 128 + row;
+      const int iy = div_wp(mp, p.wp_magic), ix = mp - iy * p.Wp;
+      live = t.valid() && ix < p.W && iy < t.bh_eff;
+      off0 = live ? (((size_t)t.img * p.H + t.y0 + iy) * p.W + ix) * p.Cout : 0;
+    };
+    Vec16<TO> rcur[4], rnext[4];
+    bool live_n;
+    size_t off_n;
+    locate(w, live_n, off_n);
+    if (res && live_n) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (v < nv) rnext[v].load(res + off_n + 16 * v);
+    }
+    while (w.valid()) {
+      const uint32_t acc = w.it & (uint32_t)(p.acc_stages - 1), aph = (w.it >> p.acc_shift) & 1u;
+      const bool live = live_n;
+      const size_t off0 = off_n;
+      const bool has_res = live && res != nullptr;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) rcur[v] = rnext[v];
+      for (int i = 0; i < NG && w.valid(); ++i) w.step(p);
+      locate(w, live_n, off_n);
+      if (res && live_n) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (v < nv) rnext[v].load(res + off_n + 16 * v);
+      }
+      const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
+      ptx::mbar_wait(bar_tfull + 8 * acc, aph);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int v = 0; v < 4; v += 2) {
+        if (v < nv) {
           uint32_t a0[16], a1[16];
-          ptx::tmem_ld16(taddr + (uint32_t)c, a0);
-          if (two) ptx::tmem_ld16(taddr + (uint32_t)(c + 16), a1);
-          if (g + 1 < ngroups) fetch(g + 1, rnext);
+          ptx::tmem_ld16(taddr + (uint32_t)(16 * v), a0);
+          if (v + 1 < nv) ptx::tmem_ld16(taddr + (uint32_t)(16 * v + 16), a1);
           ptx::tmem_ld_wait();
           if (live) {
-            finish16<TO>(p.bias, p.act, a0, r[0], has_res, c, out + off0 + c);
-            if (two) finish16<TO>(p.bias, p.act, a1, r[1], has_res, c + 16, out + off0 + c + 16);
+            finish16<TO>(p.bias, p.act, a0, rcur[v], has_res, 16 * v, out + off0 + 16 * v);
+            if (v + 1 < nv) finish16<TO>(p.bias, p.act, a1, rcur[v + 1], has_res, 16 * v + 16, out + off0 + 16 * v + 16);
           }
-        };
-        fetch(0, r0);
-        ptx::mbar_wait(bar_tfull + 8 * acc, aph);
-        ptx::tc_fence_after();
-        for (int g = 0; g < ngroups; g += 2) {
-          group(g, r0, r1);
-          if (g + 1 < ngroups) group(g + 1, r1, r0);
         }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(bar_tempty + 8 * acc);
       }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_tempty + 8 * acc);
     }
   }
 
@@ -246,15 +269,24 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapB, const HaloP p) {
 // host side
 // =======================================================================================================
 struct TcHaloState {
-  CUtensorMap mapB;
+  CUtensorMap mapA, mapB;
   HaloP p;
   int grid, smem_bytes, dtype_in, dtype_out;
 };
 
+// pixels of one 8-channel plane: the TMA box ((bh + 3) rows of Wp) and the furthest tap read of the last sub-tile
+static int halo_plane_pixels(int bh, int Wp) {
+  const int n_sub = (bh * Wp + 127) / 128;
+  const int reach = n_sub * 128 + 2 * Wp + 2, box = (bh + 3) * Wp;
+  return ((reach > box ? reach : box) + 7) & ~7;
+}
+
 static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   const int N = op.i[0], H = op.i[1], W = op.i[2], C = op.i[3], Cout = op.i[4];
   if (op.i[5] != 3 || op.i[6] != 3 || op.i[7] != 1 || op.i[8] != 1) return 0;
-  if ((C != 16 && C != 32 && C != 48 && C != 64) || Cout % 16 || Cout > 256) return 0;   // instantiated widths
+  if (op.dtype_out != op.dtype_in) return 0;      // 16-bit activations in and out (the backbone case)
+  if ((C != 16 && C != 32 && C != 48 && C != 64) || Cout % 16 || Cout > 64) return 0;   // instantiated widths; <= 4 residual vectors
+  if (W + 1 > 256 || N <= 0 || H <= 0 || W <= 0) return 0;
   memset(&p, 0, sizeof(p));
   p.C = C; p.Cout = Cout; p.H = H; p.W = W; p.Nimg = N; p.Wp = W + 1;
   p.wp_magic = (uint32_t)(((1ull << 32) + p.Wp - 1) / p.Wp);
@@ -270,9 +302,9 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   long long best_tiles = 1ll << 60;
   for (int bh = 1; bh <= H; ++bh) {
     const int n_sub_full = (bh * p.Wp + 127) / 128;
-    const int P_alloc = (n_sub_full * 128 + 2 * p.Wp + 2 + 7) & ~7;
+    const int P_alloc = halo_plane_pixels(bh, p.Wp);
     const long long halo_bytes = (long long)P_alloc * C * 2;
-    if (P_alloc > 16383 || 2 * halo_bytes > budget) break;
+    if (P_alloc > 16383 || bh + 3 > 256 || 2 * halo_bytes > budget) break;
     const int full = H / bh, rem = H - full * bh;
     long long tiles = (long long)full * n_sub_full + (rem ? (rem * p.Wp + 127) / 128 : 0);
     if (tiles < best_tiles || (tiles == best_tiles && bh > best_bh)) { best_tiles = tiles; best_bh = bh; }
@@ -284,8 +316,10 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   if (nb >= (1ll << 31)) return 0;
   p.num_bands = (int)nb;
   const int n_sub_full = (p.bh * p.Wp + 127) / 128;
-  p.P_alloc = (n_sub_full * 128 + 2 * p.Wp + 2 + 7) & ~7;
+  (void)n_sub_full;
+  p.P_alloc = halo_plane_pixels(p.bh, p.Wp);
   p.halo_bytes = p.P_alloc * C * 2;
+  p.plane_tx_bytes = (p.bh + 3) * p.Wp * 16;
   p.acc_shift = 4 * Cout <= 512 ? 2 : 1;
   p.acc_stages = 1 << p.acc_shift;
   int cols = 32;
@@ -330,6 +364,15 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
   cuuint32_t es[2] = {1, 1};
   e = tc_encode_map(&s->mapB, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, op.in[1], dims, strides, box,
                     es, p.kb * 2, "B weights (halo)");
+  if (!e) {
+    // 8-channel planes of the NHWC input: box {8, Wp, bh + 3, 1}, no swizzle (16-byte rows = UMMA core-matrix rows)
+    cuuint64_t adims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.Nimg};
+    cuuint64_t astr[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
+    cuuint32_t abox[4] = {8, (cuuint32_t)p.Wp, (cuuint32_t)(p.bh + 3), 1};
+    cuuint32_t aes[4] = {1, 1, 1, 1};
+    e = tc_encode_map(&s->mapA, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, op.in[0], adims, astr, abox,
+                      aes, 0, "A halo planes");
+  }
   if (e) { delete s; return e; }
   *out = s;
   return CAPF_OK;
@@ -343,7 +386,7 @@ static int halo_launch_c(const TcHaloState* s, cudaStream_t st) {
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_conv3_halo_kernel smem opt-in: %s", cudaGetErrorString(e));
     opted = true;
   }
-  tc_conv3_halo_kernel<C, TI, TO><<<s->grid, HALO_THREADS, s->smem_bytes, st>>>(s->mapB, s->p);
+  tc_conv3_halo_kernel<C, TI, TO><<<s->grid, HALO_THREADS, s->smem_bytes, st>>>(s->mapA, s->mapB, s->p);
   return check_launch("tc_conv3_halo_kernel");
 }
 
@@ -361,8 +404,6 @@ static int halo_launch_typed(const TcHaloState* s, cudaStream_t st) {
 int tc_halo_launch(const TcHaloState* s, cudaStream_t st) {
   if (s->dtype_in == CAPF_F16 && s->dtype_out == CAPF_F16) return halo_launch_typed<__half, __half>(s, st);
   if (s->dtype_in == CAPF_BF16 && s->dtype_out == CAPF_BF16) return halo_launch_typed<__nv_bfloat16, __nv_bfloat16>(s, st);
-  if (s->dtype_in == CAPF_F16 && s->dtype_out == CAPF_F32) return halo_launch_typed<__half, float>(s, st);
-  if (s->dtype_in == CAPF_BF16 && s->dtype_out == CAPF_F32) return halo_launch_typed<__nv_bfloat16, float>(s, st);
   return set_error(CAPF_ERR_UNSUPPORTED, "halo conv: dtype combination");
 }
 
