@@ -258,10 +258,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         ptx::tmem_ld16(taddr + (uint32_t)c, a0);
         if (two) ptx::tmem_ld16(taddr + (uint32_t)(c + 16), a1);
         if (g + 1 < ngroups) fetch(g + 1, rnext);
+        Bias16 b0, b1;
+        b0.load(p.bias, ncol0 + c);
+        b1.load(p.bias, ncol0 + (two ? c + 16 : c));
         ptx::tmem_ld_wait();
         if (live) {
-          finish16<TO>(p.bias, p.act, a0, r[0], has_res, ncol0 + c, out + off0 + c);
-          if (two) finish16<TO>(p.bias, p.act, a1, r[1], has_res, ncol0 + c + 16, out + off0 + c + 16);
+          finish16<TO>(b0, p.act, a0, r[0], has_res, out + off0 + c);
+          if (two) finish16<TO>(b1, p.act, a1, r[1], has_res, out + off0 + c + 16);
         }
       };
       fetch(0, r0);                                  // independent of the MMAs: issue before waiting for them
@@ -379,7 +382,7 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
     *out = s;
     return CAPF_OK;
   }
-  if (op.i[13] == 2) { delete s; return set_error(CAPF_ERR_UNSUPPORTED, "tc conv: halo variant requested but not applicable"); }
+  if (op.i[13] >= 2) { delete s; return set_error(CAPF_ERR_UNSUPPORTED, "tc conv: halo variant requested but not applicable"); }
   TcP& p = s->p;
   memset(&p, 0, sizeof(p));
   const bool rows = (g.KH == 1 && g.KW == 1 && g.stride == 1 && g.pad == 0);

@@ -98,6 +98,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the two 64-bit shared-memory descriptors given as (lo, hi) words: the hi words are kernel constants and
+// the lo words advance by plain 32-bit adds, which keeps the single issuing thread's instruction count down.
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once every tcgen05 op previously issued by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -125,6 +138,9 @@ __host__ __device__ inline uint32_t tc_desc_hi(int swizzle_bytes, int sbo_bytes)
 }
 // Low word: start address >> 4 in [0,14), leading byte offset >> 4 in [16,30) (distance between the two 16-byte
 // K slices of one MMA in the un-swizzled layout; ignored, canonical value 1, in the swizzled K-major layouts).
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t smem_addr, uint32_t lbo_field) {
+  return ((smem_addr >> 4) & 0x3fffu) | (lbo_field << 16);
+}
 __device__ __forceinline__ uint64_t tc_make_desc(uint32_t smem_addr, uint32_t lbo_field, uint32_t hi) {
   return ((uint64_t)hi << 32) | (uint64_t)(((smem_addr >> 4) & 0x3fffu) | (lbo_field << 16));
 }
@@ -209,18 +225,26 @@ template <> struct Vec16<__nv_bfloat16> {
   }
 };
 
+// 16 bias values (broadcast loads through the read-only path); zeros when the op has no bias.  Issued BEFORE the
+// tcgen05.wait::ld so the L1 latency overlaps the TMEM read.
+struct Bias16 {
+  float4 b[4];
+  __device__ __forceinline__ void load(const float* __restrict__ bias, int n) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+      b[q4] = bias ? __ldg(reinterpret_cast<const float4*>(bias + n) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+};
+
 // bias + GELU + residual + ReLU on 16 accumulator columns of one output row, then the store.
 template <typename TO>
-__device__ __forceinline__ void finish16(const float* __restrict__ bias, int act, const uint32_t (&raw)[16], const Vec16<TO>& rv, bool has_res, int n, TO* dst) {
+__device__ __forceinline__ void finish16(const Bias16& bs, int act, const uint32_t (&raw)[16], const Vec16<TO>& rv, bool has_res, TO* dst) {
   float v[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
-  if (bias) {
 #pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n) + q4);
-      v[4 * q4] += b4.x; v[4 * q4 + 1] += b4.y; v[4 * q4 + 2] += b4.z; v[4 * q4 + 3] += b4.w;
-    }
+  for (int q4 = 0; q4 < 4; ++q4) {
+    v[4 * q4] += bs.b[q4].x; v[4 * q4 + 1] += bs.b[q4].y; v[4 * q4 + 2] += bs.b[q4].z; v[4 * q4 + 3] += bs.b[q4].w;
   }
   if (act == CAPF_ACT_GELU) {
 #pragma unroll

@@ -12,8 +12,8 @@
 // zero column are computed and dropped (1 / Wp of the tensor work).  The folded weights ([Cout][9 * Cin], swizzled
 // K-major chunks exactly as in capf_tc.cu) are fetched once per CTA by TMA and stay resident.
 //
-// Roles (512 threads): warp 0 = TMA producer (weights once, then one box per 8-channel plane per band; out-of-image
-// elements are zero-filled by TMA), warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4..15 = three 4-warp
+// Roles (512 threads): warp 0 = TMA producer (weights once, then the halo of each band; out-of-image elements are
+// zero-filled by TMA), warps 1 and 3 = tcgen05.mma issuers, warp 2 = TMEM allocator, warps 4..15 = three 4-warp
 // epilogue groups taking 128-row sub-tiles round-robin.  Halo bands are double buffered; four TMEM accumulators.
 #include <new>
 
@@ -41,6 +41,7 @@ struct HaloP {
   int plane_tx_bytes;       // bytes one TMA box (one 8-channel plane of a band) delivers
   int acc_stages, acc_shift, tmem_cols, acc_stride;   // acc_stages = 1 << acc_shift accumulators in flight
   uint32_t idesc, b_desc_hi, a_desc_hi;
+  int a_rows;               // 0: halo stored as un-swizzled 8-channel planes; 1: swizzled pixel rows of C channels (C = 16|32|64)
   int act;
   const void* x;
   const float* bias;
@@ -80,7 +81,7 @@ struct HaloWalk {
   }
 };
 
-template <int C, typename TI, typename TO>
+template <int C, int NV, typename TI, typename TO>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const HaloP p) {
   constexpr int KSTEPS = C / 16;                                   // 16-channel MMA steps per filter tap
@@ -109,7 +110,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     ptx::mbar_init(bar_b, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_hfull + 8 * b, 1);
-      ptx::mbar_init(bar_hempty + 8 * b, 1);
+      ptx::mbar_init(bar_hempty + 8 * b, 2);     // both MMA issuer warps commit
     }
     for (int a = 0; a < HALO_MAX_ACC; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);
@@ -146,19 +147,31 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const uint32_t full = bar_hfull + 8 * buf;
         ptx::mbar_arrive_expect_tx(full, (uint32_t)(CHUNKS * p.plane_tx_bytes));
         const uint32_t halo = smem_halo + buf * p.halo_bytes;
+        if (p.a_rows) {
+          ptx::tma_load_4d(&mapA, full, halo, 0, -1, bin * p.bh - 1, img);    // one box: whole pixels, swizzled rows
+        } else {
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c)
-          ptx::tma_load_4d(&mapA, full, halo + (uint32_t)c * (uint32_t)p.P_alloc * 16u, 8 * c, -1, bin * p.bh - 1, img);
+          for (int c = 0; c < CHUNKS; ++c)
+            ptx::tma_load_4d(&mapA, full, halo + (uint32_t)c * (uint32_t)p.P_alloc * 16u, 8 * c, -1, bin * p.bh - 1, img);
+        }
         if (++bin == p.bands_per_img) { bin = 0; ++img; }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
+  } else if (warp == 1 || warp == 3) {
+    // ===================================== MMA issuers ======================================
+    // Two issuing warps (even / odd sub-tiles, disjoint accumulators): with N = Cout <= 64 one tcgen05.mma retires in
+    // 16-64 cycles, about what a single thread needs to set one up, so one issuer alone would pace the tensor pipe.
+    const uint32_t parity = warp == 1 ? 0u : 1u;
     ptx::mbar_wait(bar_b, 0);
     ptx::tc_fence_after();
-    const uint32_t lbo_field = (uint32_t)p.P_alloc;      // chunk-plane pitch = P_alloc * 16 bytes, >> 4
-    const uint64_t b_desc0 = tc_make_desc(smem_b, 1u, p.b_desc_hi);
+    const uint32_t pix_units = p.a_rows ? (uint32_t)CHUNKS : 1u;      // descriptor address units (16 B) per halo pixel
+    const uint32_t k_units = p.a_rows ? 2u : 2u * (uint32_t)p.P_alloc;  // ... per 16-channel K step
+    const uint32_t a_lbo = p.a_rows ? 1u : (uint32_t)p.P_alloc;
+    const uint32_t b_lo0 = tc_desc_lo(smem_b, 1u);
     const uint32_t b_chunk16 = (uint32_t)p.b_chunk_bytes >> 4;
+    uint32_t tap_off[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) tap_off[tap] = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * pix_units;
     HaloWalk w;
     w.init(p, band0, band1);
     uint32_t k = 0;
@@ -166,45 +179,48 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
       ptx::mbar_wait(bar_hfull + 8 * buf, hph);
       ptx::tc_fence_after();
-      const uint64_t a_desc0 = tc_make_desc(smem_halo + buf * p.halo_bytes, lbo_field, p.a_desc_hi);
+      const uint32_t a_lo0 = tc_desc_lo(smem_halo + buf * p.halo_bytes, a_lbo);
       const int n_sub = w.n_sub;
       for (int j = 0; j < n_sub; ++j) {
-        const uint32_t acc = w.it & (uint32_t)(p.acc_stages - 1), aph = (w.it >> p.acc_shift) & 1u;
-        ptx::mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-          // descriptor start-address field counts 16-byte units == halo pixels
-          const uint64_t a_sub = a_desc0 + (uint32_t)(j * 128);
+        if ((w.it & 1u) == parity) {
+          const uint32_t acc = w.it & (uint32_t)(p.acc_stages - 1), aph = (w.it >> p.acc_shift) & 1u;
+          ptx::mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+            const uint32_t a_sub = a_lo0 + (uint32_t)(j * 128) * pix_units;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t a_tap = a_sub + (uint32_t)((tap / 3) * p.Wp + (tap % 3));
+            for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-            for (int kk = 0; kk < KSTEPS; ++kk) {
-              const uint64_t a_d = a_tap + (uint32_t)(2 * kk) * (uint32_t)p.P_alloc;
-              const uint64_t b_d = b_desc0 + (uint32_t)(tap * CPT + kk / KPC) * b_chunk16 + (uint32_t)((kk % KPC) * 2);
-              ptx::umma_f16(d_tmem, a_d, b_d, p.idesc, (tap | kk) ? 1u : 0u);
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                const uint32_t a_lo = a_sub + tap_off[tap] + (uint32_t)kk * k_units;
+                const uint32_t b_lo = b_lo0 + (uint32_t)(tap * CPT + kk / KPC) * b_chunk16 + (uint32_t)((kk % KPC) * 2);
+                ptx::umma_f16_lohi(d_tmem, a_lo, p.a_desc_hi, b_lo, p.b_desc_hi, p.idesc, (tap | kk) ? 1u : 0u);
+              }
             }
+            ptx::umma_commit(bar_tfull + 8 * acc);
           }
-          ptx::umma_commit(bar_tfull + 8 * acc);
-          if (j == n_sub - 1) ptx::umma_commit(bar_hempty + 8 * buf);   // band fully read -> producer may refill
+          __syncwarp();
         }
-        __syncwarp();
         w.step(p);
       }
+      // this warp's MMAs on the band are all issued: its share of "band consumed" (2 arrivals free the buffer)
+      if (ptx::elect_one()) ptx::umma_commit(bar_hempty + 8 * buf);
+      __syncwarp();
       ++k;
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =========================================
-    // Three 4-warp groups take sub-tiles round-robin.  The residual of a group's NEXT sub-tile is requested before
-    // the current one is finished, so its DRAM latency is covered by a whole sub-tile period.
+    // Three 4-warp groups take sub-tiles round-robin.  Narrow outputs (NV <= 2 vectors of 16 columns) request the
+    // residual of the group's NEXT sub-tile before finishing the current one, so its DRAM latency is covered by a
+    // whole sub-tile period; wide ones request it at the top of the tile, ahead of the accumulator wait.
     constexpr int NG = HALO_EPI_GROUPS;
+    constexpr bool AHEAD = NV <= 2;
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const TO* res = reinterpret_cast<const TO*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
-    const int nv = p.Cout >> 4;                      // 16-column vectors per row (<= 4)
 
     HaloWalk w;
     w.init(p, band0, band1);
@@ -216,43 +232,49 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       live = t.valid() && ix < p.W && iy < t.bh_eff;
       off0 = live ? (((size_t)t.img * p.H + t.y0 + iy) * p.W + ix) * p.Cout : 0;
     };
-    Vec16<TO> rcur[4], rnext[4];
+    auto fetch = [&](Vec16<TO> (&r)[NV], bool live, size_t off0) {
+      if (res && live) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) r[v].load(res + off0 + 16 * v);
+      }
+    };
+    Vec16<TO> rcur[NV], rnext[AHEAD ? NV : 1];
     bool live_n;
     size_t off_n;
     locate(w, live_n, off_n);
-    if (res && live_n) {
-#pragma unroll
-      for (int v = 0; v < 4; ++v)
-        if (v < nv) rnext[v].load(res + off_n + 16 * v);
-    }
+    if constexpr (AHEAD) fetch(rnext, live_n, off_n);
     while (w.valid()) {
       const uint32_t acc = w.it & (uint32_t)(p.acc_stages - 1), aph = (w.it >> p.acc_shift) & 1u;
       const bool live = live_n;
       const size_t off0 = off_n;
       const bool has_res = live && res != nullptr;
+      if constexpr (AHEAD) {
 #pragma unroll
-      for (int v = 0; v < 4; ++v) rcur[v] = rnext[v];
+        for (int v = 0; v < NV; ++v) rcur[v] = rnext[v];
+      } else {
+        fetch(rcur, live, off0);
+      }
       for (int i = 0; i < NG && w.valid(); ++i) w.step(p);
       locate(w, live_n, off_n);
-      if (res && live_n) {
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          if (v < nv) rnext[v].load(res + off_n + 16 * v);
-      }
+      if constexpr (AHEAD) fetch(rnext, live_n, off_n);
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
       ptx::mbar_wait(bar_tfull + 8 * acc, aph);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int v = 0; v < 4; v += 2) {
-        if (v < nv) {
-          uint32_t a0[16], a1[16];
-          ptx::tmem_ld16(taddr + (uint32_t)(16 * v), a0);
-          if (v + 1 < nv) ptx::tmem_ld16(taddr + (uint32_t)(16 * v + 16), a1);
-          ptx::tmem_ld_wait();
-          if (live) {
-            finish16<TO>(p.bias, p.act, a0, rcur[v], has_res, 16 * v, out + off0 + 16 * v);
-            if (v + 1 < nv) finish16<TO>(p.bias, p.act, a1, rcur[v + 1], has_res, 16 * v + 16, out + off0 + 16 * v + 16);
-          }
+      for (int v = 0; v < NV; v += 2) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const bool two = v + 1 < NV;
+        uint32_t a0[16], a1[16];
+        ptx::tmem_ld16(taddr + (uint32_t)(16 * v), a0);
+        if (two) ptx::tmem_ld16(taddr + (uint32_t)(16 * v + 16), a1);
+        Bias16 b0, b1;
+        b0.load(p.bias, 16 * v);
+        if (two) b1.load(p.bias, 16 * v + 16);
+        ptx::tmem_ld_wait();
+        if (live) {
+          finish16<TO>(b0, p.act, a0, rcur[v], has_res, out + off0 + 16 * v);
+          if (two) finish16<TO>(b1, p.act, a1, rcur[two ? v + 1 : v], has_res, out + off0 + 16 * v + 16);
         }
       }
       ptx::tc_fence_before();
@@ -303,7 +325,7 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   for (int bh = 1; bh <= H; ++bh) {
     const int n_sub_full = (bh * p.Wp + 127) / 128;
     const int P_alloc = halo_plane_pixels(bh, p.Wp);
-    const long long halo_bytes = (long long)P_alloc * C * 2;
+    const long long halo_bytes = ((long long)P_alloc * C * 2 + 1023) & ~1023ll;
     if (P_alloc > 16383 || bh + 3 > 256 || 2 * halo_bytes > budget) break;
     const int full = H / bh, rem = H - full * bh;
     long long tiles = (long long)full * n_sub_full + (rem ? (rem * p.Wp + 127) / 128 : 0);
@@ -318,7 +340,7 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   const int n_sub_full = (p.bh * p.Wp + 127) / 128;
   (void)n_sub_full;
   p.P_alloc = halo_plane_pixels(p.bh, p.Wp);
-  p.halo_bytes = p.P_alloc * C * 2;
+  p.halo_bytes = (p.P_alloc * C * 2 + 1023) & ~1023;
   p.plane_tx_bytes = (p.bh + 3) * p.Wp * 16;
   p.acc_shift = 4 * Cout <= 512 ? 2 : 1;
   p.acc_stages = 1 << p.acc_shift;
@@ -348,7 +370,17 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
   const bool bf16 = op.dtype_in == CAPF_BF16;
   p.idesc = tc_idesc(bf16, p.Cout);
   p.b_desc_hi = tc_desc_hi(p.kb * 2, 8 * p.kb * 2);
-  p.a_desc_hi = tc_desc_hi(0, 128);               // un-swizzled: 8-row groups are 128 contiguous bytes
+  const int variant = op.i[13];
+  // un-swizzled 8-channel planes work for every C; swizzled whole-pixel rows need a power-of-two row (and move 4-8x
+  // fewer TMA elements).  UMMA applies the swizzle XOR to the absolute shared-memory address, so the shifted-window
+  // starts need no descriptor base offset (measured on B200: base_offset = 0 is exact, (start >> 7) & 7 is wrong).
+  p.a_rows = variant != 2 && (p.C == 16 || p.C == 32 || p.C == 64);
+  if (p.a_rows) {
+    p.a_desc_hi = tc_desc_hi(p.C * 2, 8 * p.C * 2);   // swizzle span == pixel row; 8-row groups contiguous
+    p.plane_tx_bytes = (p.bh + 3) * p.Wp * 16;        // x CHUNKS == the single whole-pixel box
+  } else {
+    p.a_desc_hi = tc_desc_hi(0, 128);                 // un-swizzled: 8-row groups are 128 contiguous bytes
+  }
   p.act = op.i[11];
   p.x = op.in[0];
   p.bias = (const float*)op.in[2];
@@ -368,26 +400,37 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
     // 8-channel planes of the NHWC input: box {8, Wp, bh + 3, 1}, no swizzle (16-byte rows = UMMA core-matrix rows)
     cuuint64_t adims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.Nimg};
     cuuint64_t astr[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
-    cuuint32_t abox[4] = {8, (cuuint32_t)p.Wp, (cuuint32_t)(p.bh + 3), 1};
+    cuuint32_t abox[4] = {(cuuint32_t)(p.a_rows ? p.C : 8), (cuuint32_t)p.Wp, (cuuint32_t)(p.bh + 3), 1};
     cuuint32_t aes[4] = {1, 1, 1, 1};
     e = tc_encode_map(&s->mapA, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, op.in[0], adims, astr, abox,
-                      aes, 0, "A halo planes");
+                      aes, p.a_rows ? p.C * 2 : 0, "A halo");
   }
   if (e) { delete s; return e; }
   *out = s;
   return CAPF_OK;
 }
 
-template <int C, typename TI, typename TO>
-static int halo_launch_c(const TcHaloState* s, cudaStream_t st) {
+template <int C, int NV, typename TI, typename TO>
+static int halo_launch_cn(const TcHaloState* s, cudaStream_t st) {
   static bool opted = false;
   if (!opted) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv3_halo_kernel<C, TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv3_halo_kernel<C, NV, TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_conv3_halo_kernel smem opt-in: %s", cudaGetErrorString(e));
     opted = true;
   }
-  tc_conv3_halo_kernel<C, TI, TO><<<s->grid, HALO_THREADS, s->smem_bytes, st>>>(s->mapA, s->mapB, s->p);
+  tc_conv3_halo_kernel<C, NV, TI, TO><<<s->grid, HALO_THREADS, s->smem_bytes, st>>>(s->mapA, s->mapB, s->p);
   return check_launch("tc_conv3_halo_kernel");
+}
+
+template <int C, typename TI, typename TO>
+static int halo_launch_c(const TcHaloState* s, cudaStream_t st) {
+  switch (s->p.Cout >> 4) {
+    case 1: return halo_launch_cn<C, 1, TI, TO>(s, st);
+    case 2: return halo_launch_cn<C, 2, TI, TO>(s, st);
+    case 3: return halo_launch_cn<C, 3, TI, TO>(s, st);
+    case 4: return halo_launch_cn<C, 4, TI, TO>(s, st);
+    default: return set_error(CAPF_ERR_UNSUPPORTED, "halo conv: Cout not instantiated");
+  }
 }
 
 template <typename TI, typename TO>
