@@ -23,8 +23,8 @@ namespace capf {
 
 constexpr int HALO_THREADS = 512;
 constexpr int HALO_HEADER_BYTES = 1024;
-constexpr int HALO_MAX_ACC = 4;
-constexpr int HALO_EPI_GROUPS = 3;         // warps 4..15
+constexpr int HALO_EPI_GROUPS = 3;          // warps 4..15
+constexpr int HALO_MAX_ACC = 2 * HALO_EPI_GROUPS;   // two TMEM accumulator stages per epilogue group
 
 struct HaloP {
   int C, Cout;              // Cout == UMMA N (single column tile)
@@ -39,7 +39,7 @@ struct HaloP {
   int b_chunk_bytes, b_bytes;
   int halo_bytes;           // one halo buffer
   int plane_tx_bytes;       // bytes one TMA box (one 8-channel plane of a band) delivers
-  int acc_stages, acc_shift, tmem_cols, acc_stride;   // acc_stages = 1 << acc_shift accumulators in flight
+  int acc_stages, tmem_cols, acc_stride;
   uint32_t idesc, b_desc_hi, a_desc_hi;
   int a_rows;               // 0: halo stored as un-swizzled 8-channel planes; 1: swizzled pixel rows of C channels (C = 16|32|64)
   int act;
@@ -56,7 +56,8 @@ __device__ __forceinline__ int div_wp(int v, uint32_t magic) { return (int)__umu
 // which is what keeps the accumulator-stage / phase bookkeeping implicit.
 struct HaloWalk {
   int band, band_end, img, bin, j, n_sub, bh_eff, y0;
-  uint32_t it;
+  uint32_t it;      // sub-tile counter of this CTA
+  uint32_t g, m;    // it % HALO_EPI_GROUPS (the epilogue group that drains it) and it / HALO_EPI_GROUPS
   __device__ __forceinline__ void load_band(const HaloP& p) {
     y0 = bin * p.bh;
     bh_eff = min(p.bh, p.H - y0);
@@ -66,12 +67,18 @@ struct HaloWalk {
     band = b0; band_end = b1;
     img = b0 / p.bands_per_img;
     bin = b0 - img * p.bands_per_img;
-    j = 0; it = 0;
+    j = 0; it = 0; g = 0; m = 0;
     load_band(p);
   }
   __device__ __forceinline__ bool valid() const { return band < band_end; }
+  // Accumulator stage of the current sub-tile and the parity of its use count.  Every epilogue group owns two
+  // stages, so a stage always has ONE producer (the issuer warp of that sub-tile parity: uses of a stage are 6
+  // sub-tiles apart) and ONE consumer group -- the ordering the parity-based mbarrier waits rely on.
+  __device__ __forceinline__ uint32_t acc() const { return 2u * g + (m & 1u); }
+  __device__ __forceinline__ uint32_t use_parity() const { return (m >> 1) & 1u; }
   __device__ __forceinline__ void step(const HaloP& p) {
     ++it;
+    if (++g == (uint32_t)HALO_EPI_GROUPS) { g = 0; ++m; }
     if (++j == n_sub) {
       j = 0;
       ++band;
@@ -183,7 +190,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const int n_sub = w.n_sub;
       for (int j = 0; j < n_sub; ++j) {
         if ((w.it & 1u) == parity) {
-          const uint32_t acc = w.it & (uint32_t)(p.acc_stages - 1), aph = (w.it >> p.acc_shift) & 1u;
+          const uint32_t acc = w.acc(), aph = w.use_parity();
           ptx::mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
@@ -244,7 +251,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     locate(w, live_n, off_n);
     if constexpr (AHEAD) fetch(rnext, live_n, off_n);
     while (w.valid()) {
-      const uint32_t acc = w.it & (uint32_t)(p.acc_stages - 1), aph = (w.it >> p.acc_shift) & 1u;
+      const uint32_t acc = w.acc(), aph = w.use_parity();
       const bool live = live_n;
       const size_t off0 = off_n;
       const bool has_res = live && res != nullptr;
@@ -342,8 +349,7 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   p.P_alloc = halo_plane_pixels(p.bh, p.Wp);
   p.halo_bytes = (p.P_alloc * C * 2 + 1023) & ~1023;
   p.plane_tx_bytes = (p.bh + 3) * p.Wp * 16;
-  p.acc_shift = 4 * Cout <= 512 ? 2 : 1;
-  p.acc_stages = 1 << p.acc_shift;
+  p.acc_stages = HALO_MAX_ACC;
   int cols = 32;
   while (cols < p.acc_stages * Cout) cols <<= 1;
   p.tmem_cols = cols;

@@ -11,6 +11,7 @@ Precision policies
   fp16 : backbone activations/weights f16 (f32 accumulate), lifter token stream f32 with f16 GEMM operands
   bf16 : same with bfloat16
 """
+import os
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional
 
@@ -510,6 +511,16 @@ class Plan:
 
     def run(self, first=0, count=-1, stream=None):
         s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        if os.environ.get("CAPF_DEBUG_SYNC", "0") != "0":      # locate a faulting op: one launch + sync at a time
+            n = len(self.prog.ops) - first if count < 0 else count
+            for k in range(first, first + n):
+                lib.check(self._L.capf_plan_run(self._h, k, 1, s), "capf_plan_run")
+                try:
+                    torch.cuda.synchronize(self.device)
+                except Exception as e:  # noqa: BLE001
+                    op = self.prog.ops[k]
+                    raise lib.CapfError(f"op {k} ({op.tag}, kind {op.kind}, i={op.i}) faulted: {e}") from e
+            return
         lib.check(self._L.capf_plan_run(self._h, first, count, s), "capf_plan_run")
 
     @property
