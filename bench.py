@@ -285,9 +285,14 @@ def run_native(args):
         qkv = [(op, ms) for op, ms in zip(plan.prog.ops, op_ms) if "joint_blocks" in op.tag and op.tag.endswith("attn.qkv")]
         qkv_tf = sum(o.flops for o, _ in qkv) / (sum(m for _, m in qkv) * 1e-3) / 1e12 if qkv else None
         step_ms_sum = sum(op_ms)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(dom[0])
         roofline = {
             "bound": "tensor", "kernel": dom[0], "achieved": dom_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": dom_tflops / peak_tf, "traffic": None, "peak_source": f"{peaks['_source']} bf16_tflops_sustained",
+            "frac": dom_tflops / peak_tf, "traffic": traffic, "peak_source": f"{peaks['_source']} bf16_tflops_sustained",
             "launches_per_step": dom[1]["launches"], "flops_per_step": dom[1]["flops"],
             "kernel_ms_per_step": dom[1]["ms"], "share_of_step": dom[1]["ms"] / step_ms_sum,
             "qkv_gemm": {"achieved": qkv_tf, "peak": peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]), "unit": "TFLOP/s",
