@@ -1,6 +1,7 @@
 // C ABI of libcapf_b200: error handling, device info, plans (validated op programs) and dispatch.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -10,6 +11,7 @@
 namespace capf {
 
 int g_num_sms = 148;
+int g_use_pdl = []() { const char* e = getenv("CAPF_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
 static thread_local char g_err[512] = "";
 
 int set_error(int code, const char* msg) {

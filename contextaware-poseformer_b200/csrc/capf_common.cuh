@@ -5,9 +5,37 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/capf_b200.h"
 
 namespace capf {
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel may
+// start while its predecessor in the stream is still draining.  Contract: a kernel calls pdl_wait() before it reads
+// or writes anything a previous kernel may have produced (it returns once the predecessor grid has completed and
+// its memory is visible), and pdl_trigger() once it no longer minds the successor being scheduled (persistent
+// one-wave kernels: at entry; multi-wave kernels: implicitly at block exit).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_use_pdl;   // capf_api.cu; env CAPF_PDL=0 turns the launch attribute off (kernels stay correct)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- storage <-> fp32 ---------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);

@@ -2,6 +2,8 @@
 // CA_PF.forward path, plus the memory-bound operators (samplers, LayerNorm, tiny attention, fuse-sum)
 // that the fp16/bf16 tensor-core path shares.  Reference citations are relative to
 // /root/reference/ContextPose/mvn/models/.
+#include <type_traits>
+
 #include "capf_common.cuh"
 #include "capf_internal.h"
 
@@ -20,6 +22,7 @@ template <typename TI, typename TW, typename TO, int BM, int BN, int TM, int TN,
 __global__ void __launch_bounds__(256)
 conv_nhwc_simt(ConvP p, const TI* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias,
                const TO* res, TO* y) {
+  pdl_wait();
   constexpr int BK = 16;
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
   __shared__ __align__(16) float As[BK][BM + 4];
@@ -184,15 +187,113 @@ static int conv_dispatch(const ConvP& p, const capf_op& op, cudaStream_t st) {
   bool vec = (p.Cin % 16 == 0) && (p.Cout % 4 == 0);
   if (!vec) {
     dim3 g((p.M + 127) / 128, (p.Cout + 31) / 32);
-    conv_nhwc_simt<TI, TW, TO, 128, 32, 4, 4, false><<<g, 256, 0, st>>>(p, x, w, bias, res, y);
+    launch_k(conv_nhwc_simt<TI, TW, TO, 128, 32, 4, 4, false>, dim3(g), dim3(256), 0, st, p, x, w, bias, res, y);
   } else if (p.Cout <= 32 || (p.Cout % 64 != 0 && p.Cout % 32 == 0 && p.Cout < 128)) {
     dim3 g((p.M + 127) / 128, (p.Cout + 31) / 32);
-    conv_nhwc_simt<TI, TW, TO, 128, 32, 4, 4, true><<<g, 256, 0, st>>>(p, x, w, bias, res, y);
+    launch_k(conv_nhwc_simt<TI, TW, TO, 128, 32, 4, 4, true>, dim3(g), dim3(256), 0, st, p, x, w, bias, res, y);
   } else {
     dim3 g((p.M + 127) / 128, (p.Cout + 63) / 64);
-    conv_nhwc_simt<TI, TW, TO, 128, 64, 8, 4, true><<<g, 256, 0, st>>>(p, x, w, bias, res, y);
+    launch_k(conv_nhwc_simt<TI, TW, TO, 128, 64, 8, 4, true>, dim3(g), dim3(256), 0, st, p, x, w, bias, res, y);
   }
   return check_launch("conv_nhwc_simt");
+}
+
+// =======================================================================================================
+// Stem conv1 of HRNet: 3x3 / stride 2 / pad 1, 3 -> 64 channels on the caller's fp32 NHWC image, folded BN + ReLU,
+// 16-bit output (pose_hrnet.py:321-322, :465-467).  K = 27 is too thin for the tensor path and the op is bound by
+// its 2.6x larger output, so: one thread per output pixel, the 33x33x3 input patch of a 16x16 output tile and the
+// 27x64 weights in shared memory, weights read as broadcast 128-bit loads, fp32 accumulate in tap order.
+// =======================================================================================================
+template <typename TO>
+__global__ void __launch_bounds__(256) stem_conv3x3s2_c3_kernel(int H, int W, int Ho, int Wo, int relu, const float* __restrict__ x,
+                                                                const float* __restrict__ w, const float* __restrict__ bias,
+                                                                TO* __restrict__ y) {
+  pdl_wait();
+  __shared__ float patch[33 * 33 * 3 + 1];
+  __shared__ __align__(16) float ws[27 * 64];
+  __shared__ __align__(16) float bs[64];
+  const int tid = threadIdx.x;
+  const int ox0 = blockIdx.x * 16, oy0 = blockIdx.y * 16, n = blockIdx.z;
+  const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+  const float* img = x + (size_t)n * H * W * 3;
+  for (int i = tid; i < 33 * 99; i += 256) {
+    const int r = i / 99, c = i - r * 99;          // c = (column, channel) flattened: contiguous in the image row
+    const int iy = iy0 + r, ixc = ix0 * 3 + c;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ixc >= 0 && ixc < W * 3) v = __ldg(img + (size_t)iy * W * 3 + ixc);
+    patch[i] = v;
+  }
+  for (int i = tid; i < 27 * 64; i += 256) ws[i] = __ldg(w + i);
+  if (tid < 64) bs[tid] = bias ? __ldg(bias + tid) : 0.f;
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  const int ox = ox0 + tx, oy = oy0 + ty;
+  float in[27];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) in[(r * 3 + s) * 3 + c] = patch[((2 * ty + r) * 33 + 2 * tx + s) * 3 + c];
+  if (ox >= Wo || oy >= Ho) return;
+  TO* dst = y + (((size_t)n * Ho + oy) * Wo + ox) * 64;
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4* wk = reinterpret_cast<const float4*>(ws + k * 64 + g * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = wk[q];
+        acc[4 * q] = fmaf(in[k], w4.x, acc[4 * q]);
+        acc[4 * q + 1] = fmaf(in[k], w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(in[k], w4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(in[k], w4.w, acc[4 * q + 3]);
+      }
+    }
+    float o[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      o[c] = acc[c] + bs[g * 16 + c];
+      if (relu) o[c] = fmaxf(o[c], 0.f);
+    }
+    // 16 channels = 32 bytes: two 128-bit stores
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 v;
+      uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if constexpr (sizeof(TO) == 2 && std::is_same<TO, __half>::value) {
+          __half2 t = __floats2half2_rn(o[8 * h + 2 * e], o[8 * h + 2 * e + 1]);
+          pv[e] = *reinterpret_cast<uint32_t*>(&t);
+        } else {
+          __nv_bfloat162 t = __floats2bfloat162_rn(o[8 * h + 2 * e], o[8 * h + 2 * e + 1]);
+          pv[e] = *reinterpret_cast<uint32_t*>(&t);
+        }
+      }
+      *reinterpret_cast<uint4*>(dst + g * 16 + 8 * h) = v;
+    }
+  }
+}
+
+static bool is_stem(const ConvP& p, const capf_op& op) {
+  return p.Cin == 3 && p.Cout == 64 && p.KH == 3 && p.KW == 3 && p.stride == 2 && p.pad == 1 && op.dtype_in == CAPF_F32 &&
+         (op.dtype_out == CAPF_F16 || op.dtype_out == CAPF_BF16) && !op.in[3] && p.act != CAPF_ACT_GELU && p.N <= 65535;
+}
+
+static int launch_stem(const ConvP& p, const capf_op& op, cudaStream_t st) {
+  dim3 g((p.Wo + 15) / 16, (p.Ho + 15) / 16, p.N);
+  const float *x = (const float*)op.in[0], *w = (const float*)op.in[1], *b = (const float*)op.in[2];
+  const int relu = p.act == CAPF_ACT_RELU;
+  if (op.dtype_out == CAPF_F16)
+    launch_k(stem_conv3x3s2_c3_kernel<__half>, dim3(g), dim3(256), 0, st, p.H, p.W, p.Ho, p.Wo, relu, x, w, b, (__half*)op.out[0]);
+  else
+    launch_k(stem_conv3x3s2_c3_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, st, p.H, p.W, p.Ho, p.Wo, relu, x, w, b, (__nv_bfloat16*)op.out[0]);
+  return check_launch("stem_conv3x3s2_c3");
 }
 
 int launch_conv_simt(const capf_op& op, cudaStream_t st) {
@@ -208,6 +309,7 @@ int launch_conv_simt(const capf_op& op, cudaStream_t st) {
   p.K = p.KH * p.KW * p.Cin;
   if (!op.in[0] || !op.in[1] || !op.out[0]) return set_error(CAPF_ERR_ARG, "conv2d: null pointer");
   int di = op.dtype_in, dd = op.dtype_out;
+  if (is_stem(p, op)) return launch_stem(p, op, st);
   if (di == CAPF_F32 && dd == CAPF_F32) return conv_dispatch<float, float, float>(p, op, st);
   if (di == CAPF_F32 && dd == CAPF_F16) return conv_dispatch<float, float, __half>(p, op, st);
   if (di == CAPF_F32 && dd == CAPF_BF16) return conv_dispatch<float, float, __nv_bfloat16>(p, op, st);
@@ -229,6 +331,7 @@ struct FuseP {
 
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseP p, T* __restrict__ y) {
+  pdl_wait();
   const int C4 = p.C >> 2;
   size_t total = (size_t)p.N * p.H * p.W * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -269,9 +372,9 @@ int launch_fuse_sum(const capf_op& op, cudaStream_t st) {
   int blocks = (int)((total + 255) / 256 < (size_t)g_num_sms * 16 ? (total + 255) / 256 : (size_t)g_num_sms * 16);
   if (blocks < 1) blocks = 1;
   switch (op.dtype_out) {
-    case CAPF_F32: fuse_sum_kernel<float><<<blocks, 256, 0, st>>>(p, (float*)op.out[0]); break;
-    case CAPF_F16: fuse_sum_kernel<__half><<<blocks, 256, 0, st>>>(p, (__half*)op.out[0]); break;
-    case CAPF_BF16: fuse_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p, (__nv_bfloat16*)op.out[0]); break;
+    case CAPF_F32: launch_k(fuse_sum_kernel<float>, dim3(blocks), dim3(256), 0, st, p, (float*)op.out[0]); break;
+    case CAPF_F16: launch_k(fuse_sum_kernel<__half>, dim3(blocks), dim3(256), 0, st, p, (__half*)op.out[0]); break;
+    case CAPF_BF16: launch_k(fuse_sum_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, p, (__nv_bfloat16*)op.out[0]); break;
     default: return set_error(CAPF_ERR_UNSUPPORTED, "fuse_sum: dtype");
   }
   return check_launch("fuse_sum");
@@ -284,6 +387,7 @@ int launch_fuse_sum(const capf_op& op, cudaStream_t st) {
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(int N, int H, int W, int C, int Ho, int Wo,
                                                            const T* __restrict__ x, T* __restrict__ y) {
+  pdl_wait();
   const int C4 = C >> 2;
   size_t total = (size_t)N * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -312,6 +416,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(int N, int H, int W, 
 template <typename T>
 __global__ void __launch_bounds__(256) bilinear_ac_kernel(int N, int H, int W, int C, int Ho, int Wo, float sy, float sx,
                                                           const T* __restrict__ x, T* __restrict__ y) {
+  pdl_wait();
   const int C4 = C >> 2;
   size_t total = (size_t)N * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -349,9 +454,9 @@ int launch_maxpool(const capf_op& op, cudaStream_t st) {
     return set_error(CAPF_ERR_ARG, "maxpool: bad shape/dtype");
   int blocks = ew_blocks((size_t)N * Ho * Wo * (C / 4));
   switch (op.dtype_in) {
-    case CAPF_F32: maxpool3x3s2_kernel<float><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, (const float*)op.in[0], (float*)op.out[0]); break;
-    case CAPF_F16: maxpool3x3s2_kernel<__half><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, (const __half*)op.in[0], (__half*)op.out[0]); break;
-    case CAPF_BF16: maxpool3x3s2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0]); break;
+    case CAPF_F32: launch_k(maxpool3x3s2_kernel<float>, dim3(blocks), dim3(256), 0, st, N, H, W, C, Ho, Wo, (const float*)op.in[0], (float*)op.out[0]); break;
+    case CAPF_F16: launch_k(maxpool3x3s2_kernel<__half>, dim3(blocks), dim3(256), 0, st, N, H, W, C, Ho, Wo, (const __half*)op.in[0], (__half*)op.out[0]); break;
+    case CAPF_BF16: launch_k(maxpool3x3s2_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, N, H, W, C, Ho, Wo, (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0]); break;
     default: return set_error(CAPF_ERR_UNSUPPORTED, "maxpool: dtype");
   }
   return check_launch("maxpool3x3s2");
@@ -365,9 +470,9 @@ int launch_bilinear(const capf_op& op, cudaStream_t st) {
   float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
   int blocks = ew_blocks((size_t)N * Ho * Wo * (C / 4));
   switch (op.dtype_in) {
-    case CAPF_F32: bilinear_ac_kernel<float><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, sy, sx, (const float*)op.in[0], (float*)op.out[0]); break;
-    case CAPF_F16: bilinear_ac_kernel<__half><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, sy, sx, (const __half*)op.in[0], (__half*)op.out[0]); break;
-    case CAPF_BF16: bilinear_ac_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(N, H, W, C, Ho, Wo, sy, sx, (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0]); break;
+    case CAPF_F32: launch_k(bilinear_ac_kernel<float>, dim3(blocks), dim3(256), 0, st, N, H, W, C, Ho, Wo, sy, sx, (const float*)op.in[0], (float*)op.out[0]); break;
+    case CAPF_F16: launch_k(bilinear_ac_kernel<__half>, dim3(blocks), dim3(256), 0, st, N, H, W, C, Ho, Wo, sy, sx, (const __half*)op.in[0], (__half*)op.out[0]); break;
+    case CAPF_BF16: launch_k(bilinear_ac_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, N, H, W, C, Ho, Wo, sy, sx, (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0]); break;
     default: return set_error(CAPF_ERR_UNSUPPORTED, "bilinear: dtype");
   }
   return check_launch("bilinear_ac");
@@ -381,6 +486,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(int rows, int D, int per
                                                         const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, const float* __restrict__ x0,
                                                         TO* __restrict__ y) {
+  pdl_wait();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* xr = x + (size_t)warp * D;
@@ -435,9 +541,9 @@ int launch_layernorm(const capf_op& op, cudaStream_t st) {
   int blocks = (rows + 7) / 8;
   const float *x = (const float*)op.in[0], *g = (const float*)op.in[1], *b = (const float*)op.in[2], *x0 = (const float*)op.in[3];
   switch (op.dtype_out) {
-    case CAPF_F32: layernorm_kernel<float, 8><<<blocks, 256, 0, st>>>(rows, D, period, op.f[0], x, g, b, x0, (float*)op.out[0]); break;
-    case CAPF_F16: layernorm_kernel<__half, 8><<<blocks, 256, 0, st>>>(rows, D, period, op.f[0], x, g, b, x0, (__half*)op.out[0]); break;
-    case CAPF_BF16: layernorm_kernel<__nv_bfloat16, 8><<<blocks, 256, 0, st>>>(rows, D, period, op.f[0], x, g, b, x0, (__nv_bfloat16*)op.out[0]); break;
+    case CAPF_F32: launch_k(layernorm_kernel<float, 8>, dim3(blocks), dim3(256), 0, st, rows, D, period, op.f[0], x, g, b, x0, (float*)op.out[0]); break;
+    case CAPF_F16: launch_k(layernorm_kernel<__half, 8>, dim3(blocks), dim3(256), 0, st, rows, D, period, op.f[0], x, g, b, x0, (__half*)op.out[0]); break;
+    case CAPF_BF16: launch_k(layernorm_kernel<__nv_bfloat16, 8>, dim3(blocks), dim3(256), 0, st, rows, D, period, op.f[0], x, g, b, x0, (__nv_bfloat16*)op.out[0]); break;
     default: return set_error(CAPF_ERR_UNSUPPORTED, "layernorm: dtype_out");
   }
   return check_launch("layernorm");
@@ -450,6 +556,7 @@ int launch_layernorm(const capf_op& op, cudaStream_t st) {
 template <typename TI, typename TO, int SEQ>
 __global__ void __launch_bounds__(128) attention_small_kernel(int groups, int heads, int hd, int tok_stride, int grp_stride,
                                                               float scale, const TI* __restrict__ qkv, TO* __restrict__ out) {
+  pdl_wait();
   constexpr int IPW = 32 / SEQ;  // items per warp
   extern __shared__ float sm[];
   const int warp_in_blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -547,13 +654,13 @@ static int attention_dispatch(const capf_op& op, cudaStream_t st) {
       cudaFuncSetAttribute(attention_small_kernel<TI, TO, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       max5 = smem;
     }
-    attention_small_kernel<TI, TO, 5><<<blocks, 128, smem, st>>>(groups, heads, hd, ts, gs, op.f[0], qkv, out);
+    launch_k(attention_small_kernel<TI, TO, 5>, dim3(blocks), dim3(128), smem, st, groups, heads, hd, ts, gs, op.f[0], qkv, out);
   } else {
     if (smem > max17) {
       cudaFuncSetAttribute(attention_small_kernel<TI, TO, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       max17 = smem;
     }
-    attention_small_kernel<TI, TO, 17><<<blocks, 128, smem, st>>>(groups, heads, hd, ts, gs, op.f[0], qkv, out);
+    launch_k(attention_small_kernel<TI, TO, 17>, dim3(blocks), dim3(128), smem, st, groups, heads, hd, ts, gs, op.f[0], qkv, out);
   }
   return check_launch("attention_small");
 }
@@ -582,6 +689,7 @@ struct SampP {
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) ref_sample_kernel(SampP p, const float* __restrict__ ref, TO* __restrict__ out,
                                                          int* __restrict__ rec) {
+  pdl_wait();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   int R = p.B * p.J;
   if (warp >= R) return;
@@ -625,6 +733,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) deform_sample_kernel(SampP p, const float* __restrict__ ref,
                                                             const float* __restrict__ ow, TO* __restrict__ out,
                                                             int* __restrict__ rec) {
+  pdl_wait();
   long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int R = p.B * p.J;
@@ -706,11 +815,11 @@ template <typename TI, typename TO>
 static int sample_dispatch(const capf_op& op, const SampP& p, cudaStream_t st) {
   if (op.kind == CAPF_OP_REF_SAMPLE) {
     int R = p.B * p.J;
-    ref_sample_kernel<TI, TO><<<(R + 7) / 8, 256, 0, st>>>(p, (const float*)op.in[0], (TO*)op.out[0], (int*)op.out[1]);
+    launch_k(ref_sample_kernel<TI, TO>, dim3((R + 7) / 8), dim3(256), 0, st, p, (const float*)op.in[0], (TO*)op.out[0], (int*)op.out[1]);
     return check_launch("ref_sample");
   }
   long long warps = (long long)p.nl * p.B * p.J * 4;
-  deform_sample_kernel<TI, TO><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(p, (const float*)op.in[0], (const float*)op.in[5],
+  launch_k(deform_sample_kernel<TI, TO>, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, st, p, (const float*)op.in[0], (const float*)op.in[5],
                                                                            (TO*)op.out[0], (int*)op.out[1]);
   return check_launch("deform_sample");
 }
@@ -736,6 +845,7 @@ int launch_sample(const capf_op& op, cudaStream_t st) {
 __global__ void __launch_bounds__(256) embed_coord_kernel(int R, int J, int D, int slabs, const float* __restrict__ kp,
                                                           const float* __restrict__ Wc, const float* __restrict__ bc,
                                                           const float* __restrict__ pos, float* __restrict__ X) {
+  pdl_wait();
   size_t total = (size_t)slabs * R * D;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int d = (int)(i % D);
@@ -756,6 +866,7 @@ __global__ void __launch_bounds__(256) embed_coord_kernel(int R, int J, int D, i
 // '(b p) l c -> b p (l c)' (pose_dformer.py:235)
 __global__ void __launch_bounds__(256) levels_to_joint_kernel(int R, int slabs, int D, const float* __restrict__ X,
                                                               float* __restrict__ Y) {
+  pdl_wait();
   const int D4 = D >> 2;
   size_t total = (size_t)R * slabs * D4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -769,6 +880,7 @@ __global__ void __launch_bounds__(256) levels_to_joint_kernel(int R, int slabs, 
 
 // keypoints_2d_cpn_crop[..., :2] /= (96, 128);  -= (1, 1)   (conpose.py:34-35), in place
 __global__ void crop_normalize_kernel(int n, float* __restrict__ c) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float2 v = reinterpret_cast<float2*>(c)[i];
@@ -780,6 +892,7 @@ __global__ void crop_normalize_kernel(int n, float* __restrict__ c) {
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) cast_kernel(size_t n, const TI* __restrict__ x, TO* __restrict__ y) {
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = from_f<TO>(to_f<TI>(x[i]));
 }
@@ -789,7 +902,7 @@ int launch_embed_coord(const capf_op& op, cudaStream_t st) {
   if (B <= 0 || J <= 0 || D <= 0 || slabs <= 0 || !op.in[0] || !op.in[1] || !op.in[2] || !op.in[3] || !op.out[0])
     return set_error(CAPF_ERR_ARG, "embed_coord: bad arguments");
   size_t total = (size_t)slabs * B * J * D;
-  embed_coord_kernel<<<ew_blocks(total), 256, 0, st>>>(B * J, J, D, slabs, (const float*)op.in[0], (const float*)op.in[1],
+  launch_k(embed_coord_kernel, dim3(ew_blocks(total)), dim3(256), 0, st, B * J, J, D, slabs, (const float*)op.in[0], (const float*)op.in[1],
                                                        (const float*)op.in[2], (const float*)op.in[3], (float*)op.out[0]);
   return check_launch("embed_coord");
 }
@@ -797,14 +910,14 @@ int launch_embed_coord(const capf_op& op, cudaStream_t st) {
 int launch_levels_to_joint(const capf_op& op, cudaStream_t st) {
   int R = op.i[0], slabs = op.i[1], D = op.i[2];
   if (R <= 0 || slabs <= 0 || D <= 0 || (D & 3)) return set_error(CAPF_ERR_ARG, "levels_to_joint: bad arguments");
-  levels_to_joint_kernel<<<ew_blocks((size_t)R * slabs * (D / 4)), 256, 0, st>>>(R, slabs, D, (const float*)op.in[0], (float*)op.out[0]);
+  launch_k(levels_to_joint_kernel, dim3(ew_blocks((size_t)R * slabs * (D / 4))), dim3(256), 0, st, R, slabs, D, (const float*)op.in[0], (float*)op.out[0]);
   return check_launch("levels_to_joint");
 }
 
 int launch_crop_normalize(const capf_op& op, cudaStream_t st) {
   int n = op.i[0];
   if (n <= 0 || !op.out[0]) return set_error(CAPF_ERR_ARG, "crop_normalize: bad arguments");
-  crop_normalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (float*)op.out[0]);
+  launch_k(crop_normalize_kernel, dim3((n + 255) / 256), dim3(256), 0, st, n, (float*)op.out[0]);
   return check_launch("crop_normalize");
 }
 
@@ -813,15 +926,15 @@ int launch_cast(const capf_op& op, cudaStream_t st) {
   if (!n || !op.in[0] || !op.out[0]) return set_error(CAPF_ERR_ARG, "cast: bad arguments");
   int blocks = ew_blocks(n);
   if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_F16)
-    cast_kernel<float, __half><<<blocks, 256, 0, st>>>(n, (const float*)op.in[0], (__half*)op.out[0]);
+    launch_k(cast_kernel<float, __half>, dim3(blocks), dim3(256), 0, st, n, (const float*)op.in[0], (__half*)op.out[0]);
   else if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_BF16)
-    cast_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>(n, (const float*)op.in[0], (__nv_bfloat16*)op.out[0]);
+    launch_k(cast_kernel<float, __nv_bfloat16>, dim3(blocks), dim3(256), 0, st, n, (const float*)op.in[0], (__nv_bfloat16*)op.out[0]);
   else if (op.dtype_in == CAPF_F16 && op.dtype_out == CAPF_F32)
-    cast_kernel<__half, float><<<blocks, 256, 0, st>>>(n, (const __half*)op.in[0], (float*)op.out[0]);
+    launch_k(cast_kernel<__half, float>, dim3(blocks), dim3(256), 0, st, n, (const __half*)op.in[0], (float*)op.out[0]);
   else if (op.dtype_in == CAPF_BF16 && op.dtype_out == CAPF_F32)
-    cast_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>(n, (const __nv_bfloat16*)op.in[0], (float*)op.out[0]);
+    launch_k(cast_kernel<__nv_bfloat16, float>, dim3(blocks), dim3(256), 0, st, n, (const __nv_bfloat16*)op.in[0], (float*)op.out[0]);
   else if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_F32)
-    cast_kernel<float, float><<<blocks, 256, 0, st>>>(n, (const float*)op.in[0], (float*)op.out[0]);
+    launch_k(cast_kernel<float, float>, dim3(blocks), dim3(256), 0, st, n, (const float*)op.in[0], (float*)op.out[0]);
   else
     return set_error(CAPF_ERR_UNSUPPORTED, "cast: dtype combination");
   return check_launch("cast");

@@ -125,6 +125,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1;
+  // PDL: this one-wave persistent grid is fully resident -> let the successor be scheduled as SMs drain; nothing
+  // produced by the predecessor (activations, residual) has been touched before this point.
+  pdl_trigger();
+  pdl_wait();
   int t0, t1;
   tile_range(p, t0, t1);
 
@@ -487,7 +491,7 @@ static int tc_launch_typed(const TcConvState* s, cudaStream_t st) {
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_gemm_kernel smem opt-in: %s", cudaGetErrorString(e));
     max_smem = TC_SMEM_LIMIT;
   }
-  tc_gemm_kernel<TO><<<s->grid, TC_THREADS, s->smem_bytes, st>>>(s->mapA, s->mapB, s->p);
+  launch_k(tc_gemm_kernel<TO>, dim3(s->grid), dim3(TC_THREADS), s->smem_bytes, st, s->mapA, s->mapB, s->p);
   return check_launch("tc_gemm_kernel");
 }
 

@@ -133,6 +133,8 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();                                      // one-wave persistent grid: successor may be scheduled as SMs drain
+  if (warp != 0) pdl_wait();                          // warp 0 first starts the (constant) weight fetch, then waits
 
   // contiguous band range of this CTA
   const int band0 = (int)(((long long)p.num_bands * blockIdx.x) / gridDim.x);
@@ -145,6 +147,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar_b, (uint32_t)p.b_bytes);
       for (int c = 0; c < 9 * CPT; ++c) ptx::tma_load_2d(&mapB, bar_b, smem_b + c * p.b_chunk_bytes, c * KB, 0);
+      pdl_wait();                                     // activations of the predecessor are read from here on
       const int img0 = band0 / p.bands_per_img;
       int img = img0, bin = band0 - img0 * p.bands_per_img;
       uint32_t k = 0;
@@ -424,7 +427,7 @@ static int halo_launch_cn(const TcHaloState* s, cudaStream_t st) {
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_conv3_halo_kernel smem opt-in: %s", cudaGetErrorString(e));
     opted = true;
   }
-  tc_conv3_halo_kernel<C, NV, TI, TO><<<s->grid, HALO_THREADS, s->smem_bytes, st>>>(s->mapA, s->mapB, s->p);
+  launch_k(tc_conv3_halo_kernel<C, NV, TI, TO>, dim3(s->grid), dim3(HALO_THREADS), s->smem_bytes, st, s->mapA, s->mapB, s->p);
   return check_launch("tc_conv3_halo_kernel");
 }
 

@@ -59,6 +59,25 @@ def test_conv2d_simt(shape, dt, act, use_res):
     assert rel_l2(out.float().cpu(), y) < (2e-6 if dt == torch.float32 else 1.5e-3)
 
 
+@pytest.mark.parametrize("shape", [(2, 17, 13), (3, 64, 48), (1, 256, 256)], ids=str)
+@pytest.mark.parametrize("odt", [torch.float16, torch.bfloat16])
+def test_stem_conv_f32_image_to_16bit(shape, odt):
+    """HRNet conv1 (pose_hrnet.py:321-322): fp32 NHWC image in, folded-BN 3x3/s2 3->64 + ReLU, 16-bit out
+    (the specialised stem kernel of capf_simt.cu)."""
+    N, H, W = shape
+    g = _gen(11)
+    x = torch.randn(N, H, W, 3, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) / 27 ** 0.5
+    bias = torch.randn(64, generator=g)
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, bias, 2, 1)).permute(0, 2, 3, 1)
+    wp = w.permute(2, 3, 1, 0).reshape(-1, 64).contiguous().to(DEV)
+    out = torch.full((N, Ho, Wo, 64), float("nan"), dtype=odt, device=DEV)
+    run_op(lib.OP_CONV2D, torch.float32, odt, [N, H, W, 3, 64, 3, 3, 2, 1, Ho, Wo, lib.ACT_RELU, lib.IMPL_SIMT], [],
+           [x.to(DEV), wp, bias.to(DEV), None], [out])
+    assert rel_l2(out.float().cpu(), y) < (6e-4 if odt == torch.float16 else 4e-3)
+
+
 def test_conv2d_rejects_bad_arguments():
     x = torch.zeros(1, 4, 4, 16, device=DEV)
     with pytest.raises(lib.CapfError, match="Ho/Wo"):
