@@ -38,7 +38,8 @@ struct HaloP {
   int kb, cpt;              // weight chunk width (elements) and chunks per tap, as in capf_tc.cu
   int b_chunk_bytes, b_bytes;
   int halo_bytes;           // one halo buffer
-  int plane_tx_bytes;       // bytes one TMA box (one 8-channel plane of a band) delivers
+  int plane_tx_bytes;       // bytes per 8-channel plane of a band (n_boxes slabs of box_rows halo rows)
+  int box_rows, n_boxes;    // the band is fetched as n_boxes TMA boxes of box_rows rows each
   int acc_stages, tmem_cols, acc_stride;
   uint32_t idesc, b_desc_hi, a_desc_hi;
   int a_rows;               // 0: halo stored as un-swizzled 8-channel planes; 1: swizzled pixel rows of C channels (C = 16|32|64)
@@ -47,6 +48,7 @@ struct HaloP {
   const float* bias;
   const void* res;
   void* out;
+  long long* trace;         // optional (debug): per-role clock64 timeline of CTA 0, see tools/halo_trace.py
 };
 
 // v / Wp without a divide: magic = ceil(2^32 / Wp), exact for the pixel counts of one band (< 2^16)
@@ -133,6 +135,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[11 * 256] = clock64();
   pdl_trigger();                                      // one-wave persistent grid: successor may be scheduled as SMs drain
   if (warp != 0) pdl_wait();                          // warp 0 first starts the (constant) weight fetch, then waits
 
@@ -148,21 +151,29 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       ptx::mbar_arrive_expect_tx(bar_b, (uint32_t)p.b_bytes);
       for (int c = 0; c < 9 * CPT; ++c) ptx::tma_load_2d(&mapB, bar_b, smem_b + c * p.b_chunk_bytes, c * KB, 0);
       pdl_wait();                                     // activations of the predecessor are read from here on
+      // One TMA box is served with little request parallelism (measured: a single 79 KB box of 64-byte rows arrives
+      // at ~6 B/clk/SM, from DRAM or L2 alike), while independent boxes overlap -- so a band is fetched as n_boxes
+      // row slabs that all complete on the same mbarrier.
       const int img0 = band0 / p.bands_per_img;
       int img = img0, bin = band0 - img0 * p.bands_per_img;
       uint32_t k = 0;
       for (int band = band0; band < band1; ++band, ++k) {
         const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
         ptx::mbar_wait(bar_hempty + 8 * buf, hph ^ 1u);
+        if (p.trace && blockIdx.x == 0) p.trace[0 * 256 + (k & 255)] = clock64();
         const uint32_t full = bar_hfull + 8 * buf;
         ptx::mbar_arrive_expect_tx(full, (uint32_t)(CHUNKS * p.plane_tx_bytes));
         const uint32_t halo = smem_halo + buf * p.halo_bytes;
-        if (p.a_rows) {
-          ptx::tma_load_4d(&mapA, full, halo, 0, -1, bin * p.bh - 1, img);    // one box: whole pixels, swizzled rows
-        } else {
+        const int y_top = bin * p.bh - 1;
+        for (int b = 0; b < p.n_boxes; ++b) {
+          const uint32_t slab = (uint32_t)(b * p.box_rows * p.Wp);          // first halo pixel of this slab
+          if (p.a_rows) {
+            ptx::tma_load_4d(&mapA, full, halo + slab * (uint32_t)(C * 2), 0, -1, y_top + b * p.box_rows, img);
+          } else {
 #pragma unroll
-          for (int c = 0; c < CHUNKS; ++c)
-            ptx::tma_load_4d(&mapA, full, halo + (uint32_t)c * (uint32_t)p.P_alloc * 16u, 8 * c, -1, bin * p.bh - 1, img);
+            for (int c = 0; c < CHUNKS; ++c)
+              ptx::tma_load_4d(&mapA, full, halo + ((uint32_t)c * (uint32_t)p.P_alloc + slab) * 16u, 8 * c, -1, y_top + b * p.box_rows, img);
+          }
         }
         if (++bin == p.bands_per_img) { bin = 0; ++img; }
       }
@@ -189,6 +200,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
       ptx::mbar_wait(bar_hfull + 8 * buf, hph);
       ptx::tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(1 + parity) * 256 + (k & 255)] = clock64();
       const uint32_t a_lo0 = tc_desc_lo(smem_halo + buf * p.halo_bytes, a_lbo);
       const int n_sub = w.n_sub;
       for (int j = 0; j < n_sub; ++j) {
@@ -209,6 +221,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
               }
             }
             ptx::umma_commit(bar_tfull + 8 * acc);
+            if (p.trace && blockIdx.x == 0) p.trace[(3 + parity) * 256 + ((w.it >> 1) & 255)] = clock64();
           }
           __syncwarp();
         }
@@ -235,6 +248,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     HaloWalk w;
     w.init(p, band0, band1);
     for (int i = 0; i < grp && w.valid(); ++i) w.step(p);
+    uint32_t trace_n = 0;
 
     auto locate = [&](const HaloWalk& t, bool& live, size_t& off0) {
       const int mp = t.j * 128 + row;
@@ -270,6 +284,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
       ptx::mbar_wait(bar_tfull + 8 * acc, aph);
       ptx::tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0) p.trace[(5 + grp) * 256 + (trace_n & 255)] = clock64();
 #pragma unroll
       for (int v = 0; v < NV; v += 2) {
         constexpr int dummy = 0;
@@ -289,6 +304,8 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_tempty + 8 * acc);
+      if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0) p.trace[(8 + grp) * 256 + (trace_n & 255)] = clock64();
+      ++trace_n;
     }
   }
 
@@ -307,9 +324,16 @@ struct TcHaloState {
 };
 
 // pixels of one 8-channel plane: the TMA box ((bh + 3) rows of Wp) and the furthest tap read of the last sub-tile
-static int halo_plane_pixels(int bh, int Wp) {
+// halo rows per TMA box: the smallest count >= 2 whose slab starts stay 128-byte aligned in shared memory
+static int halo_box_rows(int Wp, int row_bytes) {
+  int r = 2;
+  while ((r * Wp * row_bytes) % 128) ++r;
+  return r;
+}
+static int halo_plane_pixels(int bh, int Wp, int box_rows) {
   const int n_sub = (bh * Wp + 127) / 128;
-  const int reach = n_sub * 128 + 2 * Wp + 2, box = (bh + 3) * Wp;
+  const int n_boxes = (bh + 3 + box_rows - 1) / box_rows;
+  const int reach = n_sub * 128 + 2 * Wp + 2, box = n_boxes * box_rows * Wp;
   return ((reach > box ? reach : box) + 7) & ~7;
 }
 
@@ -327,6 +351,11 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   p.cpt = C / p.kb;
   p.b_chunk_bytes = Cout * p.kb * 2;
   p.b_bytes = 9 * p.cpt * p.b_chunk_bytes;
+  // un-swizzled 8-channel planes work for every C; swizzled whole-pixel rows need a power-of-two row (and move 4-8x
+  // fewer TMA elements).  UMMA applies the swizzle XOR to the absolute shared-memory address, so the shifted-window
+  // starts need no descriptor base offset (measured on B200: base_offset = 0 is exact, (start >> 7) & 7 is wrong).
+  p.a_rows = op.i[13] != 2 && (C == 16 || C == 32 || C == 64);
+  p.box_rows = halo_box_rows(p.Wp, p.a_rows ? C * 2 : 16);
   const int b_region = (p.b_bytes + 1023) & ~1023;
   const int budget = TC_SMEM_LIMIT - 1024 - HALO_HEADER_BYTES - b_region;
   // band height: fewest 128-row sub-tiles per image, then the tallest band (fewest halo re-reads)
@@ -334,9 +363,9 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   long long best_tiles = 1ll << 60;
   for (int bh = 1; bh <= H; ++bh) {
     const int n_sub_full = (bh * p.Wp + 127) / 128;
-    const int P_alloc = halo_plane_pixels(bh, p.Wp);
+    const int P_alloc = halo_plane_pixels(bh, p.Wp, p.box_rows);
     const long long halo_bytes = ((long long)P_alloc * C * 2 + 1023) & ~1023ll;
-    if (P_alloc > 16383 || bh + 3 > 256 || 2 * halo_bytes > budget) break;
+    if (P_alloc > 16383 || 2 * halo_bytes > budget) break;
     const int full = H / bh, rem = H - full * bh;
     long long tiles = (long long)full * n_sub_full + (rem ? (rem * p.Wp + 127) / 128 : 0);
     if (tiles < best_tiles || (tiles == best_tiles && bh > best_bh)) { best_tiles = tiles; best_bh = bh; }
@@ -349,9 +378,10 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   p.num_bands = (int)nb;
   const int n_sub_full = (p.bh * p.Wp + 127) / 128;
   (void)n_sub_full;
-  p.P_alloc = halo_plane_pixels(p.bh, p.Wp);
+  p.P_alloc = halo_plane_pixels(p.bh, p.Wp, p.box_rows);
   p.halo_bytes = (p.P_alloc * C * 2 + 1023) & ~1023;
-  p.plane_tx_bytes = (p.bh + 3) * p.Wp * 16;
+  p.n_boxes = (p.bh + 3 + p.box_rows - 1) / p.box_rows;
+  p.plane_tx_bytes = p.n_boxes * p.box_rows * p.Wp * 16;
   p.acc_stages = HALO_MAX_ACC;
   int cols = 32;
   while (cols < p.acc_stages * Cout) cols <<= 1;
@@ -379,14 +409,8 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
   const bool bf16 = op.dtype_in == CAPF_BF16;
   p.idesc = tc_idesc(bf16, p.Cout);
   p.b_desc_hi = tc_desc_hi(p.kb * 2, 8 * p.kb * 2);
-  const int variant = op.i[13];
-  // un-swizzled 8-channel planes work for every C; swizzled whole-pixel rows need a power-of-two row (and move 4-8x
-  // fewer TMA elements).  UMMA applies the swizzle XOR to the absolute shared-memory address, so the shifted-window
-  // starts need no descriptor base offset (measured on B200: base_offset = 0 is exact, (start >> 7) & 7 is wrong).
-  p.a_rows = variant != 2 && (p.C == 16 || p.C == 32 || p.C == 64);
   if (p.a_rows) {
     p.a_desc_hi = tc_desc_hi(p.C * 2, 8 * p.C * 2);   // swizzle span == pixel row; 8-row groups contiguous
-    p.plane_tx_bytes = (p.bh + 3) * p.Wp * 16;        // x CHUNKS == the single whole-pixel box
   } else {
     p.a_desc_hi = tc_desc_hi(0, 128);                 // un-swizzled: 8-row groups are 128 contiguous bytes
   }
@@ -395,6 +419,7 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
   p.bias = (const float*)op.in[2];
   p.res = op.in[3];
   p.out = op.out[0];
+  p.trace = (long long*)op.in[4];     // debug only (NULL in every program the host layer builds)
   s->grid = p.num_bands < g_num_sms ? p.num_bands : g_num_sms;
   s->dtype_in = op.dtype_in;
   s->dtype_out = op.dtype_out;
@@ -409,7 +434,7 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
     // 8-channel planes of the NHWC input: box {8, Wp, bh + 3, 1}, no swizzle (16-byte rows = UMMA core-matrix rows)
     cuuint64_t adims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.Nimg};
     cuuint64_t astr[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
-    cuuint32_t abox[4] = {(cuuint32_t)(p.a_rows ? p.C : 8), (cuuint32_t)p.Wp, (cuuint32_t)(p.bh + 3), 1};
+    cuuint32_t abox[4] = {(cuuint32_t)(p.a_rows ? p.C : 8), (cuuint32_t)p.Wp, (cuuint32_t)p.box_rows, 1};
     cuuint32_t aes[4] = {1, 1, 1, 1};
     e = tc_encode_map(&s->mapA, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, op.in[0], adims, astr, abox,
                       aes, p.a_rows ? p.C * 2 : 0, "A halo");
