@@ -533,8 +533,78 @@ __global__ void __launch_bounds__(256) layernorm_kernel(int rows, int D, int per
   }
 }
 
+// LayerNorm + narrow Linear (the head, pose_dformer.py:205-208,240): one warp per row, everything in fp32.
+template <int MAXV, int MAXP>
+__global__ void __launch_bounds__(256) layernorm_proj_kernel(int rows, int D, int nproj, float eps, const float* __restrict__ x,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ Wp, const float* __restrict__ bp,
+                                                             float* __restrict__ y) {
+  pdl_wait();
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (size_t)warp * D;
+  const int nv = D >> 7;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      v[i] = __ldg(reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4));
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  float acc[MAXP];
+#pragma unroll
+  for (int o = 0; o < MAXP; ++o) acc[o] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 n;
+      n.x = (v[i].x - mean) * rstd * g.x + b.x;
+      n.y = (v[i].y - mean) * rstd * g.y + b.y;
+      n.z = (v[i].z - mean) * rstd * g.z + b.z;
+      n.w = (v[i].w - mean) * rstd * g.w + b.w;
+#pragma unroll
+      for (int o = 0; o < MAXP; ++o) {
+        if (o < nproj) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(Wp + (size_t)o * D + c));
+          acc[o] = fmaf(n.x, w.x, fmaf(n.y, w.y, fmaf(n.z, w.z, fmaf(n.w, w.w, acc[o]))));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < MAXP; ++o) {
+    if (o < nproj) {
+      const float t = warp_sum(acc[o]);
+      if (lane == 0) y[(size_t)warp * nproj + o] = t + (bp ? __ldg(bp + o) : 0.f);
+    }
+  }
+}
+
 int launch_layernorm(const capf_op& op, cudaStream_t st) {
   int rows = op.i[0], D = op.i[1], period = op.i[2];
+  if (op.i[3] > 0) {
+    const int np = op.i[3];
+    if (np > 8 || period != 0 || op.dtype_in != CAPF_F32 || op.dtype_out != CAPF_F32 || !op.in[4] || (D & 127) || D > 1024 || rows <= 0)
+      return set_error(CAPF_ERR_ARG, "layernorm+proj: n_proj <= 8, no x0, f32 in/out, D % 128 == 0, D <= 1024");
+    launch_k(layernorm_proj_kernel<8, 8>, dim3((rows + 7) / 8), dim3(256), 0, st, rows, D, np, op.f[0], (const float*)op.in[0],
+             (const float*)op.in[1], (const float*)op.in[2], (const float*)op.in[4], (const float*)op.in[5], (float*)op.out[0]);
+    return check_launch("layernorm_proj");
+  }
   if (rows <= 0 || D <= 0 || (D & 127) || D > 128 * 8) return set_error(CAPF_ERR_ARG, "layernorm: D must be a multiple of 128, <= 1024");
   if (op.dtype_in != CAPF_F32) return set_error(CAPF_ERR_UNSUPPORTED, "layernorm: input stream is f32");
   if (period > 0 && !op.in[3]) return set_error(CAPF_ERR_ARG, "layernorm: period without x0");
@@ -728,7 +798,9 @@ __global__ void __launch_bounds__(256) ref_sample_kernel(SampP p, const float* _
 }
 
 // (a8) deformable gather, padding_mode='border' (pose_dformer.py:122-135). One warp per (level, b, j, head):
-// softmax over the head's 4 logits, tanh offsets, 4 samples x 4 corners, sample-weighted sum.
+// softmax over the head's 4 logits, tanh offsets, 4 samples x 4 corners, sample-weighted sum.  Narrow levels do not fill
+// a warp with channels (C = 32 is 8 lanes of 4), so the 32 lanes are split into G = 32 / L groups (L = lanes that
+// cover the channels) and each group takes 4 / G of the samples; the partial sums meet through shuffles.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) deform_sample_kernel(SampP p, const float* __restrict__ ref,
                                                             const float* __restrict__ ow, TO* __restrict__ out,
@@ -744,6 +816,9 @@ __global__ void __launch_bounds__(256) deform_sample_kernel(SampP p, const float
   int rj = (int)(t % R), l = (int)(t / R);
   int b = rj / p.J;
   const int H = p.H[l], W = p.W[l], C = p.C[l];
+  const int L = C <= 32 ? 8 : C <= 64 ? 16 : 32;      // lanes per sample group
+  const int G = 32 / L;                               // sample groups: 4, 2 or 1
+  const int grp = lane / L, li = lane - grp * L;
   const float* row = ow + ((size_t)l * R + rj) * 48;
   float lg[4], mx = -INFINITY;
 #pragma unroll
@@ -752,45 +827,65 @@ __global__ void __launch_bounds__(256) deform_sample_kernel(SampP p, const float
 #pragma unroll
   for (int s = 0; s < 4; ++s) { lg[s] = expf(lg[s] - mx); den += lg[s]; }
   float gx = __ldg(ref + 2 * rj), gy = __ldg(ref + 2 * rj + 1);
-  Corners c[4];
-  float aw[4];
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    aw[s] = lg[s] / den;
-    float ox = tanhf(__ldg(row + 16 + (h * 4 + s) * 2)), oy = tanhf(__ldg(row + 16 + (h * 4 + s) * 2 + 1));
-    const float px = __fadd_rn(ox, gx), py = __fadd_rn(oy, gy);
-    c[s] = make_corners<true>(px, py, W, H);
-    if (rec && lane == 0) {
-      int* r = rec + ((((size_t)l * R + rj) * 16) + h * 4 + s) * 8;
-      r[0] = c[s].x0; r[1] = c[s].y0; r[2] = (int)c[s].mask; r[3] = 0;
-      r[4] = __float_as_int(px); r[5] = __float_as_int(py); r[6] = 0; r[7] = 0;
-    }
-  }
   const TI* m = (const TI*)p.map[l] + (size_t)b * H * W * C;
   TO* o = out + p.off[l] + ((size_t)rj * 4 + h) * C;
-  for (int ch = lane * 4; ch < C; ch += 128) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[2];                                        // up to 2 channel steps per lane (C <= 256); more loop below
+  for (int ch0 = 0; ch0 < C; ch0 += 256) {
+    acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      // every lane evaluates every sample's position (cheap, keeps the debug record complete); it only gathers its own
+      const float aw = lg[s] / den;
+      float ox = tanhf(__ldg(row + 16 + (h * 4 + s) * 2)), oy = tanhf(__ldg(row + 16 + (h * 4 + s) * 2 + 1));
+      const float px = __fadd_rn(ox, gx), py = __fadd_rn(oy, gy);
+      const Corners c = make_corners<true>(px, py, W, H);
+      if (rec && lane == 0 && ch0 == 0) {
+        int* r = rec + ((((size_t)l * R + rj) * 16) + h * 4 + s) * 8;
+        r[0] = c.x0; r[1] = c.y0; r[2] = (int)c.mask; r[3] = 0;
+        r[4] = __float_as_int(px); r[5] = __float_as_int(py); r[6] = 0; r[7] = 0;
+      }
+      if ((s & (G - 1)) != grp) continue;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (c[s].mask & (1u << k)) {
-          int xx = c[s].x0 + (k & 1), yy = c[s].y0 + (k >> 1);
-          float4 v = ld4<TI>(m + ((size_t)yy * W + xx) * C + ch);
-          float wk = c[s].w[k];
-          a.x = __fadd_rn(a.x, __fmul_rn(v.x, wk));
-          a.y = __fadd_rn(a.y, __fmul_rn(v.y, wk));
-          a.z = __fadd_rn(a.z, __fmul_rn(v.z, wk));
-          a.w = __fadd_rn(a.w, __fmul_rn(v.w, wk));
+      for (int it = 0; it < 2; ++it) {
+        const int ch = ch0 + (it * L + li) * 4;
+        if (ch < C && (it == 0 || L == 32)) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (c.mask & (1u << k)) {
+              int xx = c.x0 + (k & 1), yy = c.y0 + (k >> 1);
+              float4 v = ld4<TI>(m + ((size_t)yy * W + xx) * C + ch);
+              float wk = c.w[k];
+              a.x = __fadd_rn(a.x, __fmul_rn(v.x, wk));
+              a.y = __fadd_rn(a.y, __fmul_rn(v.y, wk));
+              a.z = __fadd_rn(a.z, __fmul_rn(v.z, wk));
+              a.w = __fadd_rn(a.w, __fmul_rn(v.w, wk));
+            }
+          }
+          acc[it].x = fmaf(aw, a.x, acc[it].x);
+          acc[it].y = fmaf(aw, a.y, acc[it].y);
+          acc[it].z = fmaf(aw, a.z, acc[it].z);
+          acc[it].w = fmaf(aw, a.w, acc[it].w);
         }
       }
-      acc.x = fmaf(aw[s], a.x, acc.x);
-      acc.y = fmaf(aw[s], a.y, acc.y);
-      acc.z = fmaf(aw[s], a.z, acc.z);
-      acc.w = fmaf(aw[s], a.w, acc.w);
     }
-    st4<TO>(o + ch, acc);
+    // combine the sample groups (lanes li, li + L, ...)
+    for (int off = L; off < 32; off <<= 1) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        acc[it].x += __shfl_xor_sync(0xffffffffu, acc[it].x, off);
+        acc[it].y += __shfl_xor_sync(0xffffffffu, acc[it].y, off);
+        acc[it].z += __shfl_xor_sync(0xffffffffu, acc[it].z, off);
+        acc[it].w += __shfl_xor_sync(0xffffffffu, acc[it].w, off);
+      }
+    }
+    if (grp == 0) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int ch = ch0 + (it * L + li) * 4;
+        if (ch < C && (it == 0 || L == 32)) st4<TO>(o + ch, acc[it]);
+      }
+    }
   }
 }
 

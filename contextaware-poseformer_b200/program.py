@@ -382,9 +382,13 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
         block(f"{vn}joint_blocks.{i}", Y, R, E, 8, B, J, 1, J)
 
     # ---- (a10) head ----------------------------------------------------------------------------------------
-    t = pb.layernorm(Y, R, E, vn + "head.0", 1e-5, adt, tag=vn + "head.0")
     out = Buf("out", (R, 3), "f32", "output")
-    pb.linear(t, R, E, [vn + "head.1.weight"], [vn + "head.1.bias"], 3, out=out, tag=vn + "head.1")
+    pb._emit(lib.OP_LAYERNORM, "f32", "f32", [R, E, 0, 3], [1e-5],
+             [Y, WSlot("g:head.0", (E,), "f32", vec_packer([vn + "head.0.weight"])),
+              WSlot("b:head.0", (E,), "f32", vec_packer([vn + "head.0.bias"])), None,
+              WSlot("w:head.1", (3, E), "f32", vec_packer([vn + "head.1.weight"])),
+              WSlot("b:head.1", (3,), "f32", vec_packer([vn + "head.1.bias"]))], [out],
+             tag=vn + "head", flops=2 * R * E * 3)
     prog.outputs["out"] = out
     return prog
 

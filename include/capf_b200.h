@@ -91,9 +91,11 @@ typedef enum capf_op_kind {
  *
  * CAPF_OP_LAYERNORM -- nn.LayerNorm over the last dim (pose_dformer.py:65,72,120,138,206), optionally of
  *                    (x + x0) with x0 broadcast every `period` rows (the `x + x_0` of :120).
- *     i[0]=rows i[1]=D i[2]=period(0 = no x0)   f[0]=eps
+ *     i[0]=rows i[1]=D i[2]=period(0 = no x0)  i[3]=n_proj(0 = none)   f[0]=eps
  *     in[0]=x [rows][D] f32  in[1]=gamma f32  in[2]=beta f32  in[3]=x0 [period][D] f32 or NULL
  *     out[0]=y [rows][D] dtype_out
+ *     n_proj > 0 (<= 8) fuses a narrow nn.Linear behind the norm -- the head LayerNorm(640)+Linear(640->3) of
+ *     pose_dformer.py:205-208,240:  in[4]=W [n_proj][D] f32, in[5]=b [n_proj] f32 or NULL, out[0]=[rows][n_proj] f32
  *
  * CAPF_OP_ATTENTION -- Attention.forward softmax(q k^T * scale) v  (pose_dformer.py:47-55) for the two tiny
  *                    sequence shapes of the model: 5 levels of one joint (:231-234) or 17 joints (:235-238).

@@ -85,7 +85,10 @@ class Interp:
             x = x + self.t(op.ins[3]).reshape(period, D).repeat(rows // period, 1)
         y = F.layer_norm(x, (D,), self.t(op.ins[1]), self.t(op.ins[2]), op.f[0])
         out = self.t(op.outs[0])
-        out.copy_(y.to(out.dtype))
+        if len(op.i) > 3 and op.i[3]:        # fused projection (the head: LayerNorm + Linear(D -> n), pose_dformer.py:205-208)
+            n = op.i[3]
+            y = y @ self.t(op.ins[4]).reshape(n, D).t() + self.t(op.ins[5]).reshape(n)
+        out.copy_(y.reshape(out.shape).to(out.dtype))
 
     def _op6(self, op):   # ATTENTION
         groups, seq, heads, hd, ts, gs = op.i[:6]

@@ -189,6 +189,20 @@ def test_samplers_match_aten_values():
         assert (got - want).abs().max() < 2e-5
 
 
+def test_layernorm_with_fused_head_projection():
+    """head = LayerNorm(640, eps 1e-5) + Linear(640 -> 3) (pose_dformer.py:205-208,240) as one op."""
+    g = _gen(9)
+    rows, D = 53, 640
+    x = torch.randn(rows, D, generator=g) * 3 + 0.5
+    gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    Wp, bp = torch.randn(3, D, generator=g) / D ** 0.5, torch.randn(3, generator=g)
+    want = F.linear(F.layer_norm(x, (D,), gamma, beta, 1e-5), Wp, bp)
+    out = torch.empty(rows, 3, device=DEV)
+    run_op(lib.OP_LAYERNORM, torch.float32, torch.float32, [rows, D, 0, 3], [1e-5],
+           [x.to(DEV), gamma.to(DEV), beta.to(DEV), None, Wp.to(DEV), bp.to(DEV)], [out])
+    assert (out.cpu() - want).abs().max() < 2e-5
+
+
 def test_token_glue_ops():
     g = _gen(7)
     B, J, D, S = 3, 17, 128, 5
