@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <type_traits>
+
 #include "capf_common.cuh"
 #include "capf_internal.h"
 
@@ -123,6 +125,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -264,6 +279,51 @@ int tc_halo_supported(const capf_op& op);
 int tc_halo_prepare(const capf_op& op, TcHaloState** out);
 int tc_halo_launch(const TcHaloState* s, cudaStream_t st);
 void tc_halo_release(TcHaloState* s);
+
+// Same for a 16-bit output row staged in shared memory: the residual (if any) is read from, and the result written
+// back to, the two 16-byte chunks at smem addresses s0 / s1.
+template <typename TO>
+__device__ __forceinline__ void finish16_smem(const Bias16& bs, int act, const uint32_t (&raw)[16], bool has_res, uint32_t s0, uint32_t s1) {
+  static_assert(sizeof(TO) == 2, "staged epilogue is for 16-bit outputs");
+  float v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    v[4 * q4] += bs.b[q4].x; v[4 * q4 + 1] += bs.b[q4].y; v[4 * q4 + 2] += bs.b[q4].z; v[4 * q4 + 3] += bs.b[q4].w;
+  }
+  if (act == CAPF_ACT_GELU) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
+  }
+  if (has_res) {
+    Vec16<TO> rv;
+    rv.v[0] = ptx::ld_shared_v4(s0);
+    rv.v[1] = ptx::ld_shared_v4(s1);
+    rv.add_to(v);
+  }
+  if (act == CAPF_ACT_RELU) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+  }
+  uint4 o[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t* po = reinterpret_cast<uint32_t*>(&o[h]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if constexpr (std::is_same<TO, __half>::value) {
+        __half2 t = __floats2half2_rn(v[8 * h + 2 * e], v[8 * h + 2 * e + 1]);
+        po[e] = *reinterpret_cast<uint32_t*>(&t);
+      } else {
+        __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * h + 2 * e], v[8 * h + 2 * e + 1]);
+        po[e] = *reinterpret_cast<uint32_t*>(&t);
+      }
+    }
+  }
+  ptx::st_shared_v4(s0, o[0]);
+  ptx::st_shared_v4(s1, o[1]);
+}
 
 // host helpers (capf_tc.cu)
 int tc_get_encoder();

@@ -151,9 +151,6 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       ptx::mbar_arrive_expect_tx(bar_b, (uint32_t)p.b_bytes);
       for (int c = 0; c < 9 * CPT; ++c) ptx::tma_load_2d(&mapB, bar_b, smem_b + c * p.b_chunk_bytes, c * KB, 0);
       pdl_wait();                                     // activations of the predecessor are read from here on
-      // One TMA box is served with little request parallelism (measured: a single 79 KB box of 64-byte rows arrives
-      // at ~6 B/clk/SM, from DRAM or L2 alike), while independent boxes overlap -- so a band is fetched as n_boxes
-      // row slabs that all complete on the same mbarrier.
       const int img0 = band0 / p.bands_per_img;
       int img = img0, bin = band0 - img0 * p.bands_per_img;
       uint32_t k = 0;
@@ -198,16 +195,21 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     uint32_t k = 0;
     while (w.valid()) {
       const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
+      long long tw0 = 0;
+      if (p.trace && blockIdx.x == 0 && lane == 0) tw0 = clock64();
       ptx::mbar_wait(bar_hfull + 8 * buf, hph);
       ptx::tc_fence_after();
-      if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(1 + parity) * 256 + (k & 255)] = clock64();
+      if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(1 + parity) * 256 + (k & 255)] = clock64() - tw0;   // halo wait
       const uint32_t a_lo0 = tc_desc_lo(smem_halo + buf * p.halo_bytes, a_lbo);
       const int n_sub = w.n_sub;
       for (int j = 0; j < n_sub; ++j) {
         if ((w.it & 1u) == parity) {
           const uint32_t acc = w.acc(), aph = w.use_parity();
+          long long tw1 = 0;
+          if (p.trace && blockIdx.x == 0 && lane == 0) tw1 = clock64();
           ptx::mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
           ptx::tc_fence_after();
+          if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(12 + parity) * 256 + ((w.it >> 1) & 255)] = clock64() - tw1;  // tempty wait
           if (ptx::elect_one()) {
             const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
             const uint32_t a_sub = a_lo0 + (uint32_t)(j * 128) * pix_units;
@@ -234,61 +236,65 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =========================================
-    // Three 4-warp groups take sub-tiles round-robin.  Narrow outputs (NV <= 2 vectors of 16 columns) request the
-    // residual of the group's NEXT sub-tile before finishing the current one, so its DRAM latency is covered by a
-    // whole sub-tile period; wide ones request it at the top of the tile, ahead of the accumulator wait.
+    // Three 4-warp groups take sub-tiles round-robin; a warp owns 32 accumulator rows (= 32 consecutive padded pixels).
+    // All global traffic of the epilogue goes through a warp-private, XOR-swizzled staging tile of 32 pixels x Cout:
+    //   * the residual of the warp's NEXT sub-tile is requested with cp.async right after the current one has been
+    //     written out (a whole group period ahead of its use), 16 bytes per lane, consecutive lanes -> consecutive
+    //     addresses (a per-row-per-thread LDG pattern would touch 16-32 cache lines per instruction and made the LSU,
+    //     not the tensor pipe, the limiter of the C = 64 layers);
+    //   * each thread adds its row in place (conflict-free row-wise access thanks to the swizzle);
+    //   * the finished tile leaves with the same coalesced lane mapping.
     constexpr int NG = HALO_EPI_GROUPS;
-    constexpr bool AHEAD = NV <= 2;
+    constexpr int CH = NV * 2;                        // 16-byte chunks per pixel row of the staging tile
+    constexpr int ROWB = NV * 32;                     // bytes per pixel row
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
-    const int row = q * 32 + lane;
     const TO* res = reinterpret_cast<const TO*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
+    const uint32_t stage = smem_halo + 2u * (uint32_t)p.halo_bytes + (uint32_t)(warp - 4) * (32u * ROWB);
+    // chunk c of pixel r lives at r * ROWB + ((c ^ swz(r)) * 16); swz keeps both access patterns conflict-free
+    // (CH = 6, i.e. Cout = 48, is not a power of two: stored plain, a few bank conflicts on that rare shape)
+    auto swz = [](int r) { return CH == 8 ? (r & 7) : CH == 4 ? ((r >> 1) & 3) : CH == 2 ? ((r >> 2) & 1) : 0; };
+    auto slot = [&](int r, int c) { return stage + (uint32_t)(r * ROWB + ((c ^ swz(r)) * 16)); };
 
     HaloWalk w;
     w.init(p, band0, band1);
     for (int i = 0; i < grp && w.valid(); ++i) w.step(p);
     uint32_t trace_n = 0;
 
-    auto locate = [&](const HaloWalk& t, bool& live, size_t& off0) {
-      const int mp = t.j * 128 + row;
+    // global element offset of padded pixel (sub-tile t, row r of this warp), or -1 when it is padding / past the band
+    auto pixel_off = [&](const HaloWalk& t, int r) -> long long {
+      const int mp = t.j * 128 + q * 32 + r;
       const int iy = div_wp(mp, p.wp_magic), ix = mp - iy * p.Wp;
-      live = t.valid() && ix < p.W && iy < t.bh_eff;
-      off0 = live ? (((size_t)t.img * p.H + t.y0 + iy) * p.W + ix) * p.Cout : 0;
+      const bool live = t.valid() && ix < p.W && iy < t.bh_eff;
+      return live ? (long long)((((size_t)t.img * p.H + t.y0 + iy) * p.W + ix) * p.Cout) : -1;
     };
-    auto fetch = [&](Vec16<TO> (&r)[NV], bool live, size_t off0) {
-      if (res && live) {
+    // coalesced lane mapping: item = i * 32 + lane -> (pixel row r = item / CH, chunk c = item % CH)
+    auto prefetch_residual = [&](const HaloWalk& t) {
+      if (res == nullptr) return;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) r[v].load(res + off0 + 16 * v);
+      for (int i = 0; i < CH; ++i) {
+        const int item = i * 32 + lane, r = item / CH, c = item % CH;
+        const long long off = pixel_off(t, r);
+        if (off >= 0) ptx::cp_async16(slot(r, c), res + off + c * 8);
       }
+      ptx::cp_async_commit();
     };
-    Vec16<TO> rcur[NV], rnext[AHEAD ? NV : 1];
-    bool live_n;
-    size_t off_n;
-    locate(w, live_n, off_n);
-    if constexpr (AHEAD) fetch(rnext, live_n, off_n);
+    prefetch_residual(w);
     while (w.valid()) {
       const uint32_t acc = w.acc(), aph = w.use_parity();
-      const bool live = live_n;
-      const size_t off0 = off_n;
-      const bool has_res = live && res != nullptr;
-      if constexpr (AHEAD) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) rcur[v] = rnext[v];
-      } else {
-        fetch(rcur, live, off0);
-      }
+      const HaloWalk cur = w;
       for (int i = 0; i < NG && w.valid(); ++i) w.step(p);
-      locate(w, live_n, off_n);
-      if constexpr (AHEAD) fetch(rnext, live_n, off_n);
+      const bool live = pixel_off(cur, lane) >= 0;
+      const bool has_res = live && res != nullptr;
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
       ptx::mbar_wait(bar_tfull + 8 * acc, aph);
       ptx::tc_fence_after();
       if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0) p.trace[(5 + grp) * 256 + (trace_n & 255)] = clock64();
+      ptx::cp_async_wait_all();                      // this tile's residual (requested one group period ago) has landed
+      __syncwarp();
 #pragma unroll
       for (int v = 0; v < NV; v += 2) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const bool two = v + 1 < NV;
         uint32_t a0[16], a1[16];
         ptx::tmem_ld16(taddr + (uint32_t)(16 * v), a0);
@@ -297,13 +303,20 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         b0.load(p.bias, 16 * v);
         if (two) b1.load(p.bias, 16 * v + 16);
         ptx::tmem_ld_wait();
-        if (live) {
-          finish16<TO>(b0, p.act, a0, rcur[v], has_res, out + off0 + 16 * v);
-          if (two) finish16<TO>(b1, p.act, a1, rcur[two ? v + 1 : v], has_res, out + off0 + 16 * v + 16);
-        }
+        finish16_smem<TO>(b0, p.act, a0, has_res, slot(lane, 2 * v), slot(lane, 2 * v + 1));
+        if (two) finish16_smem<TO>(b1, p.act, a1, has_res, slot(lane, 2 * v + 2), slot(lane, 2 * v + 3));
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(bar_tempty + 8 * acc);
+      ptx::mbar_arrive(bar_tempty + 8 * acc);          // accumulator drained: the issuer may reuse the stage
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int item = i * 32 + lane, r = item / CH, c = item % CH;
+        const long long off = pixel_off(cur, r);
+        if (off >= 0) *reinterpret_cast<uint4*>(out + off + c * 8) = ptx::ld_shared_v4(slot(r, c));
+      }
+      __syncwarp();
+      prefetch_residual(w);
       if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0) p.trace[(8 + grp) * 256 + (trace_n & 255)] = clock64();
       ++trace_n;
     }
@@ -324,12 +337,10 @@ struct TcHaloState {
 };
 
 // pixels of one 8-channel plane: the TMA box ((bh + 3) rows of Wp) and the furthest tap read of the last sub-tile
-// halo rows per TMA box: the smallest count >= 2 whose slab starts stay 128-byte aligned in shared memory
-static int halo_box_rows(int Wp, int row_bytes) {
-  int r = 2;
-  while ((r * Wp * row_bytes) % 128) ++r;
-  return r;
-}
+// Halo rows per TMA box.  Measured with tools/microbench/tma_bench.cu on B200: a box costs ~350 cycles of TMA-engine
+// time plus ~1 cycle per 64 bytes, whatever its shape (64- or 128-byte rows, with or without zero-filled columns), so
+// a band is fetched as ONE box (79 KB in 1.9k cycles = 42 B/clk/SM) unless it exceeds the 256-row box limit.
+static int halo_box_rows(int bh) { return bh + 3 <= 256 ? bh + 3 : 128; }
 static int halo_plane_pixels(int bh, int Wp, int box_rows) {
   const int n_sub = (bh * Wp + 127) / 128;
   const int n_boxes = (bh + 3 + box_rows - 1) / box_rows;
@@ -355,15 +366,15 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   // fewer TMA elements).  UMMA applies the swizzle XOR to the absolute shared-memory address, so the shifted-window
   // starts need no descriptor base offset (measured on B200: base_offset = 0 is exact, (start >> 7) & 7 is wrong).
   p.a_rows = op.i[13] != 2 && (C == 16 || C == 32 || C == 64);
-  p.box_rows = halo_box_rows(p.Wp, p.a_rows ? C * 2 : 16);
   const int b_region = (p.b_bytes + 1023) & ~1023;
-  const int budget = TC_SMEM_LIMIT - 1024 - HALO_HEADER_BYTES - b_region;
+  const int stage_bytes = 4 * HALO_EPI_GROUPS * 32 * Cout * 2;   // warp-private epilogue staging tiles
+  const int budget = TC_SMEM_LIMIT - 1024 - HALO_HEADER_BYTES - b_region - stage_bytes;
   // band height: fewest 128-row sub-tiles per image, then the tallest band (fewest halo re-reads)
   int best_bh = 0;
   long long best_tiles = 1ll << 60;
   for (int bh = 1; bh <= H; ++bh) {
     const int n_sub_full = (bh * p.Wp + 127) / 128;
-    const int P_alloc = halo_plane_pixels(bh, p.Wp, p.box_rows);
+    const int P_alloc = halo_plane_pixels(bh, p.Wp, halo_box_rows(bh));
     const long long halo_bytes = ((long long)P_alloc * C * 2 + 1023) & ~1023ll;
     if (P_alloc > 16383 || 2 * halo_bytes > budget) break;
     const int full = H / bh, rem = H - full * bh;
@@ -378,6 +389,7 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   p.num_bands = (int)nb;
   const int n_sub_full = (p.bh * p.Wp + 127) / 128;
   (void)n_sub_full;
+  p.box_rows = halo_box_rows(p.bh);
   p.P_alloc = halo_plane_pixels(p.bh, p.Wp, p.box_rows);
   p.halo_bytes = (p.P_alloc * C * 2 + 1023) & ~1023;
   p.n_boxes = (p.bh + 3 + p.box_rows - 1) / p.box_rows;
@@ -387,7 +399,7 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   while (cols < p.acc_stages * Cout) cols <<= 1;
   p.tmem_cols = cols;
   p.acc_stride = Cout;
-  smem_bytes = 1024 + HALO_HEADER_BYTES + b_region + 2 * p.halo_bytes;
+  smem_bytes = 1024 + HALO_HEADER_BYTES + b_region + 2 * p.halo_bytes + stage_bytes;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM
   return 1;
 }
