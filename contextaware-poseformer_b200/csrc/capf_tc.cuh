@@ -130,6 +130,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
@@ -323,6 +324,43 @@ __device__ __forceinline__ void finish16_smem(const Bias16& bs, int act, const u
   }
   ptx::st_shared_v4(s0, o[0]);
   ptx::st_shared_v4(s1, o[1]);
+}
+
+// Generic staged variant: 16 output columns = sizeof(TO) chunks of 16 bytes at the shared-memory addresses s[].
+template <typename TO>
+__device__ __forceinline__ void finish16_stage(const Bias16& bs, int act, const uint32_t (&raw)[16], bool has_res,
+                                               const uint32_t (&s)[sizeof(TO)]) {
+  if constexpr (sizeof(TO) == 2) {
+    finish16_smem<TO>(bs, act, raw, has_res, s[0], s[1]);
+  } else {
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      v[4 * q4] += bs.b[q4].x; v[4 * q4 + 1] += bs.b[q4].y; v[4 * q4 + 2] += bs.b[q4].z; v[4 * q4 + 3] += bs.b[q4].w;
+    }
+    if (act == CAPF_ACT_GELU) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
+    }
+    if (has_res) {
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint4 r = ptx::ld_shared_v4(s[q4]);
+        v[4 * q4] += __uint_as_float(r.x); v[4 * q4 + 1] += __uint_as_float(r.y);
+        v[4 * q4 + 2] += __uint_as_float(r.z); v[4 * q4 + 3] += __uint_as_float(r.w);
+      }
+    }
+    if (act == CAPF_ACT_RELU) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+      ptx::st_shared_v4(s[q4], make_uint4(__float_as_uint(v[4 * q4]), __float_as_uint(v[4 * q4 + 1]), __float_as_uint(v[4 * q4 + 2]),
+                                          __float_as_uint(v[4 * q4 + 3])));
+  }
 }
 
 // host helpers (capf_tc.cu)
