@@ -166,6 +166,7 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     B, H, W = args.batch, args.height, args.width
     model, weights, cfg = build_model(args.backbone, args.precision, dev, graph=not args.no_graph)
