@@ -329,31 +329,78 @@ struct FuseP {
   const void* t[4];
 };
 
+// 16 bytes (8 x 16-bit or 4 x fp32 elements) per thread, 32-bit index arithmetic.
+template <typename T> struct Vec16B;
+template <> struct Vec16B<float> {
+  static constexpr int E = 4;
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) { float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec16B<__half> {
+  static constexpr int E = 8;
+  float v[8];
+  __device__ __forceinline__ void load(const __half* p) {
+    uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+  }
+  __device__ __forceinline__ void store(__half* p) const {
+    uint4 t;
+    __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+template <> struct Vec16B<__nv_bfloat16> {
+  static constexpr int E = 8;
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseP p, T* __restrict__ y) {
   pdl_wait();
-  const int C4 = p.C >> 2;
-  size_t total = (size_t)p.N * p.H * p.W * C4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % C4);
-    size_t pix = i / C4;
-    int xx = (int)(pix % p.W);
-    size_t t2 = pix / p.W;
-    int yy = (int)(t2 % p.H), n = (int)(t2 / p.H);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int E = Vec16B<T>::E;
+  const uint32_t CV = (uint32_t)p.C / E;                      // 16-byte vectors per pixel
+  const uint32_t rowv = (uint32_t)p.W * CV;                   // ... per image row
+  const uint32_t total = (uint32_t)p.N * p.H * rowv;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / rowv, inrow = i - r * rowv;        // r = n * H + y
+    const uint32_t xx = inrow / CV, cv = inrow - xx * CV;
+    const uint32_t n = r / (uint32_t)p.H, yy = r - n * (uint32_t)p.H;
+    Vec16B<T> a;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       if (t < p.nt) {
-        int s = p.sh[t];
-        size_t off = (((size_t)n * (p.H >> s) + (yy >> s)) * (p.W >> s) + (xx >> s)) * p.C + c4 * 4;
-        float4 v = ld4<T>((const T*)p.t[t] + off);
+        const int s = p.sh[t];
+        const size_t off = (((size_t)n * (p.H >> s) + (yy >> s)) * (p.W >> s) + (xx >> s)) * p.C + cv * E;
+        Vec16B<T> v;
+        v.load((const T*)p.t[t] + off);
         // first term initialises (reference: y = x[0] ... then y = y + term)
-        if (t == 0) a = v;
-        else { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+#pragma unroll
+        for (int e = 0; e < E; ++e) a.v[e] = t == 0 ? v.v[e] : a.v[e] + v.v[e];
       }
     }
-    if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-    st4<T>(y + i * 4, a);
+    if (p.relu) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) a.v[e] = fmaxf(a.v[e], 0.f);
+    }
+    a.store(y + (size_t)i * E);
   }
 }
 
@@ -368,7 +415,12 @@ int launch_fuse_sum(const capf_op& op, cudaStream_t st) {
       return set_error(CAPF_ERR_ARG, "fuse_sum: bad term");
   }
   if (op.dtype_in != op.dtype_out) return set_error(CAPF_ERR_UNSUPPORTED, "fuse_sum: dtype_in != dtype_out");
-  size_t total = (size_t)p.N * p.H * p.W * (p.C / 4);
+  const int E = op.dtype_out == CAPF_F32 ? 4 : 8;              // elements per 16-byte vector
+  if (p.C % E) return set_error(CAPF_ERR_ARG, "fuse_sum: C must be a multiple of 16 bytes of elements");
+  size_t total = (size_t)p.N * p.H * p.W * (p.C / E);
+  if (total >= (1ull << 31)) return set_error(CAPF_ERR_UNSUPPORTED, "fuse_sum: tensor too large for 32-bit indexing");
+  for (int t = 0; t < p.nt; ++t)
+    if ((uintptr_t)p.t[t] & 15) return set_error(CAPF_ERR_ARG, "fuse_sum: terms must be 16-byte aligned");
   int blocks = (int)((total + 255) / 256 < (size_t)g_num_sms * 16 ? (total + 255) / 256 : (size_t)g_num_sms * 16);
   if (blocks < 1) blocks = 1;
   switch (op.dtype_out) {
