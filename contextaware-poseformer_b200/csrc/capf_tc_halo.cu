@@ -15,6 +15,7 @@
 // Roles (512 threads): warp 0 = TMA producer (weights once, then the halo of each band; out-of-image elements are
 // zero-filled by TMA), warps 1 and 3 = tcgen05.mma issuers, warp 2 = TMEM allocator, warps 4..15 = three 4-warp
 // epilogue groups taking 128-row sub-tiles round-robin.  Halo bands are double buffered; four TMEM accumulators.
+#include <cstdlib>
 #include <new>
 
 #include "capf_tc.cuh"
@@ -48,6 +49,7 @@ struct HaloP {
   const float* bias;
   const void* res;
   void* out;
+  int l2_hints;             // 1: evict_first input / residual reads, evict_last output writes (env CAPF_L2_HINTS)
   long long* trace;         // optional (debug): per-role clock64 timeline of CTA 0, see tools/halo_trace.py
 };
 
@@ -153,6 +155,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       pdl_wait();                                     // activations of the predecessor are read from here on
       const int img0 = band0 / p.bands_per_img;
       int img = img0, bin = band0 - img0 * p.bands_per_img;
+      const uint64_t pol_in = p.l2_hints ? ptx::policy_evict_first() : 0;
       uint32_t k = 0;
       for (int band = band0; band < band1; ++band, ++k) {
         const uint32_t buf = k & 1u, hph = (k >> 1) & 1u;
@@ -165,7 +168,8 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         for (int b = 0; b < p.n_boxes; ++b) {
           const uint32_t slab = (uint32_t)(b * p.box_rows * p.Wp);          // first halo pixel of this slab
           if (p.a_rows) {
-            ptx::tma_load_4d(&mapA, full, halo + slab * (uint32_t)(C * 2), 0, -1, y_top + b * p.box_rows, img);
+            if (p.l2_hints) ptx::tma_load_4d_hint(&mapA, full, halo + slab * (uint32_t)(C * 2), 0, -1, y_top + b * p.box_rows, img, pol_in);
+            else ptx::tma_load_4d(&mapA, full, halo + slab * (uint32_t)(C * 2), 0, -1, y_top + b * p.box_rows, img);
           } else {
 #pragma unroll
             for (int c = 0; c < CHUNKS; ++c)
@@ -261,6 +265,7 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     w.init(p, band0, band1);
     for (int i = 0; i < grp && w.valid(); ++i) w.step(p);
     uint32_t trace_n = 0;
+    const uint64_t pol_in = ptx::policy_evict_first(), pol_out = ptx::policy_evict_last();
 
     // global element offset of padded pixel (sub-tile t, row r of this warp), or -1 when it is padding / past the band
     auto pixel_off = [&](const HaloWalk& t, int r) -> long long {
@@ -276,7 +281,10 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       for (int i = 0; i < CH; ++i) {
         const int item = i * 32 + lane, r = item / CH, c = item % CH;
         const long long off = pixel_off(t, r);
-        if (off >= 0) ptx::cp_async16(slot(r, c), res + off + c * 8);
+        if (off >= 0) {
+          if (p.l2_hints) ptx::cp_async16_hint(slot(r, c), res + off + c * 8, pol_in);
+          else ptx::cp_async16(slot(r, c), res + off + c * 8);
+        }
       }
       ptx::cp_async_commit();
     };
@@ -313,7 +321,10 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       for (int i = 0; i < CH; ++i) {
         const int item = i * 32 + lane, r = item / CH, c = item % CH;
         const long long off = pixel_off(cur, r);
-        if (off >= 0) *reinterpret_cast<uint4*>(out + off + c * 8) = ptx::ld_shared_v4(slot(r, c));
+        if (off >= 0) {
+          if (p.l2_hints) ptx::st_global_v4_hint(out + off + c * 8, ptx::ld_shared_v4(slot(r, c)), pol_out);
+          else *reinterpret_cast<uint4*>(out + off + c * 8) = ptx::ld_shared_v4(slot(r, c));
+        }
       }
       __syncwarp();
       prefetch_residual(w);
@@ -431,6 +442,7 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
   p.bias = (const float*)op.in[2];
   p.res = op.in[3];
   p.out = op.out[0];
+  { const char* e = getenv("CAPF_L2_HINTS"); p.l2_hints = (e && e[0] == '0') ? 0 : 1; }
   p.trace = (long long*)op.in[4];     // debug only (NULL in every program the host layer builds)
   s->grid = p.num_bands < g_num_sms ? p.num_bands : g_num_sms;
   s->dtype_in = op.dtype_in;
