@@ -25,6 +25,10 @@ int launch_levels_to_joint(const capf_op& op, cudaStream_t st);
 int launch_crop_normalize(const capf_op& op, cudaStream_t st);
 int launch_cast(const capf_op& op, cudaStream_t st);
 
+// tensor-pipe HRNet stem conv1 (capf_stem.cu): fp32 NHWC image -> 64 channels, 3x3 / stride 2
+int stem_tc_supported(const capf_op& op);
+int launch_stem_tc(const capf_op& op, cudaStream_t st);
+
 // tcgen05 path (capf_tc.cu): per-op prepared state lives in the plan
 struct TcConvState;                                   // tensor maps + launch geometry
 int tc_conv_supported(const capf_op& op);             // 1 if the tcgen05 kernel handles this op

@@ -309,6 +309,7 @@ int launch_conv_simt(const capf_op& op, cudaStream_t st) {
   p.K = p.KH * p.KW * p.Cin;
   if (!op.in[0] || !op.in[1] || !op.out[0]) return set_error(CAPF_ERR_ARG, "conv2d: null pointer");
   int di = op.dtype_in, dd = op.dtype_out;
+  if (stem_tc_supported(op)) return launch_stem_tc(op, st);   // tensor-pipe stem (capf_stem.cu); env CAPF_STEM_TC=0 -> below
   if (is_stem(p, op)) return launch_stem(p, op, st);
   if (di == CAPF_F32 && dd == CAPF_F32) return conv_dispatch<float, float, float>(p, op, st);
   if (di == CAPF_F32 && dd == CAPF_F16) return conv_dispatch<float, float, __half>(p, op, st);

@@ -12,6 +12,7 @@
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator,
 // warps 4..11 = epilogue (tcgen05.ld -> bias/GELU/residual/ReLU -> global).  Two TMEM accumulator stages let the
 // epilogue of tile i overlap the MMAs of tile i+1; a ring of smem stages decouples TMA from the tensor pipe.
+#include <cstdlib>
 #include <new>
 
 #include "capf_tc.cuh"
@@ -24,11 +25,21 @@ namespace capf {
 constexpr int TC_THREADS = 384;          // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_HEADER_BYTES = 1024;       // barriers + TMEM base pointer
-constexpr int TC_A_STAGE_BYTES = 128 * 128; // 128 rows x 64 elements x 2 B
+constexpr int TC_A_SUB_BYTES = 128 * 128;   // one 128-row sub-tile of a stage: 128 rows x 64 elements x 2 B
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_STG_BYTES = 32 * 128;      // epilogue staging tile of one warp: 32 rows x 128 bytes
 
 struct TcP {
   int mode;                 // 0 = rows ([M][K] matrix), 1 = conv (NHWC, 4-D boxes)
   int M;                    // rows mode: valid rows
+  int msub;                 // 128-row sub-tiles per tile (1 | 2): both share every B stage, one accumulator each
+  int a_stage_bytes;        // msub * TC_A_SUB_BYTES (B follows A inside a stage)
+  int a_sub_bytes;          // offset of sub-tile 1 inside one A chunk = 128 * kb * 2
+  int nacc;                 // TMEM accumulator stages (2, or 1 when 2 * msub * BN > 512 columns)
+  int epi;                  // 0: direct per-row epilogue, 1: staged (coalesced) epilogue
+  int stg_bufs;             // staging buffers per epilogue warp (2 with a residual, else 1)
+  uint32_t stg_off;         // staging region offset from the first pipeline stage
+  uint32_t bias_off;        // per-warp bias slices (8 x 256 floats), offset from the first pipeline stage
   int Cout, BN, n_tiles_n;
   int num_chunks;           // K chunks = taps * (Cin / kb)
   int kb;                   // elements per chunk: 16 | 32 | 64  (32 | 64 | 128-byte swizzled rows)
@@ -44,11 +55,13 @@ struct TcP {
   int tx_bytes_per_chunk;   // bytes the two TMA boxes of one chunk deliver
   uint32_t idesc;           // tcgen05 instruction descriptor (kind::f16, fp32 accumulate, M=128, N=BN)
   uint32_t desc_hi;         // high word of the smem matrix descriptors (SBO, version, swizzle mode)
-  int tmem_cols;            // allocated TMEM columns (power of two >= 2*BN)
+  int tmem_cols;            // allocated TMEM columns (power of two >= nacc * msub * BN)
+  int acc_stride;           // TMEM columns per accumulator stage = msub * BN
   int act;
   const float* bias;
   const void* res;
   void* out;
+  long long* trace;         // optional (debug, op.in[4]): clock64 timeline of CTA 0, see tools/gemm_trace.py
 };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t hi) { return tc_make_desc(smem_addr, 1u, hi); }
@@ -85,7 +98,8 @@ __device__ __forceinline__ void tile_range(const TcP& p, int& t0, int& t1) {
 // =======================================================================================================
 // the kernel
 // =======================================================================================================
-template <typename TO>
+// MODE: bit 0 = residual add, bit 1 = GELU (compile-time epilogue variants)
+template <typename TO, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -100,6 +114,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[0] = clock64();
+    p.trace[1] = (long long)gt;
+  }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapA);
@@ -124,13 +145,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1;
+  const uint32_t acc_stride = (uint32_t)p.acc_stride;
   // PDL: this one-wave persistent grid is fully resident -> let the successor be scheduled as SMs drain; nothing
   // produced by the predecessor (activations, residual) has been touched before this point.
+  if (tr && threadIdx.x == 0) p.trace[2] = clock64();
   pdl_trigger();
   pdl_wait();
+  if (tr && threadIdx.x == 0) p.trace[3] = clock64();
   int t0, t1;
   tile_range(p, t0, t1);
+  const int tile_rows = 128 * p.msub;
 
   if (warp == 0) {
     // ===================================== TMA producer (one elected thread) ================
@@ -139,7 +163,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       TileWalk w;
       w.init(p, t0);
       for (int tile = t0; tile < t1; ++tile, w.next(p)) {
-        const int m0 = (w.tx + p.tiles_x * (w.ty + p.tiles_y * w.tn)) * 128;            // rows mode (tiles_y == 1)
+        const int m0 = (w.tx + p.tiles_x * (w.ty + p.tiles_y * w.tn)) * tile_rows;      // rows mode (tiles_y == 1)
         const int ix_base = w.tx * p.bw * p.stride - p.pad, iy_base = w.ty * p.bh * p.stride - p.pad, n0 = w.tn * p.bn;
         const int nb0 = w.n_tile * p.BN;
         int r = 0, sx = 0, cc = 0, kcol = 0;       // filter tap (r, sx), channel chunk inside the tap, B column
@@ -149,7 +173,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t full = bar_full + 8 * stage;
           ptx::mbar_arrive_expect_tx(full, (uint32_t)(nc * p.tx_bytes_per_chunk));
           uint32_t a_dst = stage0 + stage * p.stage_bytes;
-          uint32_t b_dst = a_dst + TC_A_STAGE_BYTES;
+          uint32_t b_dst = a_dst + p.a_stage_bytes;
           for (int j = 0; j < nc; ++j) {
             if (p.mode == 1) ptx::tma_load_4d(&mapA, full, a_dst, cc * p.kb, ix_base + sx, iy_base + r, n0);
             else ptx::tma_load_2d(&mapA, full, a_dst, kcol, m0);
@@ -162,6 +186,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               if (++sx == p.KW) { sx = 0; ++r; }
             }
           }
+          if (tr) { const int n = (tile - t0) * ((p.num_chunks + p.cps - 1) / p.cps) + c0 / p.cps; if (n < 64) p.trace[64 + n] = clock64(); }
           if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -169,7 +194,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
     // The whole warp walks the pipeline (uniform control flow); one elected lane issues the tcgen05 ops.
-    // A full stage is always 4 MMAs of K = 16: (64 / kb) chunks x (kb / 16) steps.
+    // A full stage is always 4 MMAs of K = 16 per 128-row sub-tile: (64 / kb) chunks x (kb / 16) steps; the msub
+    // sub-tiles of a tile read the same B stage and accumulate into neighbouring TMEM column ranges.
     uint32_t a_off[4], b_off[4];
     {
       const int ksteps = p.kb >> 4;
@@ -181,9 +207,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
     const int mma_per_chunk = p.kb >> 4;
-    uint32_t stage = 0, phase = 0, it = 0;
-    for (int tile = t0; tile < t1; ++tile, ++it) {
-      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+    const uint32_t a_sub16 = (uint32_t)p.a_sub_bytes >> 4;
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = t0; tile < t1; ++tile) {
       ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * acc_stride;
@@ -195,97 +221,194 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const bool last = c0 + p.cps >= p.num_chunks;
         if (ptx::elect_one()) {
           const uint32_t a_src = stage0 + stage * p.stage_bytes;
-          const uint64_t a_desc = make_desc(a_src, p.desc_hi), b_desc = make_desc(a_src + TC_A_STAGE_BYTES, p.desc_hi);
+          const uint64_t a_desc = make_desc(a_src, p.desc_hi), b_desc = make_desc(a_src + p.a_stage_bytes, p.desc_hi);
+          for (int sub = 0; sub < p.msub; ++sub) {
+            const uint64_t a_sub = a_desc + (uint64_t)(sub * a_sub16);
+            const uint32_t d_sub = d_tmem + (uint32_t)(sub * p.BN);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < nmma) {
-              ptx::umma_f16(d_tmem, a_desc + a_off[i], b_desc + b_off[i], p.idesc, accumulate);
-              accumulate = 1;
+            for (int i = 0; i < 4; ++i) {
+              if (i < nmma) ptx::umma_f16(d_sub, a_sub + a_off[i], b_desc + b_off[i], p.idesc, (accumulate | (uint32_t)i) ? 1u : 0u);
             }
           }
           ptx::umma_commit(bar_empty + 8 * stage);      // smem slot reusable once these MMAs have read it
           if (last) ptx::umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+          if (tr) { const int n = (tile - t0) * ((p.num_chunks + p.cps - 1) / p.cps) + c0 / p.cps; if (n < 64) p.trace[128 + n] = clock64(); }
         }
         __syncwarp();
         accumulate = 1;
         if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1u; }
       }
+      if (++acc == (uint32_t)p.nacc) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =========================================
-    // 8 warps: quadrant q = warp & 3 owns TMEM lanes [32q, 32q+32) (= tile rows); the two warps of a quadrant split
-    // the BN accumulator columns.  Per group of 32 columns: two tcgen05.ld in flight, the residual of the NEXT group
-    // already requested, one wait, then bias/GELU/residual/ReLU and 16-byte stores.
+    // 8 warps: quadrant q = warp & 3 owns TMEM lanes [32q, 32q+32) (= rows of a 128-row sub-tile).  With one sub-tile
+    // per tile the two warps of a quadrant split the BN accumulator columns; with two sub-tiles each takes one.
+    //
+    // All global traffic is coalesced through a warp-private, XOR-swizzled staging tile of 32 rows x 128 bytes (one
+    // "slab" = 64 16-bit / 32 fp32 columns): the residual slab is requested with cp.async one slab ahead (and pulled
+    // into L2 a whole tile ahead), every thread adds its own row in place, and the finished slab leaves with 16 bytes
+    // per lane, consecutive lanes -> consecutive addresses.  The epilogue is a single warp's dependent instruction
+    // stream per 32 rows, so its instruction count is what bounds short GEMMs: activation / residual are compile-time
+    // variants (MODE), the bias slice of the column tile sits in shared memory before the accumulator is waited for,
+    // and the rows-mode store addresses are affine (no shuffles, no 64-bit multiplies in the loop).
+    constexpr bool HAS_RES = (MODE & 1) != 0;
+    constexpr int SW = 128 / (int)sizeof(TO);          // columns per slab
+    constexpr int CPG = 16 * (int)sizeof(TO) / 16;     // 16-byte chunks per 16 columns
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    const int row = q * 32 + lane;
+    const int sub = p.msub == 2 ? half : 0;
+    const int row = sub * 128 + q * 32 + lane;
     const int split = ((p.BN / 16 + 1) / 2) * 16;
-    const int cbeg = half ? split : 0, cend = half ? p.BN : split;
-    const int ngroups = (cend - cbeg + 31) / 32;
+    const int cbeg = (p.msub == 1 && half) ? split : 0, cend = (p.msub == 1 && !half) ? split : p.BN;
+    const int nslabs = (cend - cbeg + SW - 1) / SW;
     const TO* res = reinterpret_cast<const TO*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
     // tile-invariant position of this thread's row inside the output-pixel box
     const int bx = row % p.bw;
     const int by = (row / p.bw) % p.bh, bi = row / (p.bw * p.bh);
-    uint32_t it = 0;
+    const uint32_t tcol0 = (uint32_t)(sub * p.BN) + ((uint32_t)(q * 32) << 16);
+    const float floor_v = p.act == CAPF_ACT_RELU ? 0.f : -__int_as_float(0x7f800000);
+    uint8_t* const stg_ptr = smem_raw + (stage0 - raw) + p.stg_off + (uint32_t)(warp - 4) * (uint32_t)(p.stg_bufs * TC_STG_BYTES);
+    const uint32_t stg = stage0 + p.stg_off + (uint32_t)(warp - 4) * (uint32_t)(p.stg_bufs * TC_STG_BYTES);
+    float* const sbias = reinterpret_cast<float*>(smem_raw + (stage0 - raw) + p.bias_off) + (warp - 4) * 256;
+    auto slot_off = [&](uint32_t buf, int r, int c) { return buf * TC_STG_BYTES + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); };
+    const uint64_t pol_out = ptx::policy_evict_last();
+    const uint32_t row_bytes = (uint32_t)p.Cout * (uint32_t)sizeof(TO);
+    // output row (pixel) index of accumulator row `row` of the tile the walker points at, -1 when it is padding
+    auto row_index = [&](const TileWalk& t) -> int {
+      if (p.mode == 1) {
+        const int ox = t.tx * p.bw + bx, oy = t.ty * p.bh + by, n = t.tn * p.bn + bi;
+        const bool ok = bi < p.bn && ox < p.Wo && oy < p.Ho && n < p.Nimg;
+        return ok ? (n * p.Ho + oy) * p.Wo + ox : -1;
+      }
+      const int m = t.tx * tile_rows + row;
+      return m < p.M ? m : -1;
+    };
+    uint32_t acc = 0, acc_phase = 0;
     TileWalk w;
     w.init(p, t0);
-    for (int tile = t0; tile < t1; ++tile, ++it, w.next(p)) {
-      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-      long long orow;  // output row (pixel) index, -1 when this tile row is padding
-      if (p.mode == 1) {
-        const int ox = w.tx * p.bw + bx, oy = w.ty * p.bh + by, n = w.tn * p.bn + bi;
-        const bool ok = bi < p.bn && ox < p.Wo && oy < p.Ho && n < p.Nimg;
-        orow = ok ? ((long long)n * p.Ho + oy) * p.Wo + ox : -1;
-      } else {
-        const int m = w.tx * 128 + row;
-        orow = m < p.M ? (long long)m : -1;
-      }
-      const bool live = orow >= 0;
-      const bool has_res = live && res != nullptr;
+    for (int tile = t0; tile < t1; ++tile) {
+      const int myrow = row_index(w);
       const int ncol0 = w.n_tile * p.BN;
-      const size_t off0 = (size_t)(live ? orow : 0) * p.Cout + ncol0;
-      const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
-
-      Vec16<TO> r0[2], r1[2];
-      auto fetch = [&](int g, Vec16<TO> (&r)[2]) {
-        if (has_res) {
-          const int c = cbeg + 32 * g;
-          r[0].load(res + off0 + c);
-          if (c + 16 < cend) r[1].load(res + off0 + c + 16);
+      const uint32_t taddr = tmem_base + acc * acc_stride + tcol0;
+      // bias slice of this warp's columns -> shared memory (zeros without a bias)
+      for (int c = 4 * lane; c < cend - cbeg; c += 128)
+        *reinterpret_cast<float4*>(sbias + c) = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + cbeg + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // item = i * 32 + lane -> (row r = item / chs, chunk c = item % chs) of a slab with chs 16-byte chunks per row
+      auto prefetch_res = [&](int s, uint32_t buf) {
+        const int c0 = cbeg + s * SW;
+        const int chs = (min(SW, cend - c0) * (int)sizeof(TO)) >> 4;
+        const uint32_t magic = (65536u + (uint32_t)chs - 1u) / (uint32_t)chs;
+        for (int i = 0; i < chs; ++i) {
+          const int item = i * 32 + lane, r = (int)(((uint32_t)item * magic) >> 16), c = item - r * chs;
+          const int grow = __shfl_sync(0xffffffffu, myrow, r);
+          if (grow >= 0) ptx::cp_async16(stg + slot_off(buf, r, c), reinterpret_cast<const uint8_t*>(res + (size_t)grow * p.Cout + ncol0 + c0) + 16 * c);
         }
+        ptx::cp_async_commit();
       };
-      auto group = [&](int g, const Vec16<TO> (&r)[2], Vec16<TO> (&rnext)[2]) {
-        const int c = cbeg + 32 * g;
-        const bool two = c + 16 < cend;
-        uint32_t a0[16], a1[16];
-        ptx::tmem_ld16(taddr + (uint32_t)c, a0);
-        if (two) ptx::tmem_ld16(taddr + (uint32_t)(c + 16), a1);
-        if (g + 1 < ngroups) fetch(g + 1, rnext);
-        Bias16 b0, b1;
-        b0.load(p.bias, ncol0 + c);
-        b1.load(p.bias, ncol0 + (two ? c + 16 : c));
-        ptx::tmem_ld_wait();
-        if (live) {
-          finish16<TO>(b0, p.act, a0, r[0], has_res, out + off0 + c);
-          if (two) finish16<TO>(b1, p.act, a1, r[1], has_res, out + off0 + c + 16);
+      TileWalk wn = w;
+      wn.next(p);
+      if (HAS_RES) {
+        prefetch_res(0, 0);                          // independent of the MMAs: issue before waiting for them
+        if (tile + 1 < t1) {                         // next tile's residual rows: HBM -> L2 while this tile is processed
+          const int nrow = row_index(wn);
+          if (nrow >= 0) {
+            const uint8_t* a = reinterpret_cast<const uint8_t*>(res + (size_t)nrow * p.Cout + wn.n_tile * p.BN + cbeg);
+            for (int b = 0; b < (cend - cbeg) * (int)sizeof(TO); b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + b));
+          }
         }
-      };
-      fetch(0, r0);                                  // independent of the MMAs: issue before waiting for them
+      }
+      __syncwarp();
       ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
       ptx::tc_fence_after();
-      for (int g = 0; g < ngroups; g += 2) {
-        group(g, r0, r1);
-        if (g + 1 < ngroups) group(g + 1, r1, r0);
+      if (tr && warp == 4 && lane == 0 && tile - t0 < 16) p.trace[192 + 2 * (tile - t0)] = clock64();
+      int fine = 224;
+#define CAPF_STAMP() do { if (tr && warp == 4 && lane == 0 && tile == t0 && fine < 256) p.trace[fine++] = clock64(); } while (0)
+      uint32_t buf = 0;
+      for (int s = 0; s < nslabs; ++s) {
+        const int c0 = cbeg + s * SW;
+        const int ncol = min(SW, cend - c0);
+        if (HAS_RES && s + 1 < nslabs) prefetch_res(s + 1, buf ^ 1u);
+#pragma unroll
+        for (int g = 0; g < SW; g += 32) {
+          if (g < ncol) {
+            const bool two = g + 16 < ncol;
+            uint32_t a0[16], a1[16];
+            ptx::tmem_ld16(taddr + (uint32_t)(c0 + g), a0);
+            if (two) ptx::tmem_ld16(taddr + (uint32_t)(c0 + g + 16), a1);
+            CAPF_STAMP();
+            ptx::tmem_ld_wait();
+            CAPF_STAMP();
+            if (HAS_RES && g == 0) {                   // this slab's residual has landed (the next one may be in flight)
+              if (s + 1 < nslabs) ptx::cp_async_wait_group1(); else ptx::cp_async_wait_all();
+              __syncwarp();
+            }
+            CAPF_STAMP();
+            epi16<TO, MODE>(a0, sbias + (c0 - cbeg) + g, floor_v, stg_ptr + buf * TC_STG_BYTES + lane * 128, (uint32_t)((g / 16) * CPG), (uint32_t)lane & 7u);
+            if (two) epi16<TO, MODE>(a1, sbias + (c0 - cbeg) + g + 16, floor_v, stg_ptr + buf * TC_STG_BYTES + lane * 128, (uint32_t)((g / 16 + 1) * CPG), (uint32_t)lane & 7u);
+            CAPF_STAMP();
+          }
+        }
+        if (s + 1 == nslabs) {                        // the accumulator has been read completely
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(bar_tempty + 8 * acc);     // 256 arrivals free this accumulator stage
+        }
+        __syncwarp();
+        const int chs = (ncol * (int)sizeof(TO)) >> 4;
+        if (p.mode == 0) {
+          // rows mode: the warp's 32 rows are consecutive matrix rows -> affine addresses
+          const int m_w0 = w.tx * tile_rows + sub * 128 + q * 32;
+          const int rows_live = p.M - m_w0;
+          uint8_t* gbase = reinterpret_cast<uint8_t*>(out + (size_t)m_w0 * p.Cout + ncol0 + c0);
+          if (chs == 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3), c = lane & 7;
+              if (r < rows_live) st16_hint(gbase + (uint32_t)r * row_bytes + 16 * c, *reinterpret_cast<const uint4*>(stg_ptr + slot_off(buf, r, c)), pol_out);
+            }
+          } else {
+            const uint32_t magic = (65536u + (uint32_t)chs - 1u) / (uint32_t)chs;
+            for (int i = 0; i < chs; ++i) {
+              const int item = i * 32 + lane, r = (int)(((uint32_t)item * magic) >> 16), c = item - r * chs;
+              if (r < rows_live) st16_hint(gbase + (uint32_t)r * row_bytes + 16 * c, *reinterpret_cast<const uint4*>(stg_ptr + slot_off(buf, r, c)), pol_out);
+            }
+          }
+        } else {
+          const uint32_t magic = (65536u + (uint32_t)chs - 1u) / (uint32_t)chs;
+          for (int i = 0; i < chs; ++i) {
+            const int item = i * 32 + lane, r = (int)(((uint32_t)item * magic) >> 16), c = item - r * chs;
+            const int grow = __shfl_sync(0xffffffffu, myrow, r);
+            if (grow >= 0)
+              st16_hint(reinterpret_cast<uint8_t*>(out + (size_t)grow * p.Cout + ncol0 + c0) + 16 * c, *reinterpret_cast<const uint4*>(stg_ptr + slot_off(buf, r, c)),
+                        pol_out);
+          }
+        }
+        __syncwarp();
+        CAPF_STAMP();
+        if (HAS_RES) buf ^= 1u;
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(bar_tempty + 8 * acc);   // 256 arrivals free this accumulator stage
+#undef CAPF_STAMP
+      if (nslabs == 0) {                              // BN = 16: the second warp of the quadrant has no columns
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar_tempty + 8 * acc);
+      }
+      if (tr && warp == 4 && lane == 0 && tile - t0 < 16) p.trace[193 + 2 * (tile - t0)] = clock64();
+      if (++acc == (uint32_t)p.nacc) { acc = 0; acc_phase ^= 1u; }
+      w = wn;
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (tr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[4] = clock64();
+    p.trace[5] = (long long)gt;
+    p.trace[6] = p.msub; p.trace[7] = p.BN; p.trace[8] = p.num_stages; p.trace[9] = p.num_tiles; p.trace[10] = gridDim.x; p.trace[11] = p.nacc;
+  }
 }
 
 // =======================================================================================================
@@ -344,17 +467,18 @@ int tc_conv_supported(const capf_op& op) {
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// Output-pixel box (bw x bh x bn <= 128 rows) that wastes the fewest accumulator rows.
-static void choose_box(const ConvGeo& g, int max_w, int& bw, int& bh, int& bn) {
+// Output-pixel box (bw x bh x bn <= max_rows accumulator rows) that wastes the fewest of them.
+static void choose_box(const ConvGeo& g, int max_w, int max_rows, int& bw, int& bh, int& bn) {
   double best = -1.0;
   bw = bh = bn = 1;
-  for (int w = 1; w <= g.Wo && w <= 128 && w <= max_w; ++w) {
-    for (int h = 1; h <= g.Ho && w * h <= 128; ++h) {
-      int n = 128 / (w * h);
+  for (int w = 1; w <= g.Wo && w <= max_rows && w <= max_w; ++w) {
+    for (int h = 1; h <= g.Ho && w * h <= max_rows && h * g.stride <= 256; ++h) {
+      int n = max_rows / (w * h);
       if (n > g.N) n = g.N;
+      if (n > 256) n = 256;
       if (n < 1) continue;
       double tiles = (double)ceil_div(g.Wo, w) * ceil_div(g.Ho, h) * ceil_div(g.N, n);
-      double util = ((double)g.Wo * g.Ho * g.N) / (tiles * 128.0);
+      double util = ((double)g.Wo * g.Ho * g.N) / (tiles * (double)max_rows);
       // prefer wide boxes (longer contiguous runs for TMA and for the epilogue stores) on ties
       double score = util + 1e-6 * w + 1e-9 * h;
       if (score > best) { best = score; bw = w; bh = h; bn = n; }
@@ -401,54 +525,104 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   p.bias = (const float*)op.in[2];
   p.res = op.in[3];
   p.out = op.out[0];
+  p.trace = (long long*)op.in[4];     // debug only (NULL in every program the host layer builds)
+  p.M = g.N * g.Ho * g.Wo;
   const int swz = p.kb * 2;
+  const int K = g.KH * g.KW * g.Cin;
+  const int osz = op.dtype_out == CAPF_F32 ? 4 : 2;
 
-  // ---- M tiling ----------------------------------------------------------------------------------------
+  // ---- epilogue staging: two tiles per warp with a residual (one being filled by cp.async), else one ------------
+  p.epi = 1;
+  p.stg_bufs = p.res ? 2 : 1;
+  const int stg_bytes = TC_EPI_WARPS * p.stg_bufs * TC_STG_BYTES + TC_EPI_WARPS * 256 * 4;   // staging tiles + bias slices
+
+  // ---- tile shape: (msub x 128 rows) x BN columns ------------------------------------------------------------
+  // Cycle model per tile (SM clocks): the tensor pipe (N / 2 cycles per 128 x N x 16 MMA, or the shared-memory operand
+  // read of (128 + N) * 32 B at 128 B/clk when that is slower), the L2 -> SM operand feed (the chip-wide L2 cap is
+  // ~6300 B/clk = 42 B/clk/SM: every stage moves (rows + BN) * 128 B), and the epilogue's global traffic.  Two
+  // sub-tiles share every B stage, which is what makes the wide transformer GEMMs (QKV: 256 x 240 tiles, one per SM)
+  // feed less per FLOP.  i[15] forces msub, i[16] forces BN (tests / experiments).
+  int msub_lo = 1, msub_hi = 2;
+  { const char* ev = getenv("CAPF_TC_MSUB"); if (ev && (ev[0] == '1' || ev[0] == '2')) msub_lo = msub_hi = ev[0] - '0'; }
+  if (op.i[15] == 1 || op.i[15] == 2) msub_lo = msub_hi = op.i[15];
+  double best_cost = 1e300;
+  int best_msub = 0, best_bn = 0, best_bw = 0, best_bh = 0, best_bnn = 0;
+  for (int msub = msub_lo; msub <= msub_hi; ++msub) {
+    int bw = 128 * msub, bh = 1, bnn = 1, box_rows = 128 * msub;
+    long long m_tiles;
+    if (rows) {
+      m_tiles = ceil_div(p.M, 128 * msub);
+    } else {
+      choose_box(g, 256 / g.stride, 128 * msub, bw, bh, bnn);
+      box_rows = bw * bh * bnn;
+      if (msub == 2 && box_rows <= 128 && msub_lo != 2) continue;
+      m_tiles = (long long)ceil_div(g.Wo, bw) * ceil_div(g.Ho, bh) * ceil_div(g.N, bnn);
+    }
+    for (int bn = 16; bn <= 256 && bn <= g.Cout; bn += 16) {
+      if (g.Cout % bn) continue;
+      if (op.i[16] > 0 && bn != op.i[16]) continue;
+      if (msub * bn > 512) continue;
+      const int stage_bytes = msub * TC_A_SUB_BYTES + bn * 128;
+      int stages = (TC_SMEM_LIMIT - TC_HEADER_BYTES - 1024 - stg_bytes) / stage_bytes;
+      if (stages < 2) continue;
+      const int nacc = 2 * msub * bn <= 512 ? 2 : 1;
+      const long long tiles = m_tiles * (g.Cout / bn);
+      const long long grid = tiles < g_num_sms ? tiles : g_num_sms;
+      const double per_cta = (double)((tiles + grid - 1) / grid);
+      const double k16 = K / 16.0;
+      const double t_mma = msub * k16 * ((bn / 2.0) > ((128 + bn) / 4.0) ? (bn / 2.0) : ((128 + bn) / 4.0));
+      const double t_feed = (double)(box_rows + bn) * K * 2.0 / 42.0;
+      const double t_epi = (double)msub * 128.0 * bn * osz * (p.res ? 2.0 : 1.0) / 24.0 + 300.0;
+      double t_main = t_mma > t_feed ? t_mma : t_feed;
+      double cost;
+      if (nacc == 2) cost = per_cta * (t_main > t_epi ? t_main : t_epi) + (t_main < t_epi ? t_main : t_epi);
+      else cost = per_cta * (t_main + t_epi);
+      if (stages < 3) cost *= 1.15;
+      cost += 600.0 * per_cta;    // per-tile pipeline bubbles (barrier round trips, accumulator hand-over)
+      if (cost < best_cost * (1.0 - 1e-9)) {
+        best_cost = cost; best_msub = msub; best_bn = bn; best_bw = bw; best_bh = bh; best_bnn = bnn;
+      }
+    }
+  }
+  if (!best_bn) { delete s; return set_error(CAPF_ERR_UNSUPPORTED, "tc conv: no tile shape fits"); }
+  p.msub = best_msub;
+  p.BN = best_bn;
   long long m_tiles;
   if (rows) {
-    p.M = g.N * g.Ho * g.Wo;
-    p.bw = 128; p.bh = 1; p.bn = 1; p.tiles_x = ceil_div(p.M, 128); p.tiles_y = 1;
+    p.bw = 128 * p.msub; p.bh = 1; p.bn = 1; p.tiles_x = ceil_div(p.M, 128 * p.msub); p.tiles_y = 1;
     m_tiles = p.tiles_x;
   } else {
-    choose_box(g, 256 / g.stride, p.bw, p.bh, p.bn);
+    p.bw = best_bw; p.bh = best_bh; p.bn = best_bnn;
     p.tiles_x = ceil_div(g.Wo, p.bw);
     p.tiles_y = ceil_div(g.Ho, p.bh);
     m_tiles = (long long)p.tiles_x * p.tiles_y * ceil_div(g.N, p.bn);
-    p.M = g.N * g.Ho * g.Wo;
   }
-
-  // ---- N tiling: BN | Cout, multiple of 16, <= 256; fewest (waves x per-tile cost) ------------------------
-  int best_bn = 0;
-  double best_cost = 1e300;
-  for (int bn = 16; bn <= 256 && bn <= g.Cout; bn += 16) {
-    if (g.Cout % bn) continue;
-    long long tiles = m_tiles * (g.Cout / bn);
-    long long waves = (tiles + g_num_sms - 1) / g_num_sms;
-    double cost = (double)waves * (bn + 24.0);
-    if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best_bn)) { best_cost = cost; best_bn = bn; }
-  }
-  if (!best_bn) { delete s; return set_error(CAPF_ERR_UNSUPPORTED, "tc conv: no column tile"); }
-  p.BN = best_bn;
   p.n_tiles_n = g.Cout / p.BN;
   long long nt = m_tiles * p.n_tiles_n;
   if (nt >= (1ll << 31)) { delete s; return set_error(CAPF_ERR_UNSUPPORTED, "tc conv: too many tiles"); }
   p.num_tiles = (int)nt;
 
-  p.a_chunk_bytes = 128 * p.kb * 2;
+  p.a_sub_bytes = 128 * p.kb * 2;
+  p.a_chunk_bytes = p.msub * p.a_sub_bytes;
+  p.a_stage_bytes = p.msub * TC_A_SUB_BYTES;
   p.b_chunk_bytes = p.BN * p.kb * 2;
-  p.stage_bytes = TC_A_STAGE_BYTES + p.BN * 128;
-  const int box_rows = rows ? 128 : p.bw * p.bh * p.bn;
+  p.stage_bytes = p.a_stage_bytes + p.BN * 128;
+  const int box_rows = rows ? 128 * p.msub : p.bw * p.bh * p.bn;
   p.tx_bytes_per_chunk = (box_rows + p.BN) * p.kb * 2;
-  int stages = (TC_SMEM_LIMIT - TC_HEADER_BYTES - 1024) / p.stage_bytes;
+  int stages = (TC_SMEM_LIMIT - TC_HEADER_BYTES - 1024 - stg_bytes) / p.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   const int k_stages = ceil_div(p.num_chunks, p.cps);
   if (stages > 2 * k_stages && 2 * k_stages >= 2) stages = 2 * k_stages;   // no point in a ring deeper than two tiles
   if (stages < 2) { delete s; return set_error(CAPF_ERR_UNSUPPORTED, "tc conv: tile does not fit shared memory"); }
   p.num_stages = stages;
-  s->smem_bytes = TC_HEADER_BYTES + 1024 + stages * p.stage_bytes;
+  p.stg_off = (uint32_t)(stages * p.stage_bytes);
+  p.bias_off = p.stg_off + (uint32_t)(TC_EPI_WARPS * p.stg_bufs * TC_STG_BYTES);
+  s->smem_bytes = TC_HEADER_BYTES + 1024 + stages * p.stage_bytes + stg_bytes;
   if (s->smem_bytes < 120 * 1024) s->smem_bytes = 120 * 1024;   // one CTA per SM: the CTA owns the SM's TMEM columns
+  p.nacc = 2 * p.msub * p.BN <= 512 ? 2 : 1;
+  p.acc_stride = p.msub * p.BN;
   int cols = 32;
-  while (cols < 2 * p.BN) cols <<= 1;
+  while (cols < p.nacc * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
   p.idesc = tc_idesc(op.dtype_in == CAPF_BF16, p.BN);
   p.desc_hi = tc_desc_hi(swz, 8 * swz);
@@ -457,11 +631,10 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
 
   // ---- tensor maps -------------------------------------------------------------------------------------
   const CUtensorMapDataType dt = op.dtype_in == CAPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  const int K = g.KH * g.KW * g.Cin;
   if (rows) {
     cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)p.M};
     cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)p.kb, 128};
+    cuuint32_t box[2] = {(cuuint32_t)p.kb, (cuuint32_t)(128 * p.msub)};
     cuuint32_t es[2] = {1, 1};
     e = tc_encode_map(&s->mapA, dt, 2, op.in[0], dims, strides, box, es, swz, "A rows");
   } else {
@@ -483,16 +656,27 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   return CAPF_OK;
 }
 
-template <typename TO>
-static int tc_launch_typed(const TcConvState* s, cudaStream_t st) {
+template <typename TO, int MODE>
+static int tc_launch_mode(const TcConvState* s, cudaStream_t st) {
   static int max_smem = 0;   // opt-in once per instantiation (outside graph capture: Plan.capture warms up first)
   if (s->smem_bytes > max_smem) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<TO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_gemm_kernel smem opt-in: %s", cudaGetErrorString(e));
     max_smem = TC_SMEM_LIMIT;
   }
-  launch_k(tc_gemm_kernel<TO>, dim3(s->grid), dim3(TC_THREADS), s->smem_bytes, st, s->mapA, s->mapB, s->p);
+  launch_k(tc_gemm_kernel<TO, MODE>, dim3(s->grid), dim3(TC_THREADS), s->smem_bytes, st, s->mapA, s->mapB, s->p);
   return check_launch("tc_gemm_kernel");
+}
+
+template <typename TO>
+static int tc_launch_typed(const TcConvState* s, cudaStream_t st) {
+  const int mode = (s->p.res ? 1 : 0) | (s->p.act == CAPF_ACT_GELU ? 2 : 0);
+  switch (mode) {
+    case 0: return tc_launch_mode<TO, 0>(s, st);
+    case 1: return tc_launch_mode<TO, 1>(s, st);
+    case 2: return tc_launch_mode<TO, 2>(s, st);
+    default: return tc_launch_mode<TO, 3>(s, st);
+  }
 }
 
 int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {

@@ -401,6 +401,73 @@ __device__ __forceinline__ void finish16_stage(const Bias16& bs, int act, const 
   }
 }
 
+// Epilogue of 16 accumulator columns of one output row, staged in shared memory: y = max(floor, gelu?(acc + bias) +
+// residual?) -> TO, written to (and, with a residual, first read from) the CPG consecutive 16-byte chunks of the row's
+// slot in the XOR-swizzled staging tile (chunk k of row r lives at chunk position (c0 + k) ^ (r & 7)).  Compile-time
+// MODE (bit 0 residual, bit 1 GELU) and plain shared-memory pointers keep the instruction stream short and let the
+// compiler schedule it; `floor` is 0 for ReLU and -inf otherwise.
+template <typename TO, int MODE>
+__device__ __forceinline__ void epi16(const uint32_t (&raw)[16], const float* __restrict__ sbias, float floor, uint8_t* row_ptr, uint32_t chunk0,
+                                      uint32_t rx) {
+  constexpr int CPG = (int)sizeof(TO);           // 16-byte chunks per 16 columns
+  float v[16];
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * q4);
+    v[4 * q4] = __uint_as_float(raw[4 * q4]) + b.x;
+    v[4 * q4 + 1] = __uint_as_float(raw[4 * q4 + 1]) + b.y;
+    v[4 * q4 + 2] = __uint_as_float(raw[4 * q4 + 2]) + b.z;
+    v[4 * q4 + 3] = __uint_as_float(raw[4 * q4 + 3]) + b.w;
+  }
+  if constexpr ((MODE & 2) != 0) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
+  }
+  // row_ptr = this thread's 128-byte row of the staging tile, rx = row & 7 (the swizzle key), chunk0 = first chunk
+  uint4* slot[CPG];
+#pragma unroll
+  for (int k = 0; k < CPG; ++k) slot[k] = reinterpret_cast<uint4*>(row_ptr + (((chunk0 + (uint32_t)k) ^ rx) << 4));
+  if constexpr ((MODE & 1) != 0) {
+    if constexpr (sizeof(TO) == 2) {
+      Vec16<TO> rv;
+      rv.v[0] = *slot[0];
+      rv.v[1] = *slot[1];
+      rv.add_to(v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint4 t = *slot[k];
+        v[4 * k] += __uint_as_float(t.x); v[4 * k + 1] += __uint_as_float(t.y);
+        v[4 * k + 2] += __uint_as_float(t.z); v[4 * k + 3] += __uint_as_float(t.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], floor);
+  if constexpr (sizeof(TO) == 2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 o;
+      uint32_t* po = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if constexpr (std::is_same<TO, __half>::value) {
+          __half2 t = __floats2half2_rn(v[8 * h + 2 * e], v[8 * h + 2 * e + 1]);
+          po[e] = *reinterpret_cast<uint32_t*>(&t);
+        } else {
+          __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * h + 2 * e], v[8 * h + 2 * e + 1]);
+          po[e] = *reinterpret_cast<uint32_t*>(&t);
+        }
+      }
+      *slot[h] = o;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      *slot[k] = make_uint4(__float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3]));
+  }
+}
+
 // host helpers (capf_tc.cu)
 int tc_get_encoder();
 int tc_encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,

@@ -59,11 +59,12 @@ def test_conv2d_simt(shape, dt, act, use_res):
     assert rel_l2(out.float().cpu(), y) < (2e-6 if dt == torch.float32 else 1.5e-3)
 
 
-@pytest.mark.parametrize("shape", [(2, 17, 13), (3, 64, 48), (1, 256, 256)], ids=str)
+@pytest.mark.parametrize("shape", [(2, 17, 13), (3, 64, 48), (1, 256, 256), (2, 384, 288), (5, 40, 260), (300, 8, 8)], ids=str)
 @pytest.mark.parametrize("odt", [torch.float16, torch.bfloat16])
 def test_stem_conv_f32_image_to_16bit(shape, odt):
-    """HRNet conv1 (pose_hrnet.py:321-322): fp32 NHWC image in, folded-BN 3x3/s2 3->64 + ReLU, 16-bit out
-    (the specialised stem kernel of capf_simt.cu)."""
+    """HRNet conv1 (pose_hrnet.py:321-322): fp32 NHWC image in, folded-BN 3x3/s2 3->64 + ReLU, 16-bit out: the tensor-pipe
+    stem of capf_stem.cu (W % 4 == 0; one or several 128-pixel tiles per output row, ragged last tile, more tiles than
+    CTAs) and the CUDA-core stem of capf_simt.cu (odd widths)."""
     N, H, W = shape
     g = _gen(11)
     x = torch.randn(N, H, W, 3, generator=g)

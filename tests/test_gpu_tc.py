@@ -18,6 +18,57 @@ def test_tc_conv_matches_fp32_reference(case, dt):
     assert bad_rows == 0.0 and rel < tol
 
 
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+@pytest.mark.parametrize("epi", [1, 2], ids=["direct", "staged"])
+@pytest.mark.parametrize("msub", [1, 2], ids=["m128", "m256"])
+def test_tc_gemm_tile_and_epilogue_variants(case, epi, msub):
+    """Per-tap kernel forced (variant 1) with both tile heights (one / two 128-row sub-tiles sharing each B stage) and
+    both epilogues (per-row vectors / coalesced staging tile): same operator, same tolerance."""
+    rel, max_abs, bad_rows = run_tc_case(case, torch.float16, variant=1, epi=epi, msub=msub)
+    print(f"{case[0]} epi={epi} msub={msub}: rel-L2 {rel:.3e} max-abs {max_abs:.3e} bad-rows {bad_rows:.4f}")
+    tol = 2e-5 if case[4] else 1.5e-3
+    assert bad_rows == 0.0 and rel < tol
+
+
+@pytest.mark.parametrize("bn", [16, 48, 80, 240], ids=lambda v: f"bn{v}")
+def test_tc_gemm_column_tiles(bn):
+    """Forced column-tile widths (incl. BN = 16, where one epilogue warp of each quadrant has no columns, and the
+    single-accumulator-stage 256 x 240 tile of the QKV GEMM)."""
+    case = ("rows_bn_sweep", (1100, 1, 1, 128, 240, 1, 1), 0, True, False)
+    for msub in (1, 2):
+        rel, _, bad = run_tc_case(case, torch.float16, variant=1, epi=2, msub=msub, bn=bn)
+        assert bad == 0.0 and rel < 1.5e-3, (msub, bn, rel)
+
+
+def test_tc_gemm_in_place_residual_at_benchmark_size():
+    """x += Linear(t) in place on the fp32 token stream (pose_dformer.py:77-78 as the lifter runs it), every SM busy;
+    repeated launches from the same input agree bit for bit and match the fp32 reference."""
+    import ctypes
+    from capf_b200 import lib
+    M, K, N = 4352, 1280, 640
+    g = torch.Generator(device="cuda").manual_seed(11)
+    t = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x0 = torch.randn(M, N, device="cuda", generator=g)
+    want = x0 + t.float() @ w.float().t() + bias
+    outs = []
+    for _ in range(3):
+        x = x0.clone()
+        op = lib.CapfOp()
+        op.kind, op.dtype_in, op.dtype_out = lib.OP_CONV2D, lib.F16, lib.F32
+        for n, v in enumerate([M, 1, 1, K, N, 1, 1, 1, 0, 1, 1, lib.ACT_NONE, lib.IMPL_TCGEN05, 0]):
+            op.i[n] = v
+        op.inp[0], op.inp[1], op.inp[2], op.inp[3] = t.data_ptr(), w.data_ptr(), bias.data_ptr(), x.data_ptr()
+        op.out[0] = x.data_ptr()
+        lib.check(lib.load().capf_op_run(ctypes.byref(op), 0, torch.cuda.current_stream().cuda_stream), "linear")
+        torch.cuda.synchronize()
+        outs.append(x)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    rel = float((outs[0] - want).norm() / want.norm())
+    assert rel < 2e-5, rel
+
+
 @pytest.mark.parametrize("case", HALO_CASES, ids=[c[0] for c in HALO_CASES])
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
 def test_halo_conv_matches_fp32_reference(case, dt):
