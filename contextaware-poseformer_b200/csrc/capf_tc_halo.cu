@@ -24,6 +24,7 @@ namespace capf {
 
 constexpr int HALO_THREADS = 512;
 constexpr int HALO_HEADER_BYTES = 1024;
+constexpr int HALO_BIAS_OFF = 512;            // 64 fp32 bias values inside the header
 constexpr int HALO_EPI_GROUPS = 3;          // warps 4..15
 constexpr int HALO_MAX_ACC = 2 * HALO_EPI_GROUPS;   // two TMEM accumulator stages per epilogue group
 
@@ -92,7 +93,7 @@ struct HaloWalk {
   }
 };
 
-template <int C, int NV, typename TI, typename TO>
+template <int C, int NV, typename TI, typename TO, bool RES>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const HaloP p) {
   constexpr int KSTEPS = C / 16;                                   // 16-channel MMA steps per filter tap
@@ -132,6 +133,11 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   if (warp == 2) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  if (warp == 3 && lane < 16) {     // folded-BN shift (constant data, not produced by the predecessor kernel)
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias && 4 * lane < p.Cout) b4 = __ldg(reinterpret_cast<const float4*>(p.bias) + lane);
+    *reinterpret_cast<float4*>(smem_raw + (base + HALO_BIAS_OFF - raw) + 16 * lane) = b4;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -248,18 +254,26 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     //     not the tensor pipe, the limiter of the C = 64 layers);
     //   * each thread adds its row in place (conflict-free row-wise access thanks to the swizzle);
     //   * the finished tile leaves with the same coalesced lane mapping.
+    // The epilogue of a sub-tile is ONE warp's dependent instruction stream per 32 pixels, and with N <= 64 it, not the
+    // tensor pipe, paces the kernel (the issuers were measured waiting 1-2.5 k cycles per sub-tile for a free
+    // accumulator): the residual add is a compile-time variant, the bias sits in shared memory, and every lane
+    // computes the image offset of ITS pixel once per sub-tile -- the coalesced phases fetch it with one shuffle.
     constexpr int NG = HALO_EPI_GROUPS;
     constexpr int CH = NV * 2;                        // 16-byte chunks per pixel row of the staging tile
     constexpr int ROWB = NV * 32;                     // bytes per pixel row
+    constexpr int MODE = RES ? 1 : 0;
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     const TO* res = reinterpret_cast<const TO*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
     const uint32_t stage = smem_halo + 2u * (uint32_t)p.halo_bytes + (uint32_t)(warp - 4) * (32u * ROWB);
+    uint8_t* const stage_ptr = smem_raw + (stage - raw);
+    const float* const sbias = reinterpret_cast<const float*>(smem_raw + (base + HALO_BIAS_OFF - raw));
     // chunk c of pixel r lives at r * ROWB + ((c ^ swz(r)) * 16); swz keeps both access patterns conflict-free
     // (CH = 6, i.e. Cout = 48, is not a power of two: stored plain, a few bank conflicts on that rare shape)
     auto swz = [](int r) { return CH == 8 ? (r & 7) : CH == 4 ? ((r >> 1) & 3) : CH == 2 ? ((r >> 2) & 1) : 0; };
-    auto slot = [&](int r, int c) { return stage + (uint32_t)(r * ROWB + ((c ^ swz(r)) * 16)); };
+    auto slot_off = [&](int r, int c) { return (uint32_t)(r * ROWB + ((c ^ swz(r)) * 16)); };
+    const float floor_v = p.act == CAPF_ACT_RELU ? 0.f : -__int_as_float(0x7f800000);
 
     HaloWalk w;
     w.init(p, band0, band1);
@@ -267,52 +281,50 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     uint32_t trace_n = 0;
     const uint64_t pol_in = ptx::policy_evict_first(), pol_out = ptx::policy_evict_last();
 
-    // global element offset of padded pixel (sub-tile t, row r of this warp), or -1 when it is padding / past the band
-    auto pixel_off = [&](const HaloWalk& t, int r) -> long long {
-      const int mp = t.j * 128 + q * 32 + r;
+    // global element offset of this lane's padded pixel in sub-tile t, or -1 when it is padding / past the band
+    auto my_pixel_off = [&](const HaloWalk& t) -> int {
+      const int mp = t.j * 128 + q * 32 + lane;
       const int iy = div_wp(mp, p.wp_magic), ix = mp - iy * p.Wp;
       const bool live = t.valid() && ix < p.W && iy < t.bh_eff;
-      return live ? (long long)((((size_t)t.img * p.H + t.y0 + iy) * p.W + ix) * p.Cout) : -1;
+      return live ? (((t.img * p.H + t.y0 + iy) * p.W + ix) * p.Cout) : -1;
     };
     // coalesced lane mapping: item = i * 32 + lane -> (pixel row r = item / CH, chunk c = item % CH)
-    auto prefetch_residual = [&](const HaloWalk& t) {
-      if (res == nullptr) return;
+    auto prefetch_residual = [&](int myoff) {
+      if (!RES) return;
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         const int item = i * 32 + lane, r = item / CH, c = item % CH;
-        const long long off = pixel_off(t, r);
+        const int off = __shfl_sync(0xffffffffu, myoff, r);
         if (off >= 0) {
-          if (p.l2_hints) ptx::cp_async16_hint(slot(r, c), res + off + c * 8, pol_in);
-          else ptx::cp_async16(slot(r, c), res + off + c * 8);
+          if (p.l2_hints) ptx::cp_async16_hint(stage + slot_off(r, c), res + off + c * 8, pol_in);
+          else ptx::cp_async16(stage + slot_off(r, c), res + off + c * 8);
         }
       }
       ptx::cp_async_commit();
     };
-    prefetch_residual(w);
+    int myoff = my_pixel_off(w);
+    prefetch_residual(myoff);
     while (w.valid()) {
       const uint32_t acc = w.acc(), aph = w.use_parity();
-      const HaloWalk cur = w;
       for (int i = 0; i < NG && w.valid(); ++i) w.step(p);
-      const bool live = pixel_off(cur, lane) >= 0;
-      const bool has_res = live && res != nullptr;
+      const int nextoff = my_pixel_off(w);           // -1 everywhere once the walk has ended
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
       ptx::mbar_wait(bar_tfull + 8 * acc, aph);
       ptx::tc_fence_after();
       if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0) p.trace[(5 + grp) * 256 + (trace_n & 255)] = clock64();
-      ptx::cp_async_wait_all();                      // this tile's residual (requested one group period ago) has landed
-      __syncwarp();
+      if (RES) {
+        ptx::cp_async_wait_all();                    // this tile's residual (requested one group period ago) has landed
+        __syncwarp();
+      }
 #pragma unroll
       for (int v = 0; v < NV; v += 2) {
         const bool two = v + 1 < NV;
         uint32_t a0[16], a1[16];
         ptx::tmem_ld16(taddr + (uint32_t)(16 * v), a0);
         if (two) ptx::tmem_ld16(taddr + (uint32_t)(16 * v + 16), a1);
-        Bias16 b0, b1;
-        b0.load(p.bias, 16 * v);
-        if (two) b1.load(p.bias, 16 * v + 16);
         ptx::tmem_ld_wait();
-        finish16_smem<TO>(b0, p.act, a0, has_res, slot(lane, 2 * v), slot(lane, 2 * v + 1));
-        if (two) finish16_smem<TO>(b1, p.act, a1, has_res, slot(lane, 2 * v + 2), slot(lane, 2 * v + 3));
+        epi16<TO, MODE>(a0, sbias + 16 * v, floor_v, stage_ptr + lane * ROWB, (uint32_t)(2 * v), (uint32_t)swz(lane));
+        if (two) epi16<TO, MODE>(a1, sbias + 16 * v + 16, floor_v, stage_ptr + lane * ROWB, (uint32_t)(2 * v + 2), (uint32_t)swz(lane));
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_tempty + 8 * acc);          // accumulator drained: the issuer may reuse the stage
@@ -320,14 +332,16 @@ tc_conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         const int item = i * 32 + lane, r = item / CH, c = item % CH;
-        const long long off = pixel_off(cur, r);
+        const int off = __shfl_sync(0xffffffffu, myoff, r);
         if (off >= 0) {
-          if (p.l2_hints) ptx::st_global_v4_hint(out + off + c * 8, ptx::ld_shared_v4(slot(r, c)), pol_out);
-          else *reinterpret_cast<uint4*>(out + off + c * 8) = ptx::ld_shared_v4(slot(r, c));
+          const uint4 val = *reinterpret_cast<const uint4*>(stage_ptr + slot_off(r, c));
+          if (p.l2_hints) ptx::st_global_v4_hint(out + off + c * 8, val, pol_out);
+          else *reinterpret_cast<uint4*>(out + off + c * 8) = val;
         }
       }
       __syncwarp();
-      prefetch_residual(w);
+      myoff = nextoff;
+      prefetch_residual(myoff);
       if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0) p.trace[(8 + grp) * 256 + (trace_n & 255)] = clock64();
       ++trace_n;
     }
@@ -365,6 +379,8 @@ static int halo_plan(const capf_op& op, HaloP& p, int& smem_bytes) {
   if (op.dtype_out != op.dtype_in) return 0;      // 16-bit activations in and out (the backbone case)
   if ((C != 16 && C != 32 && C != 48 && C != 64) || Cout % 16 || Cout > 64) return 0;   // instantiated widths; <= 4 residual vectors
   if (W + 1 > 256 || N <= 0 || H <= 0 || W <= 0) return 0;
+  if (op.i[11] == CAPF_ACT_GELU) return 0;                         // backbone convs only: identity / ReLU epilogues
+  if ((long long)N * H * W * Cout >= (1ll << 31)) return 0;        // 32-bit element offsets in the epilogue
   memset(&p, 0, sizeof(p));
   p.C = C; p.Cout = Cout; p.H = H; p.W = W; p.Nimg = N; p.Wp = W + 1;
   p.wp_magic = (uint32_t)(((1ull << 32) + p.Wp - 1) / p.Wp);
@@ -468,16 +484,21 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
   return CAPF_OK;
 }
 
-template <int C, int NV, typename TI, typename TO>
-static int halo_launch_cn(const TcHaloState* s, cudaStream_t st) {
+template <int C, int NV, typename TI, typename TO, bool RES>
+static int halo_launch_cnr(const TcHaloState* s, cudaStream_t st) {
   static bool opted = false;
   if (!opted) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv3_halo_kernel<C, NV, TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv3_halo_kernel<C, NV, TI, TO, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_conv3_halo_kernel smem opt-in: %s", cudaGetErrorString(e));
     opted = true;
   }
-  launch_k(tc_conv3_halo_kernel<C, NV, TI, TO>, dim3(s->grid), dim3(HALO_THREADS), s->smem_bytes, st, s->mapA, s->mapB, s->p);
+  launch_k(tc_conv3_halo_kernel<C, NV, TI, TO, RES>, dim3(s->grid), dim3(HALO_THREADS), s->smem_bytes, st, s->mapA, s->mapB, s->p);
   return check_launch("tc_conv3_halo_kernel");
+}
+
+template <int C, int NV, typename TI, typename TO>
+static int halo_launch_cn(const TcHaloState* s, cudaStream_t st) {
+  return s->p.res ? halo_launch_cnr<C, NV, TI, TO, true>(s, st) : halo_launch_cnr<C, NV, TI, TO, false>(s, st);
 }
 
 template <int C, typename TI, typename TO>

@@ -46,7 +46,7 @@ HALO_CASES = [
     ("halo_c64_many_bands", (150, 32, 32, 64, 64, 3, 1), lib.ACT_NONE, True, False),
     ("halo_c48_9x7", (3, 9, 7, 48, 48, 3, 1), lib.ACT_RELU, True, False),
     ("halo_c32_64x48", (2, 64, 48, 32, 32, 3, 1), lib.ACT_RELU, True, False),
-    ("halo_c64_32x24", (2, 32, 24, 64, 64, 3, 1), lib.ACT_GELU, False, False),
+    ("halo_c64_32x24", (2, 32, 24, 64, 64, 3, 1), lib.ACT_NONE, False, False),
     ("halo_c16_tiny", (1, 3, 5, 16, 16, 3, 1), lib.ACT_NONE, False, False),
     ("halo_c64_c32", (2, 16, 16, 64, 32, 3, 1), lib.ACT_NONE, True, False),
     ("halo_c32_c64_96x72", (1, 96, 72, 32, 64, 3, 1), lib.ACT_RELU, False, False),
