@@ -2,6 +2,7 @@
 // CA_PF.forward path, plus the memory-bound operators (samplers, LayerNorm, tiny attention, fuse-sum)
 // that the fp16/bf16 tensor-core path shares.  Reference citations are relative to
 // /root/reference/ContextPose/mvn/models/.
+#include <cstdlib>
 #include <type_traits>
 
 #include "capf_common.cuh"
@@ -759,6 +760,189 @@ __global__ void __launch_bounds__(128) attention_small_kernel(int groups, int he
   }
 }
 
+// ---- 16-bit fast paths -------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]);
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+template <typename T> __device__ __forceinline__ uint4 pack8(const float (&f)[8]);
+template <> __device__ __forceinline__ uint4 pack8<__half>(const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+  return u;
+}
+template <> __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return u;
+}
+
+// Attention over the 17 joints of a frame (pose_dformer.py:235-238; 8 heads x 80): one warp per (frame, head).  K and V
+// (17 x 80, 16-bit) are staged in shared memory with 16-byte loads; lane i < 17 keeps query row i and its 80 fp32 output
+// accumulators in registers and reads K / V rows as warp-wide broadcasts, so the inner loops are 8 FMAs per LDS.128.
+template <typename T, int HDC>   // HDC = head_dim / 8
+__global__ void __launch_bounds__(128) attention17_kernel(int groups, int heads, int grp_stride, float scale, const T* __restrict__ qkv,
+                                                          T* __restrict__ out) {
+  pdl_wait();
+  constexpr int SEQ = 17, HD = HDC * 8;
+  __shared__ uint4 skv[4][2][SEQ * HDC];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * 4 + wib;
+  if (item >= (long long)groups * heads) return;
+  const int g = (int)(item / heads), h = (int)(item % heads);
+  const int D = heads * HD;
+  const T* base = qkv + (size_t)g * grp_stride * (3 * D) + h * HD;       // token t: + t * 3D (tok_stride == 1)
+  for (int c = lane; c < SEQ * HDC; c += 32) {
+    const int t = c / HDC, k = c - t * HDC;
+    const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)t * (3 * D) + D) + k;
+    skv[wib][0][c] = __ldg(src);
+    skv[wib][1][c] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(src) + D));
+  }
+  const int i = lane < SEQ ? lane : SEQ - 1;                               // idle lanes shadow the last query (no divergence)
+  uint4 q[HDC];
+#pragma unroll
+  for (int k = 0; k < HDC; ++k) q[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)i * (3 * D)) + k);
+  __syncwarp();
+  float sc[SEQ], mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < SEQ; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < HDC; ++k) {
+      float qf[8], kf[8];
+      unpack8<T>(q[k], qf);
+      unpack8<T>(skv[wib][0][j * HDC + k], kf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a = fmaf(qf[e], kf[e], a);
+    }
+    sc[j] = a * scale;
+    mx = fmaxf(mx, sc[j]);
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < SEQ; ++j) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
+  const float inv = 1.0f / den;
+  float o[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < SEQ; ++j) {
+#pragma unroll
+    for (int k = 0; k < HDC; ++k) {
+      float vf[8];
+      unpack8<T>(skv[wib][1][j * HDC + k], vf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[8 * k + e] = fmaf(sc[j], vf[e], o[8 * k + e]);
+    }
+  }
+  if (lane < SEQ) {
+    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)g * grp_stride + lane) * D + h * HD);
+#pragma unroll
+    for (int k = 0; k < HDC; ++k) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = o[8 * k + e] * inv;
+      dst[k] = pack8<T>(f);
+    }
+  }
+}
+
+// Attention over the 5 level tokens of one joint (pose_dformer.py:231-234; 8 heads x 16): one LANE per (joint, head), a
+// warp covers 4 joints.  q/k/v of a lane are 15 x 32 bytes, loaded straight into registers (the 8 heads of a token are
+// 256 contiguous bytes, so a warp's loads are full sectors); no shared memory, no synchronisation.
+template <typename T>
+__global__ void __launch_bounds__(128) attention5_kernel(int groups, int tok_stride, int grp_stride, float scale, const T* __restrict__ qkv,
+                                                         T* __restrict__ out) {
+  pdl_wait();
+  constexpr int SEQ = 5, D = 128;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long g = warp * 4 + (lane >> 3);
+  if (g >= groups) return;
+  const int h = lane & 7;
+  uint4 qv[SEQ][2], kv[SEQ][2], vv[SEQ][2];
+#pragma unroll
+  for (int t = 0; t < SEQ; ++t) {
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + ((size_t)g * grp_stride + (size_t)t * tok_stride) * (3 * D) + h * 16);
+    qv[t][0] = __ldg(src); qv[t][1] = __ldg(src + 1);
+    kv[t][0] = __ldg(src + D / 8); kv[t][1] = __ldg(src + D / 8 + 1);
+    vv[t][0] = __ldg(src + 2 * D / 8); vv[t][1] = __ldg(src + 2 * D / 8 + 1);
+  }
+#pragma unroll
+  for (int i = 0; i < SEQ; ++i) {
+    float qf[16];
+    { float a[8], b[8]; unpack8<T>(qv[i][0], a); unpack8<T>(qv[i][1], b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { qf[e] = a[e]; qf[8 + e] = b[e]; } }
+    float sc[SEQ], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SEQ; ++j) {
+      float a[8], b[8], acc = 0.f;
+      unpack8<T>(kv[j][0], a); unpack8<T>(kv[j][1], b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(qf[e], a[e], acc);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(qf[8 + e], b[e], acc);
+      sc[j] = acc * scale;
+      mx = fmaxf(mx, sc[j]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < SEQ; ++j) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
+    const float inv = 1.0f / den;
+    float o[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < SEQ; ++j) {
+      float a[8], b[8];
+      unpack8<T>(vv[j][0], a); unpack8<T>(vv[j][1], b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { o[e] = fmaf(sc[j], a[e], o[e]); o[8 + e] = fmaf(sc[j], b[e], o[8 + e]); }
+    }
+    float f0[8], f1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { f0[e] = o[e] * inv; f1[e] = o[8 + e] * inv; }
+    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)g * grp_stride + (size_t)i * tok_stride) * D + h * 16);
+    dst[0] = pack8<T>(f0);
+    dst[1] = pack8<T>(f1);
+  }
+}
+
+template <typename T>
+static int attention_fast(const capf_op& op, cudaStream_t st, bool& taken) {
+  const int groups = op.i[0], seq = op.i[1], heads = op.i[2], hd = op.i[3], ts = op.i[4], gs = op.i[5];
+  taken = false;
+  { const char* ev = getenv("CAPF_ATTN_FAST"); if (ev && ev[0] == '0') return CAPF_OK; }
+  if ((((uintptr_t)op.in[0]) | ((uintptr_t)op.out[0])) & 15) return CAPF_OK;
+  const T* qkv = (const T*)op.in[0];
+  T* out = (T*)op.out[0];
+  if (seq == 17 && hd == 80 && ts == 1) {
+    const long long items = (long long)groups * heads;
+    launch_k(attention17_kernel<T, 10>, dim3((unsigned)((items + 3) / 4)), dim3(128), 0, st, groups, heads, gs, op.f[0], qkv, out);
+    taken = true;
+    return check_launch("attention17");
+  }
+  if (seq == 5 && hd == 16 && heads == 8) {
+    const long long warps = ((long long)groups + 3) / 4;
+    launch_k(attention5_kernel<T>, dim3((unsigned)((warps + 3) / 4)), dim3(128), 0, st, groups, ts, gs, op.f[0], qkv, out);
+    taken = true;
+    return check_launch("attention5");
+  }
+  return CAPF_OK;
+}
+
 template <typename TI, typename TO>
 static int attention_dispatch(const capf_op& op, cudaStream_t st) {
   int groups = op.i[0], seq = op.i[1], heads = op.i[2], hd = op.i[3], ts = op.i[4], gs = op.i[5];
@@ -793,8 +977,18 @@ int launch_attention(const capf_op& op, cudaStream_t st) {
   if (op.i[0] <= 0 || (seq != 5 && seq != 17) || op.i[2] <= 0 || hd <= 0 || hd > 256)
     return set_error(CAPF_ERR_ARG, "attention: seq must be 5 or 17, head_dim <= 256");
   if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_F32) return attention_dispatch<float, float>(op, st);
-  if (op.dtype_in == CAPF_F16 && op.dtype_out == CAPF_F16) return attention_dispatch<__half, __half>(op, st);
-  if (op.dtype_in == CAPF_BF16 && op.dtype_out == CAPF_BF16) return attention_dispatch<__nv_bfloat16, __nv_bfloat16>(op, st);
+  if (op.dtype_in == CAPF_F16 && op.dtype_out == CAPF_F16) {
+    bool taken;
+    int e = attention_fast<__half>(op, st, taken);
+    if (e || taken) return e;
+    return attention_dispatch<__half, __half>(op, st);
+  }
+  if (op.dtype_in == CAPF_BF16 && op.dtype_out == CAPF_BF16) {
+    bool taken;
+    int e = attention_fast<__nv_bfloat16>(op, st, taken);
+    if (e || taken) return e;
+    return attention_dispatch<__nv_bfloat16, __nv_bfloat16>(op, st);
+  }
   return set_error(CAPF_ERR_UNSUPPORTED, "attention: dtype combination");
 }
 

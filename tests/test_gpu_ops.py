@@ -151,6 +151,27 @@ def test_attention(seq, heads, hd, groups):
     assert (out.cpu() - want).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("seq,heads,hd,groups", [(5, 8, 16, 51), (5, 8, 16, 4352), (17, 8, 80, 7), (17, 8, 80, 256), (17, 4, 32, 5)])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_attention_16bit(seq, heads, hd, groups, dt):
+    """16-bit qkv in / out (the lifter's fp16 / bf16 modes): the register/broadcast fast paths for (17 x 8 x 80) and
+    (5 x 8 x 16) incl. ragged warp tails, and the generic kernel for any other shape, against fp32 PyTorch on the same
+    rounded inputs."""
+    g = _gen(7)
+    D = heads * hd
+    ts, gs = (groups, 1) if seq == 5 else (1, seq)
+    rows = groups * seq
+    qkv = torch.randn(rows, 3 * D, generator=g).to(dt)
+    idx = (torch.arange(groups).view(-1, 1) * gs + torch.arange(seq).view(1, -1) * ts).reshape(-1)
+    x = qkv.float()[idx].view(groups, seq, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    a = ((x[0] @ x[1].transpose(-2, -1)) * hd ** -0.5).softmax(-1)
+    want = torch.empty(rows, D)
+    want[idx] = (a @ x[2]).transpose(1, 2).reshape(groups * seq, D)
+    out = torch.full((rows, D), float("nan"), dtype=dt, device=DEV)
+    run_op(lib.OP_ATTENTION, dt, dt, [groups, seq, heads, hd, ts, gs], [hd ** -0.5], [qkv.to(DEV)], [out])
+    assert rel_l2(out.float().cpu(), want) < (1e-3 if dt == torch.float16 else 6e-3)
+
+
 def test_samplers_match_aten_values():
     """Blend values of both gathers vs F.grid_sample (zeros / border), incl. points outside the map and on +-1."""
     import capf_oracle
