@@ -226,11 +226,12 @@ def run_native(args):
             upload(0)
             for i in range(n):
                 s = stage[i & 1]
+                if i + 1 < n:
+                    # prefetch the next step's inputs while this step computes.  Its slot was last read by step i-1,
+                    # which has completed: the blocking D2H of that step's result synchronised the host with it.
+                    upload((i + 1) & 1)
                 torch.cuda.current_stream(dev).wait_event(s["ev"])
                 o = model(s["img"], s["kp"], s["crop"])
-                if i + 1 < n:
-                    copy_stream.wait_stream(torch.cuda.current_stream(dev))   # do not overwrite a slot still being read
-                    upload((i + 1) & 1)
                 if gather is not None:
                     o = gather(o)[rank * B:(rank + 1) * B]
                 h_out.copy_(o, non_blocking=False)                            # D2H of the step's result (synchronises)

@@ -12,6 +12,7 @@ Precision policies
   bf16 : same with bfloat16
 """
 import os
+import re
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional
 
@@ -75,6 +76,7 @@ class Op:
     outs: list
     tag: str = ""
     flops: int = 0
+    lane: int = 0          # execution lane (stream): HRNet branch chains run side by side, see assign_lanes()
 
 
 @dataclass
@@ -288,6 +290,7 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
         for k, m in enumerate(maps):
             m.ref.role = "output"
             prog.outputs[f"map{k}"] = m.ref
+        assign_lanes(prog, _lanes_enabled())
         return prog
 
     D = int(pf_cfg["embed_dim_ratio"])
@@ -390,14 +393,97 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
               WSlot("b:head.1", (3,), "f32", vec_packer([vn + "head.1.bias"]))], [out],
              tag=vn + "head", flops=2 * R * E * 3)
     prog.outputs["out"] = out
+    assign_lanes(prog, _lanes_enabled())
     return prog
+
+
+def _lanes_enabled():
+    return os.environ.get("CAPF_STREAMS", "1") != "0"
+
+
+# ------------------------------------------------------------------------------------------------------
+# execution lanes: the branches of a HighResolutionModule are independent chains (pose_hrnet.py:289-290)
+# ------------------------------------------------------------------------------------------------------
+MAX_LANES = 4
+_LANE_RE = re.compile(r"\.stage\d+\.\d+\.branches\.(\d+)\.|\.stage\d+\.\d+\.fuse_layers\.\d+\.(\d+)\.|\.transition\d+\.(\d+)\.")
+
+
+def assign_lanes(prog: Program, enable: bool = True):
+    """Lane (stream) of every op.  Branch b of an HRNet stage -- its BasicBlocks, the fuse-layer convolutions that read
+    it, the transition that creates it and the fuse-sum that produces its next input -- runs on lane b; everything else
+    (stem, layer1, CPN, the lifter) on lane 0.  Kernels of one lane are ordered; lanes only meet through the data
+    dependencies op_schedule() turns into events.  One-wave kernels that leave SMs idle (C = 128 / 256 branches: 256 or
+    128 tiles on 148 SMs) then overlap with the other branches instead of serialising behind them."""
+    for op in prog.ops:
+        op.lane = 0
+    if not enable:
+        return
+    producer_lane = {}
+    for op in prog.ops:
+        lane = 0
+        if op.kind == lib.OP_CONV2D:
+            m = _LANE_RE.search(op.tag)
+            if m:
+                lane = int(next(g for g in m.groups() if g is not None))
+        elif op.kind == lib.OP_FUSE_SUM:
+            # output index i = position of the identity term: terms are ordered j = 0..n-1, j > i carry a shift
+            shifts = op.i[5:5 + op.i[4]]
+            first_up = next((k for k, sft in enumerate(shifts) if sft > 0), len(shifts))
+            ident = op.ins[first_up - 1]
+            lane = producer_lane.get(ident.root, 0) if isinstance(ident, Buf) else 0
+        op.lane = min(lane, MAX_LANES - 1)
+        for b in op.outs:
+            if isinstance(b, Buf):
+                producer_lane[b.root] = op.lane
+
+
+def op_clocks(prog: Program):
+    """Vector clocks of the lane-parallel execution.  Returns (vc, waits): vc[k][l] = index of the latest op of lane l
+    that is guaranteed complete before op k starts (-1: none); waits[k] = ops of OTHER lanes whose completion op k must
+    wait for explicitly (at most one per lane: lanes are in-order)."""
+    n = len(prog.ops)
+    vc = [None] * n
+    waits = [[] for _ in range(n)]
+    last_on_lane = [-1] * MAX_LANES
+    writers, readers = {}, {}       # root buffer -> op indices
+    for k, op in enumerate(prog.ops):
+        deps = set()
+        ins = [b.root for b in op.ins if isinstance(b, Buf)]
+        outs = [b.root for b in op.outs if isinstance(b, Buf)]
+        for r in ins:
+            deps.update(writers.get(r, ()))                 # read after write
+        for r in outs:
+            deps.update(writers.get(r, ()))                 # write after write
+            deps.update(readers.get(r, ()))                 # write after read
+        prev = last_on_lane[op.lane]
+        clock = list(vc[prev]) if prev >= 0 else [-1] * MAX_LANES
+        need = [-1] * MAX_LANES
+        for d in deps:
+            need[prog.ops[d].lane] = max(need[prog.ops[d].lane], d)
+        for l in range(MAX_LANES):
+            if l != op.lane and need[l] > clock[l]:
+                waits[k].append(need[l])
+        for d in waits[k]:
+            clock = [max(a, b) for a, b in zip(clock, vc[d])]
+        clock[op.lane] = k
+        vc[k] = clock
+        last_on_lane[op.lane] = k
+        for r in ins:
+            readers.setdefault(r, []).append(k)
+        for r in outs:
+            writers.setdefault(r, []).append(k)
+    return vc, waits
 
 
 # ------------------------------------------------------------------------------------------------------
 # memory planning: greedy reuse of dead activation buffers (exact-size pools)
 # ------------------------------------------------------------------------------------------------------
 def plan_memory(prog: Program):
-    """Returns (assignment: root Buf -> pool slot id, slots: list of (nbytes))."""
+    """Returns (assignment: root Buf -> pool slot id, slots: list of (nbytes)).
+
+    A slot is handed to a new buffer only if every op that touched its previous tenants is ordered before the new
+    buffer's producer by the lane clocks (op_clocks) -- with a single lane this is plain liveness in program order."""
+    vc, _ = op_clocks(prog)
     last_use = {}
     for k, op in enumerate(prog.ops):
         for b in list(op.ins) + list(op.outs):
@@ -405,21 +491,35 @@ def plan_memory(prog: Program):
                 last_use[b.root] = k
     keep_alive = {b.root for b in prog.inputs.values()} | {b.root for b in prog.outputs.values()}
     assign, slots, free = {}, [], {}
+    slot_users = []                 # slot -> per-lane latest op index that touched it
     for k, op in enumerate(prog.ops):
         for b in op.outs:
             if isinstance(b, Buf) and b.root not in assign:
                 r = b.root
-                pool = free.get(r.nbytes)
-                if pool and r not in keep_alive:
-                    assign[r] = pool.pop()
+                pool = free.get(r.nbytes, [])
+                pick = None
+                if r not in keep_alive:
+                    for cand in pool:
+                        if all(vc[k][l] >= slot_users[cand][l] for l in range(MAX_LANES)):
+                            pick = cand
+                            break
+                if pick is not None:
+                    pool.remove(pick)
+                    assign[r] = pick
                 else:
                     slots.append(r.nbytes)
+                    slot_users.append([-1] * MAX_LANES)
                     assign[r] = len(slots) - 1
         for b in op.ins:
             if isinstance(b, Buf) and b.root not in assign:   # program inputs
                 slots.append(b.root.nbytes)
+                slot_users.append([-1] * MAX_LANES)
                 assign[b.root] = len(slots) - 1
-        for b in set(x.root for x in list(op.ins) + list(op.outs) if isinstance(x, Buf)):
+        touched = set(x.root for x in list(op.ins) + list(op.outs) if isinstance(x, Buf))
+        for b in touched:
+            u = slot_users[assign[b]]
+            u[op.lane] = max(u[op.lane], k)
+        for b in touched:
             if last_use[b] == k and b not in keep_alive:
                 free.setdefault(b.nbytes, []).append(assign[b])
     return assign, slots
@@ -513,10 +613,42 @@ class Plan:
             else:
                 self._wtensors[k] = t.to(self.device)
 
+    # ---- lane-parallel schedule ---------------------------------------------------------------------
+    def _schedule(self):
+        """Segments (lane, first, count, wait_ops, record) of one full run: maximal runs of consecutive ops of one lane
+        with the cross-lane waits in front and an event recorded behind when another lane depends on the last op."""
+        if getattr(self, "_segs", None) is not None:
+            return self._segs
+        ops = self.prog.ops
+        _, waits = op_clocks(self.prog)
+        recorded = set(d for w in waits for d in w)
+        last_of_lane = {}
+        for k, op in enumerate(ops):
+            last_of_lane[op.lane] = k
+        self._tails = [k for l, k in last_of_lane.items() if l != 0]
+        recorded.update(self._tails)
+        segs = []
+        for k, op in enumerate(ops):
+            if segs and segs[-1][0] == op.lane and not waits[k] and not segs[-1][4]:
+                lane, first, count, w, _ = segs[-1]
+                segs[-1] = (lane, first, count + 1, w, k in recorded)
+            else:
+                segs.append((op.lane, k, 1, list(waits[k]), k in recorded))
+        self._segs = segs
+        n_side = max([op.lane for op in ops] + [0])
+        self._side = [torch.cuda.Stream(self.device) for _ in range(n_side)]
+        self._events = {k: torch.cuda.Event() for k in recorded}
+        return segs
+
     def run(self, first=0, count=-1, stream=None):
-        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        """Enqueue ops [first, first + count) (default: all).  A full run spreads the lanes of the program over side
+        streams that fork from / join back into `stream` (a torch.cuda.Stream; default: the current one), so it is
+        still one stream-ordered, graph-capturable unit of work for the caller.  Partial runs are single-stream."""
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        s = st.cuda_stream
+        n_ops = len(self.prog.ops)
         if os.environ.get("CAPF_DEBUG_SYNC", "0") != "0":      # locate a faulting op: one launch + sync at a time
-            n = len(self.prog.ops) - first if count < 0 else count
+            n = n_ops - first if count < 0 else count
             for k in range(first, first + n):
                 lib.check(self._L.capf_plan_run(self._h, k, 1, s), "capf_plan_run")
                 try:
@@ -525,7 +657,21 @@ class Plan:
                     op = self.prog.ops[k]
                     raise lib.CapfError(f"op {k} ({op.tag}, kind {op.kind}, i={op.i}) faulted: {e}") from e
             return
-        lib.check(self._L.capf_plan_run(self._h, first, count, s), "capf_plan_run")
+        full = first == 0 and (count < 0 or count == n_ops)
+        segs = self._schedule() if full else None
+        if not full or not self._side:
+            lib.check(self._L.capf_plan_run(self._h, first, count, s), "capf_plan_run")
+            return
+        streams = [st] + self._side
+        for lane, k0, n, waits, record in segs:
+            ls = streams[lane]
+            for w in waits:
+                ls.wait_event(self._events[w])
+            lib.check(self._L.capf_plan_run(self._h, k0, n, ls.cuda_stream), "capf_plan_run")
+            if record:
+                self._events[k0 + n - 1].record(ls)
+        for k in self._tails:                                   # join: the caller's stream owns the result again
+            st.wait_event(self._events[k])
 
     @property
     def num_launches(self):
@@ -557,7 +703,7 @@ class Plan:
         side.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
-            self.run(stream=side.cuda_stream)
+            self.run(stream=side)
         self._graph = g
         return g
 
