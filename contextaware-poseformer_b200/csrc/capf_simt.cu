@@ -1136,6 +1136,133 @@ __global__ void __launch_bounds__(256) deform_sample_kernel(SampP p, const float
   }
 }
 
+// 16-bit fast path of the deformable gather: one warp per (frame, joint, level).  Lane s < 16 evaluates sample s
+// (head s / 4, sample s % 4) ONCE -- softmax weight through two shuffles inside the head's 4 lanes, tanh offsets, the
+// ATen corner record -- and publishes element offsets / blend weights through shared memory; then the lanes regroup as
+// 32 / LPG sample groups of LPG lanes that each fetch 8 channels (16 bytes) per corner, so all four corners of up to
+// eight samples are in flight per instruction.  Corner order and the unfused multiply-add of ATen are kept inside a
+// sample; the per-head sum over the head's samples meets through shuffles.
+struct DSample {
+  int off[4];       // element offset of the corner pixel in the map (-1: corner outside the map)
+  float w[4];       // bilinear weights nw, ne, sw, se
+};
+
+// Gather + blend + per-head sum for one (frame, joint, level) with LPG lanes per sample group.
+template <typename T, int LPG>     // LPG = pow2 >= min(C / 8, 32)
+__device__ __forceinline__ void deform_gather(const DSample* __restrict__ samp, const float* __restrict__ aws, const T* __restrict__ m, T* __restrict__ o,
+                                              int C, int lane) {
+  constexpr int NG = 32 / LPG;                     // sample groups per instruction
+  constexpr int ITS = 16 / NG;                     // instructions per pass
+  constexpr int IPH = NG >= 4 ? 1 : 4 / NG;        // iterations that make up one head
+  constexpr int GH = NG >= 4 ? 4 : NG;             // groups that hold samples of the same head
+  const int grp = lane / LPG, li = lane - grp * LPG;
+  const int CP = C >> 3;                           // 16-byte chunks per pixel
+  const int n_pass = (CP + LPG - 1) / LPG;         // 1 unless C > 256 (LPG = 32)
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int ch = pass * LPG + li;
+    const bool active = ch < CP;                   // C / 8 not a power of two (HRNet-48): some lanes only shuffle
+    float acc[8];
+#pragma unroll
+    for (int it = 0; it < ITS; ++it) {
+      const int sidx = it * NG + grp;
+      if (it % IPH == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      }
+      const DSample d = samp[sidx];
+      const float aw = aws[sidx];
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        v[k] = (active && d.off[k] >= 0) ? __ldg(reinterpret_cast<const uint4*>(m + d.off[k]) + ch) : make_uint4(0u, 0u, 0u, 0u);
+      float a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (d.off[k] >= 0) {                       // ATen skips out-of-map corners; inside a sample: out += val * weight
+          float f[8];
+          unpack8<T>(v[k], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a[e] = __fadd_rn(a[e], __fmul_rn(f[e], d.w[k]));
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(aw, a[e], acc[e]);
+      if (it % IPH == IPH - 1) {                   // the head's four samples are in: meet across its groups, store
+#pragma unroll
+        for (int off = LPG; off < LPG * GH; off <<= 1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+        }
+        const int h = sidx >> 2;
+        if (active && (grp % GH) == 0) *reinterpret_cast<uint4*>(o + (size_t)h * C + 8 * ch) = pack8<T>(acc);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) deform_sample16_kernel(SampP p, const float* __restrict__ ref, const float* __restrict__ ow,
+                                                              T* __restrict__ out, int* __restrict__ rec) {
+  pdl_wait();
+  __shared__ DSample ssamp[8][16];
+  __shared__ float saw[8][16];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + wib;
+  const int R = p.B * p.J;
+  if (warp >= (long long)R * p.nl) return;
+  const int rj = (int)(warp / p.nl), l = (int)(warp - (long long)rj * p.nl);   // level fastest: every block mixes light and heavy levels
+  const int b = rj / p.J;
+  const int H = p.H[l], W = p.W[l], C = p.C[l];
+  const float* row = ow + ((size_t)l * R + rj) * 48;
+  if (lane < 16) {
+    const float lg = __ldg(row + lane);
+    float mx = fmaxf(lg, __shfl_xor_sync(0x0000ffffu, lg, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0x0000ffffu, mx, 2));
+    const float e = expf(lg - mx);
+    float den = e + __shfl_xor_sync(0x0000ffffu, e, 1);
+    den += __shfl_xor_sync(0x0000ffffu, den, 2);
+    const float gx = __ldg(ref + 2 * rj), gy = __ldg(ref + 2 * rj + 1);
+    const float ox = tanhf(__ldg(row + 16 + 2 * lane)), oy = tanhf(__ldg(row + 16 + 2 * lane + 1));
+    const float px = __fadd_rn(ox, gx), py = __fadd_rn(oy, gy);
+    const Corners c = make_corners<true>(px, py, W, H);
+    if (rec) {
+      int* r = rec + ((((size_t)l * R + rj) * 16) + lane) * 8;
+      r[0] = c.x0; r[1] = c.y0; r[2] = (int)c.mask; r[3] = 0;
+      r[4] = __float_as_int(px); r[5] = __float_as_int(py); r[6] = 0; r[7] = 0;
+    }
+    DSample d;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = c.x0 + (k & 1), yy = c.y0 + (k >> 1);
+      d.off[k] = (c.mask & (1u << k)) ? (yy * W + xx) * C : -1;
+      d.w[k] = c.w[k];
+    }
+    ssamp[wib][lane] = d;
+    saw[wib][lane] = e / den;
+  }
+  __syncwarp();
+  const T* m = (const T*)p.map[l] + (size_t)b * H * W * C;
+  T* o = out + p.off[l] + (size_t)rj * 4 * C;
+  const int CP = C >> 3;
+  if (CP <= 4) deform_gather<T, 4>(ssamp[wib], saw[wib], m, o, C, lane);
+  else if (CP <= 8) deform_gather<T, 8>(ssamp[wib], saw[wib], m, o, C, lane);
+  else if (CP <= 16) deform_gather<T, 16>(ssamp[wib], saw[wib], m, o, C, lane);
+  else deform_gather<T, 32>(ssamp[wib], saw[wib], m, o, C, lane);
+}
+
+template <typename T>
+static bool deform_fast_ok(const capf_op& op, const SampP& p) {
+  const char* ev = getenv("CAPF_DEFORM_FAST");
+  if (ev && ev[0] == '0') return false;
+  for (int l = 0; l < p.nl; ++l) {
+    if (p.C[l] % 8 || ((uintptr_t)p.map[l] & 15) || (p.off[l] & 7)) return false;
+    if ((long long)p.H[l] * p.W[l] * p.C[l] >= (1ll << 31)) return false;
+  }
+  return ((uintptr_t)op.out[0] & 15) == 0;
+}
+
 static int fill_samp(const capf_op& op, SampP& p, const char* who) {
   p.B = op.i[0]; p.J = op.i[1]; p.nl = op.i[2];
   if (p.B <= 0 || p.J <= 0 || p.nl < 1 || p.nl > 4) return set_error(CAPF_ERR_ARG, who);
@@ -1159,6 +1286,14 @@ static int sample_dispatch(const capf_op& op, const SampP& p, cudaStream_t st) {
     int R = p.B * p.J;
     launch_k(ref_sample_kernel<TI, TO>, dim3((R + 7) / 8), dim3(256), 0, st, p, (const float*)op.in[0], (TO*)op.out[0], (int*)op.out[1]);
     return check_launch("ref_sample");
+  }
+  if constexpr (std::is_same<TI, TO>::value && sizeof(TI) == 2) {
+    if (deform_fast_ok<TI>(op, p)) {
+      const long long w16 = (long long)p.nl * p.B * p.J;
+      launch_k(deform_sample16_kernel<TI>, dim3((unsigned)((w16 + 7) / 8)), dim3(256), 0, st, p, (const float*)op.in[0], (const float*)op.in[5],
+               (TI*)op.out[0], (int*)op.out[1]);
+      return check_launch("deform_sample16");
+    }
   }
   long long warps = (long long)p.nl * p.B * p.J * 4;
   launch_k(deform_sample_kernel<TI, TO>, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, st, p, (const float*)op.in[0], (const float*)op.in[5],

@@ -211,6 +211,48 @@ def test_samplers_match_aten_values():
         assert (got - want).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("geo", [[(16, 12, 32), (8, 6, 64), (4, 3, 128), (2, 2, 256)], [(24, 18, 48), (12, 9, 96), (6, 5, 192), (3, 3, 384)],
+                                 [(16, 12, 256)] * 4], ids=["hrnet32", "hrnet48", "cpn"])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_deform_sample_16bit_fast_path(geo, dt):
+    """The 16-bit deformable gather (one warp per (frame, joint, level), 16-byte loads): values against fp32
+    F.grid_sample(border) on the same rounded maps, corner records bit-identical to the ATen restatement and to the fp32
+    kernel -- for power-of-two channel counts, HRNet-48's 48/96/192/384 (idle lanes, two passes) and CPN's 4 x 256."""
+    import capf_oracle
+    g = _gen(21)
+    B, J = 5, 17
+    maps = [torch.randn(B, h, w, c, generator=g).to(dt) for h, w, c in geo]
+    ref = torch.rand(B * J, 2, generator=g) * 2.8 - 1.4
+    ref[0] = torch.tensor([-1.0, -1.0]); ref[1] = torch.tensor([1.0, 1.0]); ref[2] = torch.tensor([0.0, 0.0])
+    goffs = [0]
+    for h, w, c in geo:
+        goffs.append(goffs[-1] + B * J * 4 * c)
+    flat_geo = [v for t in geo for v in t]
+    ow = torch.randn(4 * B * J, 48, generator=g)
+    gout = torch.full((goffs[-1],), float("nan"), dtype=dt, device=DEV)
+    rec = torch.empty(4, B * J, 16, 8, dtype=torch.int32, device=DEV)
+    run_op(lib.OP_DEFORM_SAMPLE, dt, dt, [B, J, 4] + flat_geo + goffs[:4], [],
+           [ref.to(DEV)] + [m.to(DEV) for m in maps] + [ow.to(DEV)], [gout, rec])
+    rec32 = torch.empty_like(rec)
+    g32 = torch.empty(goffs[-1], device=DEV)
+    run_op(lib.OP_DEFORM_SAMPLE, torch.float32, torch.float32, [B, J, 4] + flat_geo + goffs[:4], [],
+           [ref.to(DEV)] + [m.float().to(DEV) for m in maps] + [ow.to(DEV)], [g32, rec32])
+    assert torch.equal(rec, rec32)
+    owv = ow.view(4, B, J, 48)
+    wts = owv[..., :16].reshape(4, B, J, 4, 4).softmax(-1)
+    pos = owv[..., 16:].reshape(4, B, J, 16, 2).tanh() + ref.view(1, B, J, 1, 2)
+    for l, (h, w, c) in enumerate(geo):
+        s = F.grid_sample(maps[l].float().permute(0, 3, 1, 2), pos[l], padding_mode="border", align_corners=True).permute(0, 2, 3, 1)
+        want = (s.reshape(B, J, 4, 4, c) * wts[l].unsqueeze(-1)).sum(-2)
+        got = gout[goffs[l]:goffs[l + 1]].view(B, J, 4, c).float().cpu()
+        assert rel_l2(got, want) < (6e-4 if dt == torch.float16 else 5e-3)
+        # index path: records recomputed by the ATen restatement from the exact fp32 positions the kernel sampled
+        r = rec[l].cpu().numpy().reshape(-1, 8)
+        pxy = np.ascontiguousarray(r[:, 4:6]).view(np.float32)
+        x0r, y0r, mr, _ = capf_oracle.grid_sample_records(pxy, h, w, border=True)
+        assert np.array_equal(r[:, 0], x0r) and np.array_equal(r[:, 1], y0r) and np.array_equal(r[:, 2], mr)
+
+
 def test_layernorm_with_fused_head_projection():
     """head = LayerNorm(640, eps 1e-5) + Linear(640 -> 3) (pose_dformer.py:205-208,240) as one op."""
     g = _gen(9)
