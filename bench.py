@@ -13,9 +13,9 @@ the [256,1,17,3] outputs -- the only collective of the path (reference train.py:
 
 One JSON line on stdout (rank 0).  `value`: device-resident inputs, CUDA-graph replay, CUDA events, max over ranks.
 `e2e`: same metric through the public API with pinned HOST inputs: H2D copies + D2H of the result inside the timed
-region.  `roofline`: the dominant kernel family (conv / linear implicit GEMM) -- algorithmic FLOPs of its launches
-divided by their summed device time (per-op CUDA events on the launching stream, one in-order pass), against the
-measured bf16 tensor peak of MEASURED_PEAKS.json.  `cpu_baseline`: the oracle (CPU restatement of the reference,
+region.  `roofline`: the dominant kernel (largest summed device time, per-op CUDA events on the launching stream, one
+in-order pass) -- its algorithmic bytes or FLOPs per launch divided by its average launch duration, against the measured
+HBM / bf16 tensor peak of MEASURED_PEAKS.json, whichever bounds it at its arithmetic intensity.  `cpu_baseline`: the oracle (CPU restatement of the reference,
 kind "port") timed on this box's host cores on a bounded sample.
 """
 import argparse
@@ -209,10 +209,10 @@ def run_native(args):
 
         # ---- timed region 2: end to end from pinned host memory ------------------------------------------
         h_img, h_kp, h_crop = images.pin_memory(), kp2d.pin_memory(), crop.pin_memory()
-        h_out = torch.empty(B, 1, 17, 3).pin_memory()
+        h_out = [torch.empty(B, 1, 17, 3).pin_memory() for _ in range(2)]
         copy_stream = torch.cuda.Stream(dev)
         stage = [dict(kp=torch.empty_like(kp_d), crop=torch.empty_like(crop_work), img=torch.empty_like(static["images"]),
-                      ev=torch.cuda.Event()) for _ in range(2)]
+                      ev=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(2)]
 
         def upload(slot):
             with torch.cuda.stream(copy_stream):
@@ -223,18 +223,23 @@ def run_native(args):
                 s["ev"].record(copy_stream)
 
         def e2e_loop(n):
+            """Every step: H2D of its inputs from pinned host memory (copy stream, one step ahead of the compute),
+            CA_PF.forward through the public API, D2H of its [B,1,17,3] result into pinned host memory.  The host never
+            blocks inside the loop: slot reuse is ordered by events, the results are complete at the final synchronise."""
+            cur = torch.cuda.current_stream(dev)
             upload(0)
             for i in range(n):
                 s = stage[i & 1]
                 if i + 1 < n:
-                    # prefetch the next step's inputs while this step computes.  Its slot was last read by step i-1,
-                    # which has completed: the blocking D2H of that step's result synchronised the host with it.
+                    if i >= 1:
+                        copy_stream.wait_event(stage[(i + 1) & 1]["done"])    # step i-1 has consumed that slot
                     upload((i + 1) & 1)
-                torch.cuda.current_stream(dev).wait_event(s["ev"])
+                cur.wait_event(s["ev"])
                 o = model(s["img"], s["kp"], s["crop"])
+                s["done"].record(cur)
                 if gather is not None:
                     o = gather(o)[rank * B:(rank + 1) * B]
-                h_out.copy_(o, non_blocking=False)                            # D2H of the step's result (synchronises)
+                h_out[i & 1].copy_(o, non_blocking=True)                      # D2H of the step's result
             return h_out
 
         e2e_loop(2)
@@ -255,54 +260,78 @@ def run_native(args):
     value = frames / (ms_total / 1e3)
     e2e_value = frames / (ms_e2e / 1e3)
     h2d = h_img.numel() * 4 + h_kp.numel() * 4 + h_crop.numel() * 4
-    d2h = h_out.numel() * 4
+    d2h = h_out[0].numel() * 4
 
     line = None
     if rank == 0:
         peaks = load_peaks()
-        # ---- roofline of the dominant kernel family (live per-op timing) -----------------------------------
+        # ---- roofline of the dominant kernel (live per-op timing) ------------------------------------------------
+        # Per-op device time: CUDA events around every op of one in-order pass on the launching stream.  Ops are
+        # grouped by the kernel the library reports for them (capf_plan_op_kernel) and their operator shape; the group
+        # with the largest summed time is "the dominant kernel".  Its bound follows from its arithmetic intensity
+        # against the measured ridge (bf16 peak / HBM peak); `achieved` = algorithmic bytes (or FLOPs) of its launches
+        # / their summed duration.
         with torch.no_grad():
             op_ms = plan.time_ops(passes=2)
-        fam = {}
-        for op, ms in zip(plan.prog.ops, op_ms):
-            if op.kind == capf_b200.lib.OP_CONV2D:
-                name = "conv/linear implicit GEMM (tcgen05)" if op.i[12] == capf_b200.lib.IMPL_TCGEN05 else "conv/linear implicit GEMM (SIMT fp32-accumulate)"
-            else:
-                name = {2: "fuse_sum", 5: "layernorm", 6: "attention", 7: "ref_sample", 8: "deform_sample"}.get(op.kind, "other")
+        kern = [plan.op_kernel(k) for k in range(len(plan.prog.ops))]
+        groups, fam = {}, {}
+        for k, (op, ms) in enumerate(zip(plan.prog.ops, op_ms)):
+            shape = "x".join(str(v) for v in op.i[:11]) if op.kind == capf_b200.lib.OP_CONV2D else "x".join(str(v) for v in op.i[:6])
+            g = groups.setdefault((kern[k], shape), {"ms": 0.0, "flops": 0, "bytes": 0, "launches": 0, "tag": op.tag})
+            g["ms"] += ms; g["flops"] += op.flops; g["bytes"] += op.nbytes; g["launches"] += 1
+            name = kern[k].split("[")[0].split("<")[0]
             d = fam.setdefault(name, {"ms": 0.0, "flops": 0, "launches": 0})
-            d["ms"] += ms
-            d["flops"] += op.flops
-            d["launches"] += 1
+            d["ms"] += ms; d["flops"] += op.flops; d["launches"] += 1
         if args.ops_csv:
             os.makedirs(os.path.dirname(os.path.abspath(args.ops_csv)), exist_ok=True)
             with open(args.ops_csv, "w") as f:
-                f.write("idx,kind,impl,tag,shape,ms,gflop,tflops\n")
+                f.write("idx,kind,lane,kernel,tag,shape,ms,gflop,mbytes,tflops,gbps\n")
                 for k, (op, ms) in enumerate(zip(plan.prog.ops, op_ms)):
                     shape = "x".join(str(v) for v in op.i[:11]) if op.kind == capf_b200.lib.OP_CONV2D else "x".join(str(v) for v in op.i[:6])
-                    impl = op.i[12] if op.kind == capf_b200.lib.OP_CONV2D else -1
-                    f.write(f"{k},{op.kind},{impl},{op.tag},{shape},{ms:.5f},{op.flops / 1e9:.4f},{op.flops / max(ms, 1e-9) / 1e9:.2f}\n")
-        dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
-        dom_tflops = dom[1]["flops"] / (dom[1]["ms"] * 1e-3) / 1e12
-        peak_tf = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
-        qkv = [(op, ms) for op, ms in zip(plan.prog.ops, op_ms) if "joint_blocks" in op.tag and op.tag.endswith("attn.qkv")]
-        qkv_tf = sum(o.flops for o, _ in qkv) / (sum(m for _, m in qkv) * 1e-3) / 1e12 if qkv else None
+                    f.write(f"{k},{op.kind},{op.lane},\"{kern[k]}\",{op.tag},{shape},{ms:.5f},{op.flops / 1e9:.4f},{op.nbytes / 1e6:.3f},"
+                            f"{op.flops / max(ms, 1e-9) / 1e9:.2f},{op.nbytes / max(ms, 1e-9) / 1e6:.1f}\n")
         step_ms_sum = sum(op_ms)
+        (dom_kernel, dom_shape), dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
+        peak_tf_sus = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
+        peak_tf = peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"])
+        peak_bw = peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])
+        intensity = dom["flops"] / max(dom["bytes"], 1)
+        ridge = peak_tf_sus * 1e12 / (peak_bw * 1e9)
+        dom_tflops = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+        dom_gbps = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(dom[0])
+                traffic = json.load(f).get(dom_kernel.split("[")[0])
+        conv = [g for (kn, _), g in groups.items() if kn.startswith("tc_") or kn.startswith("stem_tc")]
+        conv_ms, conv_fl = sum(g["ms"] for g in conv), sum(g["flops"] for g in conv)
+        qkv = [(op, ms) for op, ms in zip(plan.prog.ops, op_ms) if "joint_blocks" in op.tag and op.tag.endswith("attn.qkv")]
+        qkv_tf = sum(o.flops for o, _ in qkv) / (sum(m for _, m in qkv) * 1e-3) / 1e12 if qkv else None
+        hbm_bound = intensity < ridge
         roofline = {
-            "bound": "tensor", "kernel": dom[0], "achieved": dom_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": dom_tflops / peak_tf, "traffic": traffic, "peak_source": f"{peaks['_source']} bf16_tflops_sustained",
-            "launches_per_step": dom[1]["launches"], "flops_per_step": dom[1]["flops"],
-            "kernel_ms_per_step": dom[1]["ms"], "share_of_step": dom[1]["ms"] / step_ms_sum,
-            "qkv_gemm": {"achieved": qkv_tf, "peak": peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]), "unit": "TFLOP/s",
-                         "frac": (qkv_tf / peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"])) if qkv_tf else None,
-                         "shape": f"M={B * 17} K=640 N=1920 x4 blocks"},
+            "bound": "hbm" if hbm_bound else "tensor", "kernel": dom_kernel, "op_shape": dom_shape, "example_op": dom["tag"],
+            "achieved": dom_gbps if hbm_bound else dom_tflops, "peak": peak_bw if hbm_bound else peak_tf_sus,
+            "unit": "GB/s" if hbm_bound else "TFLOP/s",
+            "frac": (dom_gbps / peak_bw) if hbm_bound else (dom_tflops / peak_tf_sus),
+            "traffic": traffic,
+            "peak_source": f"{peaks['_source']} " + ("hbm_gbs (copy, read+write bytes)" if hbm_bound else "bf16_tflops_sustained"),
+            "arithmetic_intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
+            "launches_per_step": dom["launches"], "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
+            "flops_per_launch": dom["flops"] / dom["launches"], "avg_launch_us": 1e3 * dom["ms"] / dom["launches"],
+            "kernel_ms_per_step": dom["ms"], "share_of_step": dom["ms"] / step_ms_sum,
+            "also_tflops": dom_tflops, "also_frac_of_tensor_peak": dom_tflops / peak_tf_sus,
+            "tcgen05_kernels": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "peak": peak_tf_sus,
+                                "frac": conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tf_sus, "ms_per_step": conv_ms,
+                                "share_of_step": conv_ms / step_ms_sum},
+            "qkv_gemm": {"achieved": qkv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": (qkv_tf / peak_tf) if qkv_tf else None,
+                         "shape": f"M={B * 17} K=640 N=1920 x4 blocks", "peak_source": f"{peaks['_source']} bf16_tflops (burst)"},
             "whole_step": {"achieved": plan.prog.flops() / (ms_total / args.steps * 1e-3) / 1e12, "unit": "TFLOP/s",
                            "flops_per_frame": plan.prog.flops() / B},
-            "families_ms": {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+            "kernels_ms": {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+            "top_groups": [{"kernel": kn, "shape": sh, "ms": round(g["ms"], 4), "launches": g["launches"],
+                            "tflops": round(g["flops"] / (g["ms"] * 1e-3) / 1e12, 1), "gbps": round(g["bytes"] / (g["ms"] * 1e-3) / 1e9, 1)}
+                           for (kn, sh), g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])[:8]],
         }
         # ---- MPJPE vs reference on a small slice (parity carried with the number) ---------------------------
         cpu_base, parity = None, None
@@ -331,7 +360,7 @@ def run_native(args):
                        "l2": f"inputs larger than L2: {h_img.numel() * 4 / 1e6:.0f} MB of images per step (L2 = 126 MB); activations ~{plan.workspace_bytes / 1e9:.1f} GB",
                        "cuda_graph": not args.no_graph, "precision": args.precision},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "note": "pinned host f32 images -> H2D on a copy stream (double-buffered) -> CA_PF.forward -> D2H of [B,1,17,3]"},
+                    "ms_per_step": ms_e2e / args.steps, "note": "per step: pinned host f32 images/keypoints -> H2D on a copy stream (double-buffered, one step ahead) -> CA_PF.forward -> async D2H of [B,1,17,3] into pinned memory; one synchronise at the end of the timed region"},
             "gpu_launches": args.steps * (plan.num_launches + 1),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity,
         }

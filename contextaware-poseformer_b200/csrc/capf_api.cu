@@ -149,6 +149,30 @@ int capf_plan_run(const capf_plan* plan, int first, int count, void* stream) {
 
 int capf_plan_num_launches(const capf_plan* plan) { return plan ? (int)plan->ops.size() : 0; }
 
+int capf_plan_op_kernel(const capf_plan* plan, int k, char* buf, int cap) {
+  if (!plan || !buf || cap <= 0 || k < 0 || k >= (int)plan->ops.size()) return set_error(CAPF_ERR_ARG, "capf_plan_op_kernel: bad arguments");
+  const capf_op& op = plan->ops[k];
+  switch (op.kind) {
+    case CAPF_OP_CONV2D:
+      if (op.i[12] == CAPF_IMPL_TCGEN05) tc_conv_describe(plan->tc[k], buf, cap);
+      else snprintf(buf, cap, "%s", stem_tc_supported(op) ? "stem_tc_kernel" : "conv_nhwc_simt");
+      break;
+    case CAPF_OP_FUSE_SUM: snprintf(buf, cap, "fuse_sum_kernel"); break;
+    case CAPF_OP_MAXPOOL3X3S2: snprintf(buf, cap, "maxpool3x3s2_kernel"); break;
+    case CAPF_OP_BILINEAR: snprintf(buf, cap, "bilinear_ac_kernel"); break;
+    case CAPF_OP_LAYERNORM: snprintf(buf, cap, op.i[3] > 0 ? "layernorm_proj_kernel" : "layernorm_kernel"); break;
+    case CAPF_OP_ATTENTION: snprintf(buf, cap, "attention_kernel[seq %d]", op.i[1]); break;
+    case CAPF_OP_REF_SAMPLE: snprintf(buf, cap, "ref_sample_kernel"); break;
+    case CAPF_OP_DEFORM_SAMPLE: snprintf(buf, cap, "deform_sample_kernel"); break;
+    case CAPF_OP_EMBED_COORD: snprintf(buf, cap, "embed_coord_kernel"); break;
+    case CAPF_OP_LEVELS_TO_JOINT: snprintf(buf, cap, "levels_to_joint_kernel"); break;
+    case CAPF_OP_CROP_NORMALIZE: snprintf(buf, cap, "crop_normalize_kernel"); break;
+    case CAPF_OP_CAST: snprintf(buf, cap, "cast_kernel"); break;
+    default: snprintf(buf, cap, "?");
+  }
+  return CAPF_OK;
+}
+
 int capf_plan_destroy(capf_plan* plan) {
   if (!plan) return CAPF_OK;
   for (TcConvState* s : plan->tc)

@@ -35,5 +35,6 @@ int tc_conv_supported(const capf_op& op);             // 1 if the tcgen05 kernel
 int tc_conv_prepare(const capf_op& op, TcConvState** out);
 int tc_conv_launch(const capf_op& op, const TcConvState* s, cudaStream_t st);
 void tc_conv_release(TcConvState* s);
+void tc_conv_describe(const TcConvState* s, char* buf, int cap);   // kernel name + tile shape
 
 }  // namespace capf

@@ -12,6 +12,7 @@
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator,
 // warps 4..11 = epilogue (tcgen05.ld -> bias/GELU/residual/ReLU -> global).  Two TMEM accumulator stages let the
 // epilogue of tile i overlap the MMAs of tile i+1; a ring of smem stages decouples TMA from the tensor pipe.
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 
@@ -688,6 +689,12 @@ int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
     case CAPF_BF16: return tc_launch_typed<__nv_bfloat16>(s, st);
     default: return set_error(CAPF_ERR_UNSUPPORTED, "tc conv: dtype_out");
   }
+}
+
+void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
+  if (!s) { snprintf(buf, cap, "?"); return; }
+  if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
+  snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages]", 128 * s->p.msub, s->p.BN, s->p.num_stages);
 }
 
 void tc_conv_release(TcConvState* s) {

@@ -318,6 +318,7 @@ int tc_halo_supported(const capf_op& op);
 int tc_halo_prepare(const capf_op& op, TcHaloState** out);
 int tc_halo_launch(const TcHaloState* s, cudaStream_t st);
 void tc_halo_release(TcHaloState* s);
+void tc_halo_describe(const TcHaloState* s, char* buf, int cap);
 
 // Same for a 16-bit output row staged in shared memory: the residual (if any) is read from, and the result written
 // back to, the two 16-byte chunks at smem addresses s0 / s1.

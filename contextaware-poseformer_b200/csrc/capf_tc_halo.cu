@@ -15,6 +15,7 @@
 // Roles (512 threads): warp 0 = TMA producer (weights once, then the halo of each band; out-of-image elements are
 // zero-filled by TMA), warps 1 and 3 = tcgen05.mma issuers, warp 2 = TMEM allocator, warps 4..15 = three 4-warp
 // epilogue groups taking 128-row sub-tiles round-robin.  Halo bands are double buffered; four TMEM accumulators.
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 
@@ -530,5 +531,9 @@ int tc_halo_launch(const TcHaloState* s, cudaStream_t st) {
 }
 
 void tc_halo_release(TcHaloState* s) { delete s; }
+
+void tc_halo_describe(const TcHaloState* s, char* buf, int cap) {
+  snprintf(buf, cap, "tc_conv3_halo_kernel<C=%d,Cout=%d>[band %d rows]", s->p.C, s->p.Cout, s->p.bh);
+}
 
 }  // namespace capf

@@ -76,6 +76,7 @@ class Op:
     outs: list
     tag: str = ""
     flops: int = 0
+    nbytes: int = 0        # algorithmic bytes of one launch: inputs + outputs (+ residual, weights), each counted once
     lane: int = 0          # execution lane (stream): HRNet branch chains run side by side, see assign_lanes()
 
 
@@ -201,6 +202,7 @@ class ProgramBuilder:
                    [B, x.H, x.W, x.C, cout, k, k, stride, pad, Ho, Wo, acode, impl], [],
                    [src, w, b, residual.ref if residual is not None else None], [out],
                    tag=self.prefix + cname, flops=2 * B * Ho * Wo * cout * K)
+        self.p.ops[-1].nbytes = src.nbytes + out.nbytes + (out.nbytes if residual is not None else 0) + K * cout * _ITEMSIZE[wdt] + 4 * cout
         return arch.T(Ho, Wo, cout, out)
 
     def fuse(self, terms, relu=True):
@@ -250,6 +252,8 @@ class ProgramBuilder:
         acode = {arch.NONE: lib.ACT_NONE, arch.RELU: lib.ACT_RELU, arch.GELU: lib.ACT_GELU}[act]
         self._emit(lib.OP_CONV2D, dt_in, dt_out, [rows, 1, 1, cin, cout, 1, 1, 1, 0, 1, 1, acode, impl], [],
                    [x, w, b, residual], [out], tag=tag, flops=2 * rows * cin * cout)
+        self.p.ops[-1].nbytes = rows * cin * _ITEMSIZE[dt_in] + rows * cout * _ITEMSIZE[dt_out] * (2 if residual is not None else 1) + \
+            cin * cout * _ITEMSIZE[wdt] + 4 * cout
         return out
 
     def layernorm(self, x: Buf, rows, D, prefix, eps, out_dtype, x0: Buf = None, period=0, tag=""):
@@ -672,6 +676,13 @@ class Plan:
                 self._events[k0 + n - 1].record(ls)
         for k in self._tails:                                   # join: the caller's stream owns the result again
             st.wait_event(self._events[k])
+
+    def op_kernel(self, k: int) -> str:
+        """Name (and tile shape) of the kernel op k launches, as reported by the library."""
+        import ctypes as C
+        buf = C.create_string_buffer(160)
+        lib.check(self._L.capf_plan_op_kernel(self._h, k, buf, 160), "capf_plan_op_kernel")
+        return buf.value.decode()
 
     @property
     def num_launches(self):

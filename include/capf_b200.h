@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 3
+#define CAPF_ABI_VERSION 4
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -166,6 +166,9 @@ int capf_plan_create(const capf_op* ops, int n_ops, int device, capf_plan** out_
 /* Enqueue ops [first, first+count) on `stream`; count < 0 means "to the end". */
 int capf_plan_run(const capf_plan* plan, int first, int count, void* stream);
 int capf_plan_num_launches(const capf_plan* plan);   /* kernels one full run enqueues */
+/* Name of the kernel (and, for the tcgen05 kernels, the tile shape) op `k` of the plan launches, written to `buf`
+ * (NUL-terminated, at most `cap` bytes).  Used by bench.py / tools to attribute device time to kernels. */
+int capf_plan_op_kernel(const capf_plan* plan, int k, char* buf, int cap);
 int capf_plan_destroy(capf_plan* plan);
 /* One-off execution of a single op (builds a throw-away plan): used by the per-operator parity tests. */
 int capf_op_run(const capf_op* op, int device, void* stream);
