@@ -1,5 +1,7 @@
-// HRNet stem conv1 on the tensor pipe: 3x3 / stride 2 / pad 1, 3 -> 64 channels, straight from the caller's fp32 NHWC
-// image, folded BatchNorm + ReLU, 16-bit NHWC output (pose_hrnet.py:321-322, :465-467).
+// Backbone stem conv1 on the tensor pipe, straight from the caller's fp32 NHWC image, folded BatchNorm + ReLU, 16-bit NHWC
+// output: 3x3 / stride 2 / pad 1, 3 -> 64 channels for HRNet (pose_hrnet.py:321-322, :465-467) and 7x7 / stride 2 / pad 3
+// for the ResNet-50 of CPN (networks/resnet.py:100-104, :137-139).  The text below describes the 3x3 case; the 7x7 case
+// differs in K = 147 -> 160 and single (un-split) 16-bit operands, see StemGeo.
 //
 // The op is bound by its output (2.6x the input bytes); the CUDA-core version (capf_simt.cu) needs 1728 FMAs and 432
 // shared-memory weight loads per output pixel and ran at ~1/6 of the HBM roofline.  Here a tile is 128 consecutive
@@ -20,23 +22,38 @@
 namespace capf {
 
 constexpr int STEM_THREADS = 288;              // warps 0-3 builders, warp 4 MMA issuer / TMEM owner, warps 5-8 epilogue
-constexpr int STEM_ROW_FLOATS = 776;           // 4 pad + 257 pixels * 3 channels, rounded up to 16-byte chunks
-constexpr int STEM_ROW_CHUNKS = STEM_ROW_FLOATS / 4;
-constexpr int STEM_PATCH_BYTES = 3 * STEM_ROW_FLOATS * 4;
 constexpr int STEM_RING = 4;
-constexpr int STEM_A_PART = 4 * 128 * 16;      // one K block (32 values) of a 128-row A tile: 4 planes x 128 rows x 16 B
-constexpr int STEM_B_PART = 4 * 64 * 16;       // one K block of the weights: 4 planes x 64 rows x 16 B
-constexpr int STEM_OFF_B = 1024;
-constexpr int STEM_OFF_A = STEM_OFF_B + 2 * STEM_B_PART;
-constexpr int STEM_OFF_PATCH = STEM_OFF_A + 2 * 2 * STEM_A_PART;
-constexpr int STEM_OFF_STG = STEM_OFF_PATCH + STEM_RING * STEM_PATCH_BYTES;
-constexpr int STEM_SMEM = STEM_OFF_STG + 4 * 4096 + 1024;
+
+// Compile-time geometry of one stem variant: KS x KS taps, stride 2, pad KS / 2, 3 input channels, 64 output channels.
+//   KS = 3 (HRNet conv1, pose_hrnet.py:321):   K = 27 -> 32,  hi/lo split operands (fp32-class accuracy), 2 CTAs per SM
+//   KS = 7 (CPN ResNet conv1, resnet.py:100):  K = 147 -> 160, single 16-bit operands, 1 CTA per SM
+template <int KS, bool SPLIT>
+struct StemGeo {
+  static constexpr int PAD = KS / 2;
+  static constexpr int TAPW = 3 * KS;                         // floats of one filter row of one pixel (contiguous)
+  static constexpr int K = KS * TAPW;
+  static constexpr int KPAD = (K + 15) / 16 * 16;
+  static constexpr int NP = KPAD / 8;                         // 8-value K planes
+  static constexpr int LEAD = (4 - (3 * PAD) % 4) % 4;        // floats in front of the first tap (16-byte aligned row start)
+  static constexpr int ROW_FLOATS = (LEAD + 3 * (254 + KS) + 3) / 4 * 4;
+  static constexpr int ROW_CHUNKS = ROW_FLOATS / 4;
+  static constexpr int PATCH_BYTES = KS * ROW_FLOATS * 4;
+  static constexpr int PARTS = SPLIT ? 2 : 1;
+  static constexpr int A_PART = NP * 128 * 16;                // one operand part of a 128-row A tile
+  static constexpr int B_PART = NP * 64 * 16;
+  static constexpr int OFF_B = 1024;
+  static constexpr int OFF_A = OFF_B + PARTS * B_PART;
+  static constexpr int OFF_PATCH = OFF_A + 2 * PARTS * A_PART;
+  static constexpr int OFF_STG = OFF_PATCH + STEM_RING * PATCH_BYTES;
+  static constexpr int SMEM = OFF_STG + 4 * 4096 + 1024;
+  static constexpr int CTAS_PER_SM = SMEM <= 110 * 1024 ? 2 : 1;
+};
 
 struct StemP {
   int N, H, W, Ho, Wo, tiles_x, num_tiles, relu;
   uint32_t idesc, a_desc_hi, b_desc_hi;
   const float* x;
-  const float* w;      // [27][64] fp32, k = (r*3+s)*3+c (folded BN scale applied)
+  const float* w;      // [KS*KS*3][64] fp32, k = (r*KS+s)*3+c (folded BN scale applied)
   const float* bias;   // [64] or NULL
   void* y;
 };
@@ -62,13 +79,14 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <typename TO>
-__global__ void __launch_bounds__(STEM_THREADS, 2) stem_tc_kernel(const StemP p) {
+template <typename TO, int KS, bool SPLIT>
+__global__ void __launch_bounds__(STEM_THREADS, (StemGeo<KS, SPLIT>::CTAS_PER_SM)) stem_tc_kernel(const StemP p) {
+  using G = StemGeo<KS, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t bar_afull = base, bar_aempty = base + 16, bar_tfull = base + 32, bar_tempty = base + 48, tmem_slot = base + 64;
-  const uint32_t smem_b = base + STEM_OFF_B, smem_a = base + STEM_OFF_A, smem_patch = base + STEM_OFF_PATCH, smem_stg = base + STEM_OFF_STG;
+  const uint32_t smem_b = base + G::OFF_B, smem_a = base + G::OFF_A, smem_patch = base + G::OFF_PATCH, smem_stg = base + G::OFF_STG;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
 
@@ -85,15 +103,15 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) stem_tc_kernel(const StemP p)
     ptx::tmem_alloc(tmem_slot, 128u);
     ptx::tmem_relinquish();
   }
-  // weights: fp32 [27][64] -> hi / lo 16-bit parts in the K-major core-matrix layout (plane = 8 K values: [64 rows][16 B])
-  for (int idx = tid; idx < 64 * 32; idx += STEM_THREADS) {
-    const int n = idx >> 5, k = idx & 31;
-    const float v = k < 27 ? __ldg(p.w + k * 64 + n) : 0.f;
+  // weights: fp32 [K][64] -> 16-bit (hi / lo parts when SPLIT) in the K-major core-matrix layout (plane = 8 K values:
+  // [64 rows][16 B])
+  for (int idx = tid; idx < 64 * G::KPAD; idx += STEM_THREADS) {
+    const int n = idx / G::KPAD, k = idx - n * G::KPAD;
+    const float v = k < G::K ? __ldg(p.w + k * 64 + n) : 0.f;
     const TO hi = from_f<TO>(v);
-    const TO lo = from_f<TO>(v - to_f<TO>(hi));
     const uint32_t off = (uint32_t)((k >> 3) * 1024 + n * 16 + (k & 7) * 2);
     *reinterpret_cast<TO*>(smem_raw + (smem_b - raw) + off) = hi;
-    *reinterpret_cast<TO*>(smem_raw + (smem_b - raw) + STEM_B_PART + off) = lo;
+    if (SPLIT) *reinterpret_cast<TO*>(smem_raw + (smem_b - raw) + G::B_PART + off) = from_f<TO>(v - to_f<TO>(hi));
   }
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
@@ -112,15 +130,15 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) stem_tc_kernel(const StemP p)
       if (tile < t1) {
         const int txi = tile % p.tiles_x, rowid = tile / p.tiles_x;
         const int oy = rowid % p.Ho, n = rowid / p.Ho;
-        const int col_base = 6 * (txi * 128) - 4;
+        const int col_base = 6 * (txi * 128) - 3 * G::PAD - G::LEAD;
         const float* img = p.x + (size_t)n * p.H * p.W * 3;
-        const uint32_t dst0 = smem_patch + (uint32_t)slot * STEM_PATCH_BYTES;
-        for (int q = tid; q < 3 * STEM_ROW_CHUNKS; q += 128) {
-          const int r = q / STEM_ROW_CHUNKS, j = q - r * STEM_ROW_CHUNKS;
-          const int iy = 2 * oy - 1 + r, col0 = col_base + 4 * j;
+        const uint32_t dst0 = smem_patch + (uint32_t)slot * G::PATCH_BYTES;
+        for (int q = tid; q < KS * G::ROW_CHUNKS; q += 128) {
+          const int r = q / G::ROW_CHUNKS, j = q - r * G::ROW_CHUNKS;
+          const int iy = 2 * oy - G::PAD + r, col0 = col_base + 4 * j;
           const bool ok = iy >= 0 && iy < p.H && col0 >= 0 && col0 + 4 <= 3 * p.W;
           const float* src = ok ? img + (size_t)iy * p.W * 3 + col0 : p.x;
-          cp_async16_zfill(dst0 + (uint32_t)(r * STEM_ROW_FLOATS + 4 * j) * 4u, src, ok ? 16u : 0u);
+          cp_async16_zfill(dst0 + (uint32_t)(r * G::ROW_FLOATS + 4 * j) * 4u, src, ok ? 16u : 0u);
         }
       }
       ptx::cp_async_commit();
@@ -132,28 +150,27 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) stem_tc_kernel(const StemP p)
       named_bar_sync(1, 128);                          // ... for every builder thread; everyone is also done with tile - 1
       issue_loads(tile + STEM_RING - 1, (int)((it + STEM_RING - 1) & (STEM_RING - 1)));
       const uint32_t buf = it & 1u, aph = (it >> 1) & 1u;
-      const uint32_t patch = smem_patch + (it & (STEM_RING - 1)) * STEM_PATCH_BYTES;
-      float in[32];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int j = 0; j < 9; ++j) in[r * 9 + j] = ld_shared_f32(patch + (uint32_t)(r * STEM_ROW_FLOATS + 6 * tid + 1 + j) * 4u);
-#pragma unroll
-      for (int k = 27; k < 32; ++k) in[k] = 0.f;
+      const uint32_t patch = smem_patch + (it & (STEM_RING - 1)) * G::PATCH_BYTES + (uint32_t)(6 * tid + G::LEAD) * 4u;
       ptx::mbar_wait(bar_aempty + 8 * buf, aph ^ 1u);  // the MMAs that read this A buffer two tiles ago have completed
-      const uint32_t a_hi = smem_a + buf * (2 * STEM_A_PART) + (uint32_t)tid * 16u, a_lo = a_hi + STEM_A_PART;
+      const uint32_t a_hi = smem_a + buf * (G::PARTS * G::A_PART) + (uint32_t)tid * 16u, a_lo = a_hi + G::A_PART;
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
+      for (int kc = 0; kc < G::NP; ++kc) {
+        // the 8 im2col values of K plane kc of this pixel: k = (filter row r) * TAPW + j, contiguous in j inside a row
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = kc * 8 + e;
+          x[e] = k < G::K ? ld_shared_f32(patch + (uint32_t)((k / G::TAPW) * G::ROW_FLOATS + (k % G::TAPW)) * 4u) : 0.f;
+        }
         uint32_t h[4], l[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float x0 = in[kc * 8 + 2 * e], x1 = in[kc * 8 + 2 * e + 1];
-          const float h0 = to_f<TO>(from_f<TO>(x0)), h1 = to_f<TO>(from_f<TO>(x1));
+          const float h0 = to_f<TO>(from_f<TO>(x[2 * e])), h1 = to_f<TO>(from_f<TO>(x[2 * e + 1]));
           h[e] = pack2<TO>(h0, h1);
-          l[e] = pack2<TO>(x0 - h0, x1 - h1);
+          l[e] = pack2<TO>(x[2 * e] - h0, x[2 * e + 1] - h1);
         }
         ptx::st_shared_v4(a_hi + kc * 2048, make_uint4(h[0], h[1], h[2], h[3]));
-        ptx::st_shared_v4(a_lo + kc * 2048, make_uint4(l[0], l[1], l[2], l[3]));
+        if (SPLIT) ptx::st_shared_v4(a_lo + kc * 2048, make_uint4(l[0], l[1], l[2], l[3]));
       }
       ptx::fence_proxy_async();                        // generic-proxy writes -> visible to the tensor pipe's reads
       ptx::mbar_arrive(bar_afull + 8 * buf);
@@ -169,13 +186,14 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) stem_tc_kernel(const StemP p)
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t d_tmem = tmem_base + buf * 64u;
-        const uint32_t a0 = smem_a + buf * (2 * STEM_A_PART);
-        // (A part, B part): hi*hi, lo*hi, hi*lo
-        const uint32_t a_part[3] = {0u, (uint32_t)STEM_A_PART, 0u}, b_part[3] = {0u, 0u, (uint32_t)STEM_B_PART};
+        const uint32_t a0 = smem_a + buf * (G::PARTS * G::A_PART);
+        // (A part, B part): hi*hi, lo*hi, hi*lo when the operands are split, else the single product
+        constexpr int NC = SPLIT ? 3 : 1;
+        const uint32_t a_part[3] = {0u, (uint32_t)G::A_PART, 0u}, b_part[3] = {0u, 0u, (uint32_t)G::B_PART};
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < NC; ++c) {
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
+          for (int kk = 0; kk < G::KPAD / 16; ++kk) {
             const uint32_t a_lo = tc_desc_lo(a0 + a_part[c] + (uint32_t)kk * 4096u, 128u);     // LBO: 2048 B between K planes
             const uint32_t b_lo = tc_desc_lo(smem_b + b_part[c] + (uint32_t)kk * 2048u, 64u);   // LBO: 1024 B
             ptx::umma_f16_lohi(d_tmem, a_lo, p.a_desc_hi, b_lo, p.b_desc_hi, p.idesc, (c | kk) ? 1u : 0u);
@@ -234,7 +252,8 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) stem_tc_kernel(const StemP p)
 int stem_tc_supported(const capf_op& op) {
   const char* ev = getenv("CAPF_STEM_TC");
   if (ev && ev[0] == '0') return 0;
-  if (op.i[3] != 3 || op.i[4] != 64 || op.i[5] != 3 || op.i[6] != 3 || op.i[7] != 2 || op.i[8] != 1) return 0;
+  const int ks = op.i[5];
+  if (op.i[3] != 3 || op.i[4] != 64 || (ks != 3 && ks != 7) || op.i[6] != ks || op.i[7] != 2 || op.i[8] != ks / 2) return 0;
   if (op.dtype_in != CAPF_F32 || (op.dtype_out != CAPF_F16 && op.dtype_out != CAPF_BF16)) return 0;
   if (op.in[3] || op.i[11] == CAPF_ACT_GELU) return 0;
   if (op.i[2] % 4 || op.i[2] < 4) return 0;                                   // 16-byte chunks never straddle the row end
@@ -243,15 +262,18 @@ int stem_tc_supported(const capf_op& op) {
   return 1;
 }
 
-template <typename TO>
-static int stem_launch_typed(const StemP& p, int grid, cudaStream_t st) {
+template <typename TO, int KS, bool SPLIT>
+static int stem_launch_typed(const StemP& p, cudaStream_t st) {
+  using G = StemGeo<KS, SPLIT>;
   static bool opted = false;
   if (!opted) {
-    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<TO, KS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "stem_tc_kernel smem opt-in: %s", cudaGetErrorString(e));
     opted = true;
   }
-  launch_k(stem_tc_kernel<TO>, dim3(grid), dim3(STEM_THREADS), STEM_SMEM, st, p);
+  int grid = G::CTAS_PER_SM * g_num_sms;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  launch_k(stem_tc_kernel<TO, KS, SPLIT>, dim3(grid), dim3(STEM_THREADS), G::SMEM, st, p);
   return check_launch("stem_tc_kernel");
 }
 
@@ -268,10 +290,9 @@ int launch_stem_tc(const capf_op& op, cudaStream_t st) {
   p.w = (const float*)op.in[1];
   p.bias = (const float*)op.in[2];
   p.y = op.out[0];
-  int grid = 2 * g_num_sms;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  if (op.dtype_out == CAPF_F16) return stem_launch_typed<__half>(p, grid, st);
-  return stem_launch_typed<__nv_bfloat16>(p, grid, st);
+  const bool f16 = op.dtype_out == CAPF_F16;
+  if (op.i[5] == 3) return f16 ? stem_launch_typed<__half, 3, true>(p, st) : stem_launch_typed<__nv_bfloat16, 3, true>(p, st);
+  return f16 ? stem_launch_typed<__half, 7, false>(p, st) : stem_launch_typed<__nv_bfloat16, 7, false>(p, st);
 }
 
 }  // namespace capf

@@ -704,6 +704,24 @@ class Plan:
             ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(n)]
         return ms
 
+    def time_op_repeated(self, k: int, reps: int = 20):
+        """Average device time (ms) of `reps` back-to-back launches of op k (must be idempotent: no in-place residual)
+        between two CUDA events on the launching stream -- the kernel's steady duration without the per-op event and
+        host launch gaps that time_ops() includes.  Operands stay in their in-step cache state (L2-resident)."""
+        op = self.prog.ops[k]
+        if any(isinstance(b, Buf) and any(b.root is o.root for o in op.outs if isinstance(o, Buf)) for b in op.ins):
+            raise ValueError("time_op_repeated: op updates its input in place")
+        st = torch.cuda.current_stream(self.device)
+        for _ in range(3):
+            lib.check(self._L.capf_plan_run(self._h, k, 1, st.cuda_stream), "capf_plan_run")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            lib.check(self._L.capf_plan_run(self._h, k, 1, st.cuda_stream), "capf_plan_run")
+        e1.record(st)
+        st.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     # ---- CUDA graph ---------------------------------------------------------------------------------
     def capture(self):
         """Capture one full run into a CUDA graph (replayed by run_graph)."""

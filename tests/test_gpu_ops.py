@@ -61,22 +61,26 @@ def test_conv2d_simt(shape, dt, act, use_res):
 
 @pytest.mark.parametrize("shape", [(2, 17, 13), (3, 64, 48), (1, 256, 256), (2, 384, 288), (5, 40, 260), (300, 8, 8)], ids=str)
 @pytest.mark.parametrize("odt", [torch.float16, torch.bfloat16])
-def test_stem_conv_f32_image_to_16bit(shape, odt):
-    """HRNet conv1 (pose_hrnet.py:321-322): fp32 NHWC image in, folded-BN 3x3/s2 3->64 + ReLU, 16-bit out: the tensor-pipe
-    stem of capf_stem.cu (W % 4 == 0; one or several 128-pixel tiles per output row, ragged last tile, more tiles than
-    CTAs) and the CUDA-core stem of capf_simt.cu (odd widths)."""
+@pytest.mark.parametrize("ks", [3, 7], ids=["hrnet3x3", "cpn7x7"])
+def test_stem_conv_f32_image_to_16bit(shape, odt, ks):
+    """Backbone conv1 (HRNet pose_hrnet.py:321-322: 3x3/s2; CPN resnet.py:100: 7x7/s2): fp32 NHWC image in, folded-BN
+    3 -> 64 + ReLU, 16-bit out: the tensor-pipe stem of capf_stem.cu (W % 4 == 0; one or several 128-pixel tiles per
+    output row, ragged last tile, more tiles than CTAs) and the CUDA-core kernels of capf_simt.cu (odd widths)."""
     N, H, W = shape
     g = _gen(11)
+    pad = ks // 2
     x = torch.randn(N, H, W, 3, generator=g)
-    w = torch.randn(64, 3, 3, 3, generator=g) / 27 ** 0.5
+    w = torch.randn(64, 3, ks, ks, generator=g) / (3 * ks * ks) ** 0.5
     bias = torch.randn(64, generator=g)
-    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
-    y = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, bias, 2, 1)).permute(0, 2, 3, 1)
+    Ho, Wo = (H + 2 * pad - ks) // 2 + 1, (W + 2 * pad - ks) // 2 + 1
+    y = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, bias, 2, pad)).permute(0, 2, 3, 1)
     wp = w.permute(2, 3, 1, 0).reshape(-1, 64).contiguous().to(DEV)
     out = torch.full((N, Ho, Wo, 64), float("nan"), dtype=odt, device=DEV)
-    run_op(lib.OP_CONV2D, torch.float32, odt, [N, H, W, 3, 64, 3, 3, 2, 1, Ho, Wo, lib.ACT_RELU, lib.IMPL_SIMT], [],
+    run_op(lib.OP_CONV2D, torch.float32, odt, [N, H, W, 3, 64, ks, ks, 2, pad, Ho, Wo, lib.ACT_RELU, lib.IMPL_SIMT], [],
            [x.to(DEV), wp, bias.to(DEV), None], [out])
-    assert rel_l2(out.float().cpu(), y) < (6e-4 if odt == torch.float16 else 4e-3)
+    # 3x3: hi/lo split operands -> only the output rounding remains; 7x7: single 16-bit operands (input/weight rounding)
+    tol = (6e-4 if odt == torch.float16 else 4e-3) if ks == 3 else (9e-4 if odt == torch.float16 else 6e-3)
+    assert rel_l2(out.float().cpu(), y) < tol
 
 
 def test_conv2d_rejects_bad_arguments():
@@ -113,6 +117,19 @@ def test_maxpool_and_bilinear():
         run_op(lib.OP_BILINEAR, torch.float32, torch.float32, [2, 13, 10, 64, Ho, Wo], [], [x.to(DEV)], [out])
         want = F.interpolate(x.permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
         assert (out.cpu() - want).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_bilinear_16bit_vector_path(dt):
+    """nn.Upsample(bilinear, align_corners=True) of the CPN heads (globalNet.py:40, refineNet.py:61) on 16-bit NHWC
+    tensors: 8-channel (16-byte) vector kernel vs fp32 F.interpolate on the same rounded input; up- and down-sampling."""
+    g = _gen(13)
+    x = torch.randn(3, 16, 12, 256, generator=g).to(dt)
+    for (Ho, Wo) in ((32, 24), (64, 48), (8, 6), (16, 12), (1, 1)):
+        out = torch.full((3, Ho, Wo, 256), float("nan"), dtype=dt, device=DEV)
+        run_op(lib.OP_BILINEAR, dt, dt, [3, 16, 12, 256, Ho, Wo], [], [x.to(DEV)], [out])
+        want = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        assert rel_l2(out.float().cpu(), want) < (5e-4 if dt == torch.float16 else 4e-3)
 
 
 @pytest.mark.parametrize("D,period", [(128, 0), (640, 0), (128, 34)])
