@@ -417,6 +417,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // =======================================================================================================
 struct TcConvState {
   TcHaloState* halo = nullptr;   // non-null: the op runs on the halo-band kernel instead of tc_gemm_kernel
+  Tc2State* two = nullptr;       // non-null: the op runs on the 2-CTA GEMM kernel (capf_tc2.cu)
   CUtensorMap mapA, mapB;
   TcP p;
   int grid;
@@ -504,6 +505,12 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   const ConvGeo g = geo_of(op);
   TcConvState* s = new (std::nothrow) TcConvState();
   if (!s) return set_error(CAPF_ERR_ARG, "tc_conv_prepare: out of host memory");
+  if (op.i[13] == 0 && tc2_supported(op)) {     // wide Linears over many rows: CTA pairs (cta_group::2)
+    e = tc2_prepare(op, &s->two);
+    if (e) { delete s; return e; }
+    *out = s;
+    return CAPF_OK;
+  }
   // i[13]: kernel variant hint (0 = automatic, 1 = per-tap TMA GEMM, 2 = halo band); tests use it for A/B parity
   if (op.i[13] != 1 && tc_halo_supported(op)) {
     e = tc_halo_prepare(op, &s->halo);
@@ -682,6 +689,7 @@ static int tc_launch_typed(const TcConvState* s, cudaStream_t st) {
 
 int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
   if (!s) return set_error(CAPF_ERR_ARG, "tc conv: op was not prepared");
+  if (s->two) return tc2_launch(s->two, st);
   if (s->halo) return tc_halo_launch(s->halo, st);
   switch (s->dtype_out) {
     case CAPF_F32: return tc_launch_typed<float>(s, st);
@@ -693,11 +701,13 @@ int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
 
 void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
   if (!s) { snprintf(buf, cap, "?"); return; }
+  if (s->two) { tc2_describe(s->two, buf, cap); return; }
   if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
   snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages]", 128 * s->p.msub, s->p.BN, s->p.num_stages);
 }
 
 void tc_conv_release(TcConvState* s) {
+  if (s && s->two) tc2_release(s->two);
   if (s && s->halo) tc_halo_release(s->halo);
   delete s;
 }

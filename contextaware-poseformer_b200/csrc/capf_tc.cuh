@@ -469,6 +469,14 @@ __device__ __forceinline__ void epi16(const uint32_t (&raw)[16], const float* __
   }
 }
 
+// 2-CTA (cta_group::2) GEMM for the wide lifter Linears (capf_tc2.cu)
+struct Tc2State;
+int tc2_supported(const capf_op& op);
+int tc2_prepare(const capf_op& op, Tc2State** out);
+int tc2_launch(const Tc2State* s, cudaStream_t st);
+void tc2_release(Tc2State* s);
+void tc2_describe(const Tc2State* s, char* buf, int cap);
+
 // host helpers (capf_tc.cu)
 int tc_get_encoder();
 int tc_encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,

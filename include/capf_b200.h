@@ -75,6 +75,8 @@ typedef enum capf_op_kind {
  *     i[14] = per-tap kernel epilogue hint: 0 automatic, 1 per-row vectors, 2 coalesced staging tile
  *     i[15] = per-tap kernel tile height hint: 0 automatic, 1 = 128 rows, 2 = 256 rows (two accumulators per B stage)
  *     i[16] = per-tap kernel column-tile width hint (0 automatic, else a multiple of 16 dividing Cout)
+ *     i[17] = 2-CTA (cta_group::2) GEMM kernel for Linears over rows: 0 automatic (wide Linears with many rows),
+ *             1 never, 2 always when the shape allows (K % 64 == 0, Cout % 16 == 0)
  *     in[0]=x  [N,H,W,Cin]        dtype_in
  *     in[1]=w  SIMT: [KH*KW*Cin][Cout] (tap-major rows, Cout contiguous); TCGEN05: [Cout][KH*KW*Cin];
  *              dtype_in, except x f32 -> w f32.  BatchNorm scale is pre-folded into w by the host.

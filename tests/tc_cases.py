@@ -53,7 +53,7 @@ HALO_CASES = [
 ]
 
 
-def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=0):
+def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=0, two=0):
     """Returns (rel_l2, max_abs, frac_bad_rows) of the tcgen05 kernel against the fp32 reference."""
     name, (N, H, W, Cin, Cout, k, stride), act, use_res, out_f32 = case
     g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % (1 << 31))
@@ -84,7 +84,7 @@ def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=
     else:
         wp = w.permute(2, 3, 1, 0).reshape(-1, Cout).contiguous().to(dt).to(DEV)
     out = torch.full((N, Ho, Wo, Cout), float("nan"), dtype=odt, device=DEV)
-    run_op(lib.OP_CONV2D, dt, odt, [N, H, W, Cin, Cout, k, k, stride, pad, Ho, Wo, act, impl, variant, epi, msub, bn], [],
+    run_op(lib.OP_CONV2D, dt, odt, [N, H, W, Cin, Cout, k, k, stride, pad, Ho, Wo, act, impl, variant, epi, msub, bn, two], [],
            [x.to(dt).to(DEV), wp, bias.to(DEV), res.to(odt).to(DEV) if use_res else None], [out])
     o = out.float()
     diff = (o - y)

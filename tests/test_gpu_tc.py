@@ -30,6 +30,35 @@ def test_tc_gemm_tile_and_epilogue_variants(case, epi, msub):
     assert bad_rows == 0.0 and rel < tol
 
 
+TWO_CTA_CASES = [
+    ("rows2_qkv", (4352, 1, 1, 640, 1920, 1, 1), 0, False, False),
+    ("rows2_fc2_res_f32", (1000, 1, 1, 1280, 640, 1, 1), 0, True, True),
+    ("rows2_fc1_gelu", (1000, 1, 1, 640, 1280, 1, 1), 2, False, False),
+    ("rows2_proj_res_f32_inplace_sized", (4352, 1, 1, 640, 640, 1, 1), 0, True, True),
+    ("rows2_ragged_small", (37, 1, 1, 128, 48, 1, 1), 0, False, True),
+    ("rows2_relu_res_f16", (300, 1, 1, 64, 256, 1, 1), 1, True, False),
+    ("rows2_many_tiles", (40000, 1, 1, 64, 64, 1, 1), 0, False, False),
+]
+
+
+@pytest.mark.parametrize("case", TWO_CTA_CASES, ids=[c[0] for c in TWO_CTA_CASES])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_two_cta_gemm_matches_fp32_reference(case, dt):
+    """The cta_group::2 GEMM (csrc/capf_tc2.cu: a CTA pair per 256 x BN tile, each SM holding half of B) forced on
+    Linear shapes of the lifter and on edge shapes (ragged M, one pair, more tiles than pairs, every epilogue mode)."""
+    rel, max_abs, bad_rows = run_tc_case(case, dt, two=2)
+    print(f"{case[0]} {dt}: rel-L2 {rel:.3e} max-abs {max_abs:.3e} bad-rows {bad_rows:.4f}")
+    tol = 2e-5 if case[4] else (1.5e-3 if dt == torch.float16 else 8e-3)
+    assert bad_rows == 0.0 and rel < tol
+
+
+@pytest.mark.parametrize("bn", [16, 48, 80, 240], ids=lambda v: f"bn{v}")
+def test_two_cta_gemm_column_tiles(bn):
+    case = ("rows2_bn_sweep", (1100, 1, 1, 128, 240, 1, 1), 0, True, False)
+    rel, _, bad = run_tc_case(case, torch.float16, two=2, bn=bn)
+    assert bad == 0.0 and rel < 1.5e-3, (bn, rel)
+
+
 @pytest.mark.parametrize("bn", [16, 48, 80, 240], ids=lambda v: f"bn{v}")
 def test_tc_gemm_column_tiles(bn):
     """Forced column-tile widths (incl. BN = 16, where one epilogue warp of each quadrant has no columns, and the
