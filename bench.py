@@ -165,8 +165,13 @@ def run_native(args):
         raise SystemExit("bench.py needs a B200: libcapf_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL writes its version banner to fd 1 at its first collective, so fd 1
+        # points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     B, H, W = args.batch, args.height, args.width
     model, weights, cfg = build_model(args.backbone, args.precision, dev, graph=not args.no_graph)
@@ -374,8 +379,13 @@ def run_native(args):
             "gpu_launches": args.steps * (plan.num_launches + 1),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity,
         }
-        print(json.dumps(line))
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
+        if rank == 0 and saved_stdout is not None:
+            os.dup2(2, 1)
         dist.barrier()
         dist.destroy_process_group()
 
