@@ -67,6 +67,7 @@ static int dispatch(const capf_op& op, const TcConvState* tc, cudaStream_t st) {
     case CAPF_OP_LEVELS_TO_JOINT: return launch_levels_to_joint(op, st);
     case CAPF_OP_CROP_NORMALIZE: return launch_crop_normalize(op, st);
     case CAPF_OP_CAST: return launch_cast(op, st);
+    case CAPF_OP_PREPROCESS_U8: return launch_preprocess_u8(op, st);
     default: return set_errorf(CAPF_ERR_ARG, "unknown op kind %d", op.kind);
   }
 }
@@ -168,6 +169,7 @@ int capf_plan_op_kernel(const capf_plan* plan, int k, char* buf, int cap) {
     case CAPF_OP_LEVELS_TO_JOINT: snprintf(buf, cap, "levels_to_joint_kernel"); break;
     case CAPF_OP_CROP_NORMALIZE: snprintf(buf, cap, "crop_normalize_kernel"); break;
     case CAPF_OP_CAST: snprintf(buf, cap, "cast_kernel"); break;
+    case CAPF_OP_PREPROCESS_U8: snprintf(buf, cap, "preprocess_u8_kernel"); break;
     default: snprintf(buf, cap, "?");
   }
   return CAPF_OK;

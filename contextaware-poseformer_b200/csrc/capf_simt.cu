@@ -1455,4 +1455,59 @@ int launch_cast(const capf_op& op, cudaStream_t st) {
   return check_launch("cast");
 }
 
+// =======================================================================================================
+// Pre-processing front end: data_prefetcher.preload's image path, mvn/datasets/utils.py:45-50
+//   images = torch.flip(images_u8, [-1])                   BGR -> RGB
+//   images = (images / 255.0 - mean) / std                 HRNet      |   images / 255.0 - mean      CPN
+// and the flip-test copy torch.flip(images, [2]) (:67), fused into one pass: 3 bytes in, 12 bytes out per pixel.
+// Four pixels per thread (12 bytes -> three float4) when W % 4 == 0; IEEE divisions keep it bit-exact with torch.
+// =======================================================================================================
+__device__ __forceinline__ float prep_px(unsigned v, float m, float s, int apply_std) {
+  float t = __fsub_rn(__fdiv_rn((float)v, 255.0f), m);
+  return apply_std ? __fdiv_rn(t, s) : t;
+}
+
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(int H, int W, int mirror, int apply_std, unsigned total_groups, int gpr,
+                                                            const uint8_t* __restrict__ x, const float* __restrict__ ms, float* __restrict__ y) {
+  pdl_wait();
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= total_groups) return;
+  const float mr = __ldg(ms), mg = __ldg(ms + 1), mb = __ldg(ms + 2), sr = __ldg(ms + 3), sg = __ldg(ms + 4), sb = __ldg(ms + 5);
+  const unsigned row = i / (unsigned)gpr, g = i - row * (unsigned)gpr;       // row = b * H + h, g = group of 4 pixels in the row
+  const int w0 = 4 * (int)g;
+  const int n = min(4, W - w0);
+  const uint8_t* src_row = x + (size_t)row * W * 3;
+  float* dst = y + ((size_t)row * W + w0) * 3;
+  float o[12];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < n) {
+      const int ws = mirror ? (W - 1 - (w0 + k)) : (w0 + k);
+      const uint8_t* px = src_row + 3 * ws;
+      o[3 * k] = prep_px(px[2], mr, sr, apply_std);        // R <- byte 2
+      o[3 * k + 1] = prep_px(px[1], mg, sg, apply_std);
+      o[3 * k + 2] = prep_px(px[0], mb, sb, apply_std);    // B <- byte 0
+    }
+  }
+  if (n == 4 && ((W & 3) == 0)) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  } else {
+    for (int k = 0; k < 3 * n; ++k) dst[k] = o[k];
+  }
+}
+
+int launch_preprocess_u8(const capf_op& op, cudaStream_t st) {
+  const int B = op.i[0], H = op.i[1], W = op.i[2];
+  if (B <= 0 || H <= 0 || W <= 0 || !op.in[0] || !op.in[1] || !op.out[0]) return set_error(CAPF_ERR_ARG, "preprocess_u8: bad arguments");
+  if (op.dtype_out != CAPF_F32) return set_error(CAPF_ERR_UNSUPPORTED, "preprocess_u8: output must be f32 (the dtype CA_PF.forward takes)");
+  if (((uintptr_t)op.out[0]) & 15) return set_error(CAPF_ERR_ARG, "preprocess_u8: output must be 16-byte aligned");
+  const int gpr = (W + 3) / 4;
+  const long long groups = (long long)B * H * gpr;
+  if (groups >= (1ll << 32)) return set_error(CAPF_ERR_UNSUPPORTED, "preprocess_u8: too many pixels");
+  launch_k(preprocess_u8_kernel, dim3((unsigned)((groups + 255) / 256)), dim3(256), 0, st, H, W, op.i[3] ? 1 : 0, op.i[4] ? 1 : 0, (unsigned)groups, gpr,
+           (const uint8_t*)op.in[0], (const float*)op.in[1], (float*)op.out[0]);
+  return check_launch("preprocess_u8");
+}
+
 }  // namespace capf

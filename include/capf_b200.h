@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 4
+#define CAPF_ABI_VERSION 5
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -57,7 +57,8 @@ typedef enum capf_op_kind {
   CAPF_OP_EMBED_COORD = 9,
   CAPF_OP_LEVELS_TO_JOINT = 10,
   CAPF_OP_CROP_NORMALIZE = 11,
-  CAPF_OP_CAST = 12
+  CAPF_OP_CAST = 12,
+  CAPF_OP_PREPROCESS_U8 = 13
 } capf_op_kind;
 
 /*
@@ -141,6 +142,12 @@ typedef enum capf_op_kind {
  *     i[0]=n_points   out[0]=crop [n][2] f32
  *
  * CAPF_OP_CAST -- dtype conversion of a dense array.  i[0],i[1]=element count (lo,hi 31-bit words) in[0] out[0]
+ *
+ * CAPF_OP_PREPROCESS_U8 -- the image half of data_prefetcher.preload (mvn/datasets/utils.py:45-50, flip-test copy :67):
+ *                    uint8 BGR HWC crops -> fp32 RGB NHWC, (x / 255 - mean[c]) / std[c] with IEEE divisions (bit-exact
+ *                    with the torch expression), optionally mirrored along W (torch.flip(images, [2])).
+ *     i[0..2]=B,H,W  i[3]=mirror(0|1)  i[4]=apply_std(1: HRNet, 0: CPN `x / 255 - mean`)
+ *     in[0]=uint8 [B,H,W,3] (B,G,R)  in[1]=f32[6] device: mean R,G,B then std R,G,B   out[0]=f32 [B,H,W,3] (R,G,B)
  */
 typedef struct capf_op {
   int32_t kind;

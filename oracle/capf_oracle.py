@@ -296,3 +296,47 @@ def ca_pf_forward(sd, backbone, bb_cfg, images, kp2d, crop, trace=None):
         if trace is not None:
             trace["features"] = feats
         return lifter_forward(sd, kp2d, ref, feats, trace=trace)
+
+
+# ------------------------------------------------------------------------------------------------------
+# f1: pre-processing + flip-test front end (TEST-ONLY restatement; parity UNPINNED: the reference's data_prefetcher
+# needs a CUDA device to run at all (.cuda() calls, mvn/datasets/utils.py:18-29,41), so it cannot be executed in the
+# authoring container; this follows its source line by line)
+# ------------------------------------------------------------------------------------------------------
+JOINTS_LEFT = [4, 5, 6, 11, 12, 13]      # mvn/datasets/utils.py:12
+JOINTS_RIGHT = [1, 2, 3, 14, 15, 16]     # mvn/datasets/utils.py:13
+
+
+def prefetch_images(images_u8: torch.Tensor, backbone: str) -> torch.Tensor:
+    """mvn/datasets/utils.py:45-50 on a uint8 [B,H,W,3] BGR batch -> fp32 RGB normalised."""
+    images = torch.flip(images_u8, [-1])
+    if backbone in ("hrnet_32", "hrnet_48"):
+        mean = torch.tensor([0.485, 0.456, 0.406])
+        std = torch.tensor([0.229, 0.224, 0.225])
+        images = (images / 255.0 - mean) / std
+    else:
+        mean = torch.tensor([122.7717, 115.9465, 102.9801]).view(1, 1, 1, 3)
+        mean /= 255.
+        images = images / 255.0 - mean
+    return images.float()
+
+
+def prefetch_flip_test(images_u8, kp2d, kp2d_crop, backbone):
+    """mvn/datasets/utils.py:66-80: the stacked (plain, mirrored) inputs of the flip test."""
+    images = prefetch_images(images_u8, backbone)
+    images = torch.stack([images, torch.flip(images, [2])], dim=1)
+    k = kp2d.clone()
+    k[..., 0] *= -1
+    k[..., JOINTS_LEFT + JOINTS_RIGHT, :] = k[..., JOINTS_RIGHT + JOINTS_LEFT, :]
+    c = kp2d_crop.clone()
+    c[:, :, 0] = 192 - c[:, :, 0] - 1
+    c[:, JOINTS_LEFT + JOINTS_RIGHT] = c[:, JOINTS_RIGHT + JOINTS_LEFT]
+    return images, torch.stack([kp2d, k], dim=1), torch.stack([kp2d_crop, c], dim=1)
+
+
+def flip_test_merge(pred, pred_flip):
+    """train.py:177-180."""
+    pred_flip = pred_flip.clone()
+    pred_flip[:, :, :, 0] *= -1
+    pred_flip[:, :, JOINTS_LEFT + JOINTS_RIGHT] = pred_flip[:, :, JOINTS_RIGHT + JOINTS_LEFT]
+    return torch.mean(torch.cat((pred, pred_flip), dim=1), dim=1, keepdim=True)
