@@ -585,12 +585,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(int rows, int D, int per
   if (warp >= rows) return;
   const float* xr = x + (size_t)warp * D;
   const float* ar = period > 0 ? x0 + (size_t)(warp % period) * D : nullptr;
-  const int nv = D >> 7;  // float4 per lane (D % 128 == 0)
+  const int nv = (D + 127) >> 7;  // float4 slots per lane; lanes past the row end (D % 128 != 0) contribute nothing
   float4 v[MAXV];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    if (i < nv) {
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nv && (i * 32 + lane) * 4 < D) {
       int c = (i * 32 + lane) * 4;
       float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
       if (ar) {
@@ -605,7 +606,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(int rows, int D, int per
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    if (i < nv) {
+    if (i < nv && (i * 32 + lane) * 4 < D) {
       float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       q += (a * a + b * b) + (c * c + d * d);
     }
@@ -613,7 +614,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(int rows, int D, int per
   float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    if (i < nv) {
+    if (i < nv && (i * 32 + lane) * 4 < D) {
       int c = (i * 32 + lane) * 4;
       float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
       float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
@@ -637,12 +638,13 @@ __global__ void __launch_bounds__(256) layernorm_proj_kernel(int rows, int D, in
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* xr = x + (size_t)warp * D;
-  const int nv = D >> 7;
+  const int nv = (D + 127) >> 7;
   float4 v[MAXV];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    if (i < nv) {
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nv && (i * 32 + lane) * 4 < D) {
       v[i] = __ldg(reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4));
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(256) layernorm_proj_kernel(int rows, int D, in
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    if (i < nv) {
+    if (i < nv && (i * 32 + lane) * 4 < D) {
       float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       q += (a * a + b * b) + (c * c + d * d);
     }
@@ -662,7 +664,7 @@ __global__ void __launch_bounds__(256) layernorm_proj_kernel(int rows, int D, in
   for (int o = 0; o < MAXP; ++o) acc[o] = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    if (i < nv) {
+    if (i < nv && (i * 32 + lane) * 4 < D) {
       const int c = (i * 32 + lane) * 4;
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
       const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
@@ -693,13 +695,13 @@ int launch_layernorm(const capf_op& op, cudaStream_t st) {
   int rows = op.i[0], D = op.i[1], period = op.i[2];
   if (op.i[3] > 0) {
     const int np = op.i[3];
-    if (np > 8 || period != 0 || op.dtype_in != CAPF_F32 || op.dtype_out != CAPF_F32 || !op.in[4] || (D & 127) || D > 1024 || rows <= 0)
-      return set_error(CAPF_ERR_ARG, "layernorm+proj: n_proj <= 8, no x0, f32 in/out, D % 128 == 0, D <= 1024");
+    if (np > 8 || period != 0 || op.dtype_in != CAPF_F32 || op.dtype_out != CAPF_F32 || !op.in[4] || (D & 3) || D > 1024 || rows <= 0)
+      return set_error(CAPF_ERR_ARG, "layernorm+proj: n_proj <= 8, no x0, f32 in/out, D % 4 == 0, D <= 1024");
     launch_k(layernorm_proj_kernel<8, 8>, dim3((rows + 7) / 8), dim3(256), 0, st, rows, D, np, op.f[0], (const float*)op.in[0],
              (const float*)op.in[1], (const float*)op.in[2], (const float*)op.in[4], (const float*)op.in[5], (float*)op.out[0]);
     return check_launch("layernorm_proj");
   }
-  if (rows <= 0 || D <= 0 || (D & 127) || D > 128 * 8) return set_error(CAPF_ERR_ARG, "layernorm: D must be a multiple of 128, <= 1024");
+  if (rows <= 0 || D <= 0 || (D & 3) || D > 128 * 8) return set_error(CAPF_ERR_ARG, "layernorm: D must be a multiple of 4, <= 1024");
   if (op.dtype_in != CAPF_F32) return set_error(CAPF_ERR_UNSUPPORTED, "layernorm: input stream is f32");
   if (period > 0 && !op.in[3]) return set_error(CAPF_ERR_ARG, "layernorm: period without x0");
   int blocks = (rows + 7) / 8;

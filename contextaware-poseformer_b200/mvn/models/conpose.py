@@ -19,6 +19,8 @@ CPN_NUM_CLASS = 17              # cpn/test_config.py:16
 
 
 class CA_PF(nn.Module):
+    _variant = "h36m"          # program variant; the MPI-INF-3DHP subclass (capf_b200.mpi) overrides it
+
     def __init__(self, config, device="cuda:0", precision=None, use_cuda_graph=False):
         super().__init__()
         bb = config.model.backbone
@@ -34,8 +36,8 @@ class CA_PF(nn.Module):
             print("model backbone weights are fixed")
             for p in self.backbone.parameters():
                 p.requires_grad = False
-        self.volume_net = PoseTransformer(config.model.poseformer, backbone=bb.type)
-        self._pf_cfg = {k: config.model.poseformer[k] for k in ("base_dim", "embed_dim_ratio", "levels")}
+        self.volume_net = PoseTransformer(config.model.poseformer, backbone=bb.type, variant=self._variant)
+        self._pf_cfg = {k: config.model.poseformer[k] for k in ("base_dim", "embed_dim_ratio", "levels", "depth")}
         self.precision = precision or default_precision()
         self.use_cuda_graph = use_cuda_graph
         self._plans = {}
@@ -51,7 +53,7 @@ class CA_PF(nn.Module):
             shapes = {k: tuple(v.shape) for k, v in state.items()}
             prog = program.build_forward_program(self.backbone_type, getattr(self.backbone, "cfg", None), self._pf_cfg,
                                                  shapes, B, H, W, self.precision, use_tc=default_use_tc(),
-                                                 debug_records=debug_records)
+                                                 debug_records=debug_records, variant=self._variant)
             ent = [program.Plan(prog, state, device), ver]
             self._plans[key] = ent
         elif ent[1] != ver:

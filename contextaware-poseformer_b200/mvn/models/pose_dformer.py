@@ -50,24 +50,29 @@ def _context_block(feature_dims, dim, num_heads=4, num_samples=4, mlp_ratio=2):
 
 class PoseTransformer(nn.Module):
     def __init__(self, config=None, backbone="hrnet_32", num_joints=17, in_chans=2, num_heads=8, mlp_ratio=2.0,
-                 qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None):
+                 qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None,
+                 variant="h36m"):
+        """variant="mpi": the MPI-INF-3DHP tree's PoseTransformer (ContextPose_mpi/model/pose_dformer.py:174-262): block
+        depth from config.depth, no context_blocks in the module tree / state_dict."""
         super().__init__()
         from ... import arch
         if not qkv_bias or qk_scale is not None or num_heads != 8 or mlp_ratio != 2.0 or num_joints != 17:
             raise NotImplementedError("libcapf_b200 implements the reference's shipped hyper-parameters only")
-        base_dim, D, depth = int(config["base_dim"]), int(config["embed_dim_ratio"]), int(config["levels"])
-        self.levels = depth
+        base_dim, D, levels = int(config["base_dim"]), int(config["embed_dim_ratio"]), int(config["levels"])
+        depth = levels if variant == "h36m" else int(config["depth"])
+        self.levels = levels
         self.embed_dim_ratio = D
         self.drop_path_rate = drop_path_rate          # identity in eval; stochastic depth is a training feature
-        E = D * (depth + 1)
+        E = D * (levels + 1)
         dims = arch.feature_dims(backbone, base_dim)
         self.feature_dim_list = dims
         self.coord_embed = nn.Linear(in_chans, D)
         self.feat_embed = nn.ModuleList([nn.Linear(c, D) for c in dims])
-        self.Spatial_pos_embed = nn.Parameter(torch.zeros(1, 1 + depth, num_joints, D))
+        self.Spatial_pos_embed = nn.Parameter(torch.zeros(1, 1 + levels, num_joints, D))
         self.joint_blocks = nn.ModuleList([_block(E) for _ in range(depth)])
         self.res_blocks = nn.ModuleList([_block(D) for _ in range(depth)])
-        self.context_blocks = nn.ModuleList([_context_block(dims, D) for _ in range(depth)])
+        if variant == "h36m":
+            self.context_blocks = nn.ModuleList([_context_block(dims, D) for _ in range(levels)])
         self.head = nn.Sequential(nn.LayerNorm(E), nn.Linear(E, 3))
 
     def forward(self, keypoints_2d, ref, features_list):

@@ -268,7 +268,8 @@ class ProgramBuilder:
 # whole-forward program
 # ------------------------------------------------------------------------------------------------------
 def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H: int, W: int, precision: str = "fp32",
-                          use_tc: bool = False, debug_records: bool = False, backbone_only: bool = False) -> Program:
+                          use_tc: bool = False, debug_records: bool = False, backbone_only: bool = False,
+                          variant: str = "h36m") -> Program:
     """CA_PF.forward (conpose.py:30-42) after the crop normalisation, as a Program.
 
     inputs : images [B,H,W,3] f32 (NHWC as the caller passes them -- no permute is needed, conpose.py:32),
@@ -297,8 +298,14 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
         assign_lanes(prog, _lanes_enabled())
         return prog
 
+    if variant not in ("h36m", "mpi"):
+        raise ValueError(f"variant {variant!r}")
     D = int(pf_cfg["embed_dim_ratio"])
     levels = int(pf_cfg["levels"])
+    # H36M tree: `levels` doubles as the block depth (pose_dformer.py:169); the MPI-INF-3DHP tree has its own `depth` and
+    # no DeformableBlocks (ContextPose_mpi/model/pose_dformer.py:199,211-222)
+    depth = levels if variant == "h36m" else int(pf_cfg["depth"])
+    n_context = levels if variant == "h36m" else 0
     if levels != 4:
         raise NotImplementedError("the sampler kernels are specialised for the reference's 4 feature levels")
     dims = arch.feature_dims(backbone, int(pf_cfg["base_dim"]))
@@ -347,7 +354,7 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
     goffs = [0]
     for l in range(levels):
         goffs.append(goffs[-1] + R * 4 * dims[l])
-    for i in range(levels):
+    for i in range(n_context):
         q = f"{vn}context_blocks.{i}"
         t = pb.layernorm(Xl, levels * R, D, q + ".norm1", 1e-5, adt, x0=X0, period=R, tag=q + ".norm1")
         ow = pb.linear(t, levels * R, D, [q + ".attention_weights.weight", q + ".sampling_offsets.weight"],
@@ -381,11 +388,11 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
         pb.linear(hdn, rows, 2 * dim, [q + ".mlp.fc2.weight"], [q + ".mlp.fc2.bias"], dim, residual=x, out=x, tag=q + ".mlp.fc2")
 
     Xall = X.view(0, (S * R, D), "X[:]")
-    for i in range(levels):    # res_blocks: attention over the S level-tokens of one joint (:231-234)
+    for i in range(depth):     # res_blocks: attention over the S level-tokens of one joint (:231-234)
         block(f"{vn}res_blocks.{i}", Xall, S * R, D, 8, R, S, R, 1)
     Y = pb._buf("Y", (R, E), "f32")
     pb._emit(lib.OP_LEVELS_TO_JOINT, "f32", "f32", [R, S, D], [], [X], [Y], tag="levels_to_joint")
-    for i in range(levels):    # joint_blocks: attention over the 17 joints of a frame (:235-238)
+    for i in range(depth):     # joint_blocks: attention over the 17 joints of a frame (:235-238)
         block(f"{vn}joint_blocks.{i}", Y, R, E, 8, B, J, 1, J)
 
     # ---- (a10) head ----------------------------------------------------------------------------------------

@@ -247,8 +247,12 @@ def _context_block(sd, x, ref, feats, p, heads=4, samples=4):
     return torch.cat([x0, xl], 1), pos
 
 
-def lifter_forward(sd, kp2d, ref, feats, levels=4, prefix="volume_net.", trace=None):
-    """PoseTransformer.forward, pose_dformer.py:210-241.  kp2d, ref: [B,17,2]; feats: 4 NCHW maps -> [B,1,17,3]."""
+def lifter_forward(sd, kp2d, ref, feats, levels=4, prefix="volume_net.", trace=None, context=True, depth=None):
+    """PoseTransformer.forward, pose_dformer.py:210-241.  kp2d, ref: [B,17,2]; feats: 4 NCHW maps -> [B,1,17,3].
+
+    context=False, depth=config.depth restates the MPI-INF-3DHP variant (ContextPose_mpi/model/pose_dformer.py:236-262):
+    no DeformableBlocks, `depth` res / joint blocks; the caller applies that variant's output layout (mpi_output)."""
+    depth = levels if depth is None else depth
     S = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     b, p, _ = kp2d.shape
     x = _lin(S, kp2d, "coord_embed")
@@ -257,19 +261,19 @@ def lifter_forward(sd, kp2d, ref, feats, levels=4, prefix="volume_net.", trace=N
     x = torch.stack([x, *fr], 1) + S["Spatial_pos_embed"]
     if trace is not None:
         trace["tokens_embed"] = x.clone()
-    for i in range(levels):
+    for i in range(levels if context else 0):
         x, pos = _context_block(S, x, ref, feats, f"context_blocks.{i}")
         if trace is not None and i == 0:
             trace["deform_pos0"] = pos.clone()
     if trace is not None:
         trace["tokens_context"] = x.clone()
     x = x.permute(0, 2, 1, 3).reshape(b * p, levels + 1, -1)          # 'b l p c -> (b p) l c'
-    for i in range(levels):
+    for i in range(depth):
         x = _block(S, x, f"res_blocks.{i}")
     if trace is not None:
         trace["tokens_res"] = x.clone()
     x = x.reshape(b, p, -1)                                           # '(b p) l c -> b p (l c)'
-    for i in range(levels):
+    for i in range(depth):
         x = _block(S, x, f"joint_blocks.{i}")
     if trace is not None:
         trace["tokens_joint"] = x.clone()
@@ -285,6 +289,18 @@ def normalize_crop_(crop: torch.Tensor):
     crop[..., :2] /= torch.tensor([192 // 2, 256 // 2], device=crop.device)
     crop[..., :2] -= torch.tensor([1, 1], device=crop.device)
     return crop
+
+
+def mpi_forward(sd, bb_cfg, depth, images, kp2d, crop):
+    """VolumetricTriangulationNet.forward of the MPI-INF-3DHP tree (ContextPose_mpi/model/conpose.py:30-42 +
+    pose_dformer.py:236-262): HRNet features, lifter without context blocks, output (x[b,3,1,17,1], None)."""
+    with torch.no_grad():
+        x = images.permute(0, 3, 1, 2).contiguous()
+        ref = normalize_crop_(crop)
+        feats = hrnet_forward(sd, x, bb_cfg)
+        y = lifter_forward(sd, kp2d, ref, feats, context=False, depth=depth)           # [b,1,p,3]
+        b, _, p, _ = y.shape
+        return y.reshape(b, 1, p, 3, 1).permute(0, 3, 1, 2, 4).contiguous(), None
 
 
 def ca_pf_forward(sd, backbone, bb_cfg, images, kp2d, crop, trace=None):
