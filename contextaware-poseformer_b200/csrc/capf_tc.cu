@@ -37,7 +37,6 @@ struct TcP {
   int a_stage_bytes;        // msub * TC_A_SUB_BYTES (B follows A inside a stage)
   int a_sub_bytes;          // offset of sub-tile 1 inside one A chunk = 128 * kb * 2
   int nacc;                 // TMEM accumulator stages (2, or 1 when 2 * msub * BN > 512 columns)
-  int epi;                  // 0: direct per-row epilogue, 1: staged (coalesced) epilogue
   int stg_bufs;             // staging buffers per epilogue warp (2 with a residual, else 1)
   uint32_t stg_off;         // staging region offset from the first pipeline stage
   uint32_t bias_off;        // per-warp bias slices (8 x 256 floats), offset from the first pipeline stage
@@ -540,7 +539,6 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   const int osz = op.dtype_out == CAPF_F32 ? 4 : 2;
 
   // ---- epilogue staging: two tiles per warp with a residual (one being filled by cp.async), else one ------------
-  p.epi = 1;
   p.stg_bufs = p.res ? 2 : 1;
   const int stg_bytes = TC_EPI_WARPS * p.stg_bufs * TC_STG_BYTES + TC_EPI_WARPS * 256 * 4;   // staging tiles + bias slices
 

@@ -271,13 +271,8 @@ template <> struct Vec16<__nv_bfloat16> {
   }
 };
 
-// 16-byte global store / load with an L2 eviction-priority policy
+// 16-byte global store with an L2 eviction-priority policy
 __device__ __forceinline__ void st16_hint(void* p, uint4 v, uint64_t pol) { ptx::st_global_v4_hint(p, v, pol); }
-__device__ __forceinline__ uint4 ld16_hint(const void* p, uint64_t pol) {
-  uint4 v;
-  asm volatile("ld.global.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol) : "memory");
-  return v;
-}
 
 // 16 bias values (broadcast loads through the read-only path); zeros when the op has no bias.  Issued BEFORE the
 // tcgen05.wait::ld so the L1 latency overlaps the TMEM read.
@@ -290,28 +285,6 @@ struct Bias16 {
   }
 };
 
-// bias + GELU + residual + ReLU on 16 accumulator columns of one output row, then the store.
-template <typename TO>
-__device__ __forceinline__ void finish16(const Bias16& bs, int act, const uint32_t (&raw)[16], const Vec16<TO>& rv, bool has_res, TO* dst) {
-  float v[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
-#pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    v[4 * q4] += bs.b[q4].x; v[4 * q4 + 1] += bs.b[q4].y; v[4 * q4 + 2] += bs.b[q4].z; v[4 * q4 + 3] += bs.b[q4].w;
-  }
-  if (act == CAPF_ACT_GELU) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
-  }
-  if (has_res) rv.add_to(v);
-  if (act == CAPF_ACT_RELU) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-  }
-  Vec16<TO>::store(dst, v);
-}
-
 // halo-band 3x3 convolution (capf_tc_halo.cu)
 struct TcHaloState;
 int tc_halo_supported(const capf_op& op);
@@ -320,8 +293,9 @@ int tc_halo_launch(const TcHaloState* s, cudaStream_t st);
 void tc_halo_release(TcHaloState* s);
 void tc_halo_describe(const TcHaloState* s, char* buf, int cap);
 
-// Same for a 16-bit output row staged in shared memory: the residual (if any) is read from, and the result written
-// back to, the two 16-byte chunks at smem addresses s0 / s1.
+// bias + GELU + residual + ReLU on 16 accumulator columns of a 16-bit output row staged in shared memory: the residual (if
+// any) is read from, and the result written back to, the two 16-byte chunks at smem addresses s0 / s1 (runtime-flag
+// variant used by the stem kernel; the GEMM / halo kernels use the compile-time epi16 below).
 template <typename TO>
 __device__ __forceinline__ void finish16_smem(const Bias16& bs, int act, const uint32_t (&raw)[16], bool has_res, uint32_t s0, uint32_t s1) {
   static_assert(sizeof(TO) == 2, "staged epilogue is for 16-bit outputs");
@@ -363,43 +337,6 @@ __device__ __forceinline__ void finish16_smem(const Bias16& bs, int act, const u
   }
   ptx::st_shared_v4(s0, o[0]);
   ptx::st_shared_v4(s1, o[1]);
-}
-
-// Generic staged variant: 16 output columns = sizeof(TO) chunks of 16 bytes at the shared-memory addresses s[].
-template <typename TO>
-__device__ __forceinline__ void finish16_stage(const Bias16& bs, int act, const uint32_t (&raw)[16], bool has_res,
-                                               const uint32_t (&s)[sizeof(TO)]) {
-  if constexpr (sizeof(TO) == 2) {
-    finish16_smem<TO>(bs, act, raw, has_res, s[0], s[1]);
-  } else {
-    float v[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      v[4 * q4] += bs.b[q4].x; v[4 * q4 + 1] += bs.b[q4].y; v[4 * q4 + 2] += bs.b[q4].z; v[4 * q4 + 3] += bs.b[q4].w;
-    }
-    if (act == CAPF_ACT_GELU) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
-    }
-    if (has_res) {
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const uint4 r = ptx::ld_shared_v4(s[q4]);
-        v[4 * q4] += __uint_as_float(r.x); v[4 * q4 + 1] += __uint_as_float(r.y);
-        v[4 * q4 + 2] += __uint_as_float(r.z); v[4 * q4 + 3] += __uint_as_float(r.w);
-      }
-    }
-    if (act == CAPF_ACT_RELU) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-    }
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4)
-      ptx::st_shared_v4(s[q4], make_uint4(__float_as_uint(v[4 * q4]), __float_as_uint(v[4 * q4 + 1]), __float_as_uint(v[4 * q4 + 2]),
-                                          __float_as_uint(v[4 * q4 + 3])));
-  }
 }
 
 // Epilogue of 16 accumulator columns of one output row, staged in shared memory: y = max(floor, gelu?(acc + bias) +

@@ -73,7 +73,7 @@ typedef enum capf_op_kind {
  *     i[0..10] = N,H,W,Cin,Cout,KH,KW,stride,pad,Ho,Wo   i[11]=act  i[12]=impl
  *     i[13] = tcgen05 kernel variant hint: 0 automatic, 1 per-tap TMA implicit GEMM, 2 shared-memory halo band
  *             (3x3 / stride 1 / pad 1 whose folded weights fit in shared memory); used by the A/B parity tests
- *     i[14] = per-tap kernel epilogue hint: 0 automatic, 1 per-row vectors, 2 coalesced staging tile
+ *     i[14] = reserved (a former epilogue-variant hint; ignored)
  *     i[15] = per-tap kernel tile height hint: 0 automatic, 1 = 128 rows, 2 = 256 rows (two accumulators per B stage)
  *     i[16] = per-tap kernel column-tile width hint (0 automatic, else a multiple of 16 dividing Cout)
  *     i[17] = 2-CTA (cta_group::2) GEMM kernel for Linears over rows: 0 automatic (wide Linears with many rows),
