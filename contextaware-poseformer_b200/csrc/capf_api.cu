@@ -56,6 +56,7 @@ static int dispatch(const capf_op& op, const TcConvState* tc, cudaStream_t st) {
     case CAPF_OP_CONV2D:
       if (op.i[12] == CAPF_IMPL_TCGEN05) return tc_conv_launch(op, tc, st);
       return launch_conv_simt(op, st);
+    case CAPF_OP_BASICBLOCK: return tc_conv_launch(op, tc, st);
     case CAPF_OP_FUSE_SUM: return launch_fuse_sum(op, st);
     case CAPF_OP_MAXPOOL3X3S2: return launch_maxpool(op, st);
     case CAPF_OP_BILINEAR: return launch_bilinear(op, st);
@@ -115,6 +116,17 @@ int capf_plan_create(const capf_op* ops, int n_ops, int device, capf_plan** out_
   pl->tc.assign(n_ops, nullptr);
   for (int k = 0; k < n_ops; ++k) {
     capf_op& op = pl->ops[k];
+    if (op.kind == CAPF_OP_BASICBLOCK) {
+      if (!tc_block_supported(op)) {
+        capf_plan_destroy(pl);
+        return set_errorf(CAPF_ERR_UNSUPPORTED, "op %d: fused BasicBlock shape/dtype not supported", k);
+      }
+      e = tc_blockop_prepare(op, &pl->tc[k]);
+      if (e) {
+        capf_plan_destroy(pl);
+        return e;
+      }
+    }
     if (op.kind == CAPF_OP_CONV2D && op.i[12] == CAPF_IMPL_TCGEN05) {
       if (!tc_conv_supported(op)) {
         capf_plan_destroy(pl);
@@ -158,6 +170,7 @@ int capf_plan_op_kernel(const capf_plan* plan, int k, char* buf, int cap) {
       if (op.i[12] == CAPF_IMPL_TCGEN05) tc_conv_describe(plan->tc[k], buf, cap);
       else snprintf(buf, cap, "%s", stem_tc_supported(op) ? "stem_tc_kernel" : "conv_nhwc_simt");
       break;
+    case CAPF_OP_BASICBLOCK: tc_conv_describe(plan->tc[k], buf, cap); break;
     case CAPF_OP_FUSE_SUM: snprintf(buf, cap, "fuse_sum_kernel"); break;
     case CAPF_OP_MAXPOOL3X3S2: snprintf(buf, cap, "maxpool3x3s2_kernel"); break;
     case CAPF_OP_BILINEAR: snprintf(buf, cap, "bilinear_ac_kernel"); break;

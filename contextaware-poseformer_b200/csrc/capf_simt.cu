@@ -497,8 +497,6 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(int N, int H, int W, i
 }
 
 // 16-bit variant: 8 channels (16 bytes) per thread, 32-bit index arithmetic, one thread per output element group.
-template <typename T> __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]);
-template <typename T> __device__ __forceinline__ uint4 pack8(const float (&f)[8]);
 
 template <typename T>
 __global__ void __launch_bounds__(256) bilinear_ac16_kernel(int N, int H, int W, int C8, int Ho, int Wo, float sy, float sx,
@@ -803,31 +801,6 @@ __global__ void __launch_bounds__(128) attention_small_kernel(int groups, int he
 }
 
 // ---- 16-bit fast paths -------------------------------------------------------------------------------------
-template <> __device__ __forceinline__ void unpack8<__half>(const uint4& u, float (&f)[8]) {
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) { float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
-}
-template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) { float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
-}
-template <> __device__ __forceinline__ uint4 pack8<__half>(const float (&f)[8]) {
-  uint4 u;
-  __half2* h = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-  return u;
-}
-template <> __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float (&f)[8]) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-  return u;
-}
-
 // Attention over the 17 joints of a frame (pose_dformer.py:235-238; 8 heads x 80): one warp per (frame, head).  K and V
 // (17 x 80, 16-bit) are staged in shared memory with 16-byte loads; lane i < 17 keeps query row i and its 80 fp32 output
 // accumulators in registers and reads K / V rows as warp-wide broadcasts, so the inner loops are 8 FMAs per LDS.128.

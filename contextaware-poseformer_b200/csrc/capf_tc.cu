@@ -417,6 +417,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 struct TcConvState {
   TcHaloState* halo = nullptr;   // non-null: the op runs on the halo-band kernel instead of tc_gemm_kernel
   Tc2State* two = nullptr;       // non-null: the op runs on the 2-CTA GEMM kernel (capf_tc2.cu)
+  TcBlockState* blk = nullptr;   // non-null: a fused BasicBlock op (capf_tc_block.cu)
   CUtensorMap mapA, mapB;
   TcP p;
   int grid;
@@ -494,6 +495,16 @@ int tc_encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* 
   CUresult r = g_encode(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_errorf(CAPF_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return CAPF_OK;
+}
+
+int tc_blockop_prepare(const capf_op& op, TcConvState** out) {
+  *out = nullptr;
+  TcConvState* s = new (std::nothrow) TcConvState();
+  if (!s) return set_error(CAPF_ERR_ARG, "tc_blockop_prepare: out of host memory");
+  int e = tc_block_prepare(op, &s->blk);
+  if (e) { delete s; return e; }
+  *out = s;
   return CAPF_OK;
 }
 
@@ -687,6 +698,7 @@ static int tc_launch_typed(const TcConvState* s, cudaStream_t st) {
 
 int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
   if (!s) return set_error(CAPF_ERR_ARG, "tc conv: op was not prepared");
+  if (s->blk) return tc_block_launch(s->blk, st);
   if (s->two) return tc2_launch(s->two, st);
   if (s->halo) return tc_halo_launch(s->halo, st);
   switch (s->dtype_out) {
@@ -699,12 +711,14 @@ int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
 
 void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
   if (!s) { snprintf(buf, cap, "?"); return; }
+  if (s->blk) { tc_block_describe(s->blk, buf, cap); return; }
   if (s->two) { tc2_describe(s->two, buf, cap); return; }
   if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
   snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages]", 128 * s->p.msub, s->p.BN, s->p.num_stages);
 }
 
 void tc_conv_release(TcConvState* s) {
+  if (s && s->blk) tc_block_release(s->blk);
   if (s && s->two) tc2_release(s->two);
   if (s && s->halo) tc_halo_release(s->halo);
   delete s;

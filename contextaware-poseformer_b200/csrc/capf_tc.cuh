@@ -406,6 +406,14 @@ __device__ __forceinline__ void epi16(const uint32_t (&raw)[16], const float* __
   }
 }
 
+// fused 32-channel BasicBlock (capf_tc_block.cu)
+struct TcBlockState;
+int tc_block_supported(const capf_op& op);
+int tc_block_prepare(const capf_op& op, TcBlockState** out);
+int tc_block_launch(const TcBlockState* s, cudaStream_t st);
+void tc_block_release(TcBlockState* s);
+void tc_block_describe(const TcBlockState* s, char* buf, int cap);
+
 // 2-CTA (cta_group::2) GEMM for the wide lifter Linears (capf_tc2.cu)
 struct Tc2State;
 int tc2_supported(const capf_op& op);

@@ -290,6 +290,8 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
     else:
         raise ValueError(backbone)
     prog.feature_maps = [m.ref for m in maps]
+    if pb.use_tc:
+        fuse_basic_blocks(prog)
     prog.n_backbone_ops = len(prog.ops)
     if backbone_only:
         for k, m in enumerate(maps):
@@ -410,6 +412,56 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
 
 def _lanes_enabled():
     return os.environ.get("CAPF_STREAMS", "1") != "0"
+
+
+# ------------------------------------------------------------------------------------------------------
+# peephole: HRNet BasicBlocks of the 32-channel branch -> one fused op (csrc/capf_tc_block.cu)
+# ------------------------------------------------------------------------------------------------------
+FUSED_BLOCK_CHANNELS = 32
+FUSED_BLOCK_MAX_W = 128        # wider bands (input + intermediate, double buffered) do not fit one SM's shared memory
+
+
+def _same_buf(a, b):
+    return isinstance(a, Buf) and isinstance(b, Buf) and a.root is b.root and a.root_offset == b.root_offset and a.shape == b.shape
+
+
+def fuse_basic_blocks(prog: Program):
+    """conv3x3-BN-ReLU -> conv3x3-BN-(+x)-ReLU pairs (pose_hrnet.py:79-95) with 32 channels, 16-bit tensors and tcgen05
+    kernels become one CAPF_OP_BASICBLOCK: the intermediate tensor disappears from the program (and from HBM).  Returns the
+    number of fused pairs.  CAPF_FUSE_BLOCKS=0 keeps the two-kernel form."""
+    if os.environ.get("CAPF_FUSE_BLOCKS", "1") == "0":
+        return 0
+    readers = {}
+    for op in prog.ops:
+        for b in op.ins:
+            if isinstance(b, Buf):
+                readers[b.root] = readers.get(b.root, 0) + 1
+    out, k, fused = [], 0, 0
+    ops = prog.ops
+    while k < len(ops):
+        a = ops[k]
+        b = ops[k + 1] if k + 1 < len(ops) else None
+        ok = (b is not None and a.kind == lib.OP_CONV2D and b.kind == lib.OP_CONV2D
+              and a.dtype_in == a.dtype_out == b.dtype_in == b.dtype_out and a.dtype_in in ("f16", "bf16")
+              and a.i[12] == lib.IMPL_TCGEN05 and b.i[12] == lib.IMPL_TCGEN05
+              and a.i[3] == a.i[4] == b.i[3] == b.i[4] == FUSED_BLOCK_CHANNELS
+              and a.i[5:9] == [3, 3, 1, 1] and b.i[5:9] == [3, 3, 1, 1] and a.i[:3] == b.i[:3] and a.i[2] <= FUSED_BLOCK_MAX_W
+              and a.i[11] == lib.ACT_RELU and b.i[11] == lib.ACT_RELU
+              and a.ins[3] is None and _same_buf(b.ins[0], a.outs[0]) and _same_buf(b.ins[3], a.ins[0])
+              and readers.get(a.outs[0].root, 0) == 1 and a.outs[0].role == "act")
+        if ok:
+            x, y = a.ins[0], b.outs[0]
+            wbytes = sum(int(np.prod(w.shape)) * _ITEMSIZE[w.dtype] for w in (a.ins[1], b.ins[1]))
+            out.append(Op(lib.OP_BASICBLOCK, a.dtype_in, a.dtype_out, [a.i[0], a.i[1], a.i[2], a.i[3]], [],
+                          [x, a.ins[1], a.ins[2], b.ins[1], b.ins[2]], [y], tag=b.tag.rsplit(".", 1)[0] + ".block",
+                          flops=a.flops + b.flops, nbytes=x.nbytes + y.nbytes + wbytes))
+            fused += 1
+            k += 2
+        else:
+            out.append(a)
+            k += 1
+    prog.ops[:] = out
+    return fused
 
 
 # ------------------------------------------------------------------------------------------------------

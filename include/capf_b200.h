@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 5
+#define CAPF_ABI_VERSION 6
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -58,7 +58,8 @@ typedef enum capf_op_kind {
   CAPF_OP_LEVELS_TO_JOINT = 10,
   CAPF_OP_CROP_NORMALIZE = 11,
   CAPF_OP_CAST = 12,
-  CAPF_OP_PREPROCESS_U8 = 13
+  CAPF_OP_PREPROCESS_U8 = 13,
+  CAPF_OP_BASICBLOCK = 14
 } capf_op_kind;
 
 /*
@@ -142,6 +143,11 @@ typedef enum capf_op_kind {
  *     i[0]=n_points   out[0]=crop [n][2] f32
  *
  * CAPF_OP_CAST -- dtype conversion of a dense array.  i[0],i[1]=element count (lo,hi 31-bit words) in[0] out[0]
+ *
+ * CAPF_OP_BASICBLOCK -- one fused HRNet BasicBlock (pose_hrnet.py:66-95): y = relu(bn2(conv2(relu(bn1(conv1(x))))) + x), both
+ *                    convolutions 3x3 / stride 1 / pad 1, C -> C channels (C = 32), 16-bit NHWC; the intermediate never leaves
+ *                    the SM.  The host emits it for conv pairs that match (program.fuse_basic_blocks).
+ *     i[0..3]=N,H,W,C   in[0]=x  in[1]=w1 [C][9C]  in[2]=b1 f32[C]  in[3]=w2 [C][9C]  in[4]=b2 f32[C]   out[0]=y
  *
  * CAPF_OP_PREPROCESS_U8 -- the image half of data_prefetcher.preload (mvn/datasets/utils.py:45-50, flip-test copy :67):
  *                    uint8 BGR HWC crops -> fp32 RGB NHWC, (x / 255 - mean[c]) / std[c] with IEEE divisions (bit-exact

@@ -163,6 +163,17 @@ class Interp:
         c /= torch.tensor([96.0, 128.0])
         c -= 1.0
 
+    def _op14(self, op):  # BASICBLOCK: relu(conv2(relu(conv1(x) + b1)) + b2 + x), 16-bit intermediate like the two-op form
+        N, H, W, C = op.i[:4]
+        x = self.t(op.ins[0]).reshape(N, H, W, C)
+        xf = x.float().permute(0, 3, 1, 2)
+        w1 = self.t(op.ins[1]).float().reshape(C, 3, 3, C).permute(0, 3, 1, 2).contiguous()
+        w2 = self.t(op.ins[3]).float().reshape(C, 3, 3, C).permute(0, 3, 1, 2).contiguous()
+        u = F.relu(F.conv2d(xf, w1, self.t(op.ins[2]).float(), 1, 1)).to(x.dtype).float()
+        y = F.relu(F.conv2d(u, w2, self.t(op.ins[4]).float(), 1, 1) + xf).permute(0, 2, 3, 1)
+        out = self.t(op.outs[0])
+        out.copy_(y.reshape(out.shape).to(out.dtype))
+
     def _op12(self, op):  # CAST
         out = self.t(op.outs[0])
         out.copy_(self.t(op.ins[0]).to(out.dtype))
