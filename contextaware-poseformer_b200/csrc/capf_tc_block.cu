@@ -12,12 +12,16 @@
 // right padding).  conv2's zero padding needs MID to be ZERO outside the image (not conv1 of the padding), which the
 // first epilogue enforces; its one-pixel border of MID costs (bh + 2) / bh more conv1 work.
 //
-// Roles (512 threads): warp 0 TMA producer, warps 1 and 3 MMA issuers (even / odd sub-tiles), warp 2 TMEM allocator,
-// warps 4..15 three 4-warp epilogue groups.  Every 128-pixel sub-tile of a band owns one TMEM accumulator (phase A:
+// Roles (640 threads): warp 0 TMA producer, warps 1 and 3 MMA issuers (even / odd sub-tiles), warp 2 TMEM allocator,
+// warps 4..19 four 4-warp epilogue groups.  Every 128-pixel sub-tile of a band owns one TMEM accumulator (phase A:
 // slots [0, n1max), phase B: [n1max, n1max + n2max)), so a band needs no accumulator recycling; phase B sub-tile j starts
 // as soon as the MID rows it reads have been written (per-sub-tile "mid ready" barriers), which pipelines conv1 ->
 // epilogue 1 -> conv2 inside a band.  Barriers that are used once per band keep their phase parity in a per-role bit
 // mask (the ragged last band of an image uses fewer sub-tiles).
+//
+// Measured (tools/block_trace.py, ncu): the issuers block on MMA *issue*, ~64 clk per 128 x 32 x 16 MMA -- the shared-memory
+// port (4 KB of A + 1 KB of B per MMA, plus MID writes / residual reads / TMA writes, ~100 B/clk effective) bounds the kernel;
+// 10-25 % of a band is spent waiting for MID rows.  HBM traffic drops from 2 x 143 MB to 77 MB per block.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -27,11 +31,12 @@
 
 namespace capf {
 
-constexpr int BLK_THREADS = 512;
+constexpr int BLK_THREADS = 640;            // warps 0-3: TMA / MMA / TMEM / MMA; warps 4-19: four 4-warp epilogue groups
 constexpr int BLK_C = 32;                   // channels in = out
 constexpr int BLK_PIX = BLK_C * 2;          // bytes per pixel row (64-byte swizzle span)
 constexpr int BLK_W_BYTES = 9 * BLK_C * BLK_C * 2;   // folded weights of one convolution: 18 KB
-constexpr int BLK_GROUPS = 3;
+constexpr int BLK_GROUPS = 4;
+constexpr int BLK_EPI_WARPS = 4 * BLK_GROUPS;
 constexpr int BLK_MAX_ACC = 16;             // 16 x 32 TMEM columns
 // header layout (bytes from the 1024-aligned base)
 constexpr int BH_W = 0, BH_XFULL = 8, BH_XEMPTY = 24, BH_MIDFREE = 40, BH_TFULL = 64, BH_TEMPTY = 192, BH_MIDRDY = 320, BH_TMEM = 448;
@@ -48,6 +53,7 @@ struct BlockP {
   const float* bias1;
   const float* bias2;
   void* out;
+  long long* trace;      // optional (debug, op.in[5]): per-band wait cycles of CTA 0's issuers, see tools/block_trace.py
 };
 
 __device__ __forceinline__ int blk_div_wp(int v, uint32_t magic) { return (int)__umulhi((uint32_t)v, magic); }
@@ -67,7 +73,6 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const uint32_t smem_w1 = base + BLK_HEADER, smem_w2 = smem_w1 + BLK_W_BYTES;
   const uint32_t smem_x = smem_w2 + BLK_W_BYTES;
   const uint32_t smem_mid = smem_x + 2u * (uint32_t)p.x_bytes;
-  const uint32_t smem_stg = smem_mid + (uint32_t)p.mid_bytes;
   uint8_t* const gen = smem_raw + (base - raw);                 // generic pointer to `base`
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + BH_TMEM);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,7 +86,7 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     ptx::mbar_init(bar_w, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_xfull + 8 * b, 1);
-      ptx::mbar_init(bar_xempty + 8 * b, 2 + 12);              // both issuers (phase-A reads) + 12 epilogue warps (residual reads)
+      ptx::mbar_init(bar_xempty + 8 * b, 2 + BLK_EPI_WARPS);   // both issuers (phase-A reads) + the epilogue warps (residual reads)
     }
     ptx::mbar_init(bar_midfree, 2);                             // both issuers: phase-B reads of MID complete
     for (int a = 0; a < BLK_MAX_ACC; ++a) {
@@ -148,12 +153,18 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const uint32_t buf = k & 1u, ph = (k >> 1) & 1u;
       const int bh_eff = min(p.bh, p.H - bin * p.bh);
       const int n1 = ((bh_eff + 2) * p.Wp + 127) >> 7, n2 = (bh_eff * p.Wp + 127) >> 7;
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && k < 32;
+      long long tw = 0, w_x = 0, w_ta = 0, w_mid = 0, w_tb = 0;
+      if (tr) tw = clock64();
       ptx::mbar_wait(bar_xfull + 8 * buf, ph);
+      if (tr) { w_x = clock64() - tw; p.trace[(me * 8 + 0) * 32 + k] = clock64(); }
       ptx::tc_fence_after();
       const uint32_t x_lo = tc_desc_lo(smem_x + buf * (uint32_t)p.x_bytes, 1u);
       // ---- phase A: conv1 over bh_eff + 2 rows --------------------------------------------------------
       for (int j = me; j < n1; j += 2) {
+        if (tr) tw = clock64();
         ptx::mbar_wait(bar_tempty + 8 * j, ((pm >> j) & 1u) ^ 1u);
+        if (tr) w_ta += clock64() - tw;
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t d = tmem_base + (uint32_t)(j * BLK_C), a_sub = x_lo + (uint32_t)(j * 128) * 4u;
@@ -173,12 +184,15 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       int ready_upto = -1;
       for (int j = me; j < n2; j += 2) {
         const int need = min(n1 - 1, (j * 128 + 128 + 2 * p.Wp) >> 7);
+        if (tr) tw = clock64();
         while (ready_upto < need) {
           ++ready_upto;
           ptx::mbar_wait(bar_midrdy + 8 * ready_upto, (pm >> ready_upto) & 1u);
         }
+        if (tr) { w_mid += clock64() - tw; tw = clock64(); }
         const int a = p.n1max + j;
         ptx::mbar_wait(bar_tempty + 8 * a, ((pm >> a) & 1u) ^ 1u);
+        if (tr) w_tb += clock64() - tw;
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t d = tmem_base + (uint32_t)(a * BLK_C), a_sub = mid_lo + (uint32_t)(j * 128) * 4u;
@@ -194,6 +208,10 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       }
       if (ptx::elect_one()) ptx::umma_commit(bar_midfree);               // my phase-B reads of MID
       __syncwarp();
+      if (tr) {
+        p.trace[(me * 8 + 1) * 32 + k] = w_x; p.trace[(me * 8 + 2) * 32 + k] = w_ta; p.trace[(me * 8 + 3) * 32 + k] = w_mid;
+        p.trace[(me * 8 + 4) * 32 + k] = w_tb; p.trace[(me * 8 + 5) * 32 + k] = clock64();
+      }
       pm ^= ((1u << n1) - 1u) | (((1u << n2) - 1u) << p.n1max);
       if (++bin == p.bands_per_img) bin = 0;
     }
@@ -201,9 +219,6 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     // ===================================== epilogues =========================================
     const int q = warp & 3, grp = (warp - 4) >> 2;
     T* out = reinterpret_cast<T*>(p.out);
-    const uint32_t stg = smem_stg + (uint32_t)(warp - 4) * 2048u;
-    uint8_t* const stg_ptr = gen + (stg - base);
-    auto stg_off = [](int r, int c) { return (uint32_t)(r * BLK_PIX + ((c ^ ((r >> 1) & 3)) << 4)); };
     const uint64_t pol_out = ptx::policy_evict_last();
     int img = img0, bin = band0 - img0 * p.bands_per_img;
     uint32_t k = 0, pm = 0, gseq = 0;
@@ -265,8 +280,9 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           const int mp = j * 128 + q * 32 + lane;
           const int iy = blk_div_wp(mp, p.wp_magic), ix = mp - iy * p.Wp;
           const bool live = mp < bh_eff * p.Wp && ix < p.W;
-          const int myoff = live ? (((img * p.H + y0 + iy) * p.W + ix) * BLK_C) : -1;
+          const int myoff = live ? (((img * p.H + y0 + iy) * p.W + ix) * BLK_C) : 0;
           const uint32_t hx = (uint32_t)((iy + 2) * p.Wp + ix + 1);    // this pixel in the X band (2 halo rows, 1 zero column)
+          uint4 o[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float f[8], r[8];
@@ -276,18 +292,17 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               const float acc = __uint_as_float(c < 2 ? a0[8 * c + e] : a1[8 * (c - 2) + e]);
               f[e] = fmaxf(acc + sbias[32 + 8 * c + e] + r[e], 0.f);
             }
-            *reinterpret_cast<uint4*>(stg_ptr + stg_off(lane, c)) = pack8<T>(f);
+            o[c] = pack8<T>(f);
           }
           ptx::tc_fence_before();
           ptx::mbar_arrive(bar_tempty + 8 * a);
-          __syncwarp();
+          // the pixel's 64 output bytes straight from registers: four 16-byte stores per thread (the four stores of a
+          // thread fill its two 32-byte sectors in L2); no staging tile, no shuffles -- the epilogue warps are the
+          // critical resource of this kernel, not the LSU
+          if (live) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int item = i * 32 + lane, r = item >> 2, c = item & 3;
-            const int off = __shfl_sync(0xffffffffu, myoff, r);
-            if (off >= 0) ptx::st_global_v4_hint(out + off + c * 8, *reinterpret_cast<const uint4*>(stg_ptr + stg_off(r, c)), pol_out);
+            for (int c = 0; c < 4; ++c) ptx::st_global_v4_hint(out + myoff + c * 8, o[c], pol_out);
           }
-          __syncwarp();
         }
       }
       __syncwarp();
@@ -320,7 +335,7 @@ static int block_plan(const capf_op& op, BlockP& p, int& smem_bytes) {
   memset(&p, 0, sizeof(p));
   p.H = H; p.W = W; p.Nimg = N; p.Wp = W + 1;
   p.wp_magic = (uint32_t)(((1ull << 32) + p.Wp - 1) / p.Wp);
-  const int fixed = 1024 + BLK_HEADER + 2 * BLK_W_BYTES + 12 * 2048;
+  const int fixed = 1024 + BLK_HEADER + 2 * BLK_W_BYTES;
   int best_bh = 0;
   double best_cost = 1e300;
   for (int bh = 1; bh <= H && bh + 5 <= 256; ++bh) {
@@ -380,6 +395,7 @@ int tc_block_prepare(const capf_op& op, TcBlockState** out) {
   p.bias1 = (const float*)op.in[2];
   p.bias2 = (const float*)op.in[4];
   p.out = op.out[0];
+  p.trace = (long long*)op.in[5];      // debug only (NULL in every program the host layer builds)
   s->grid = p.num_bands < g_num_sms ? p.num_bands : g_num_sms;
   s->dtype = op.dtype_in;
   const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
