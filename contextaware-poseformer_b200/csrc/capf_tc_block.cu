@@ -13,7 +13,7 @@
 // first epilogue enforces; its one-pixel border of MID costs (bh + 2) / bh more conv1 work.
 //
 // Roles (640 threads): warp 0 TMA producer, warps 1 and 3 MMA issuers (even / odd sub-tiles), warp 2 TMEM allocator,
-// warps 4..19 four 4-warp epilogue groups.  Every 128-pixel sub-tile of a band owns one TMEM accumulator (phase A:
+// warps 4..19 four 4-warp epilogue groups (two for epilogue 1, two for epilogue 2).  Every 128-pixel sub-tile of a band owns one TMEM accumulator (phase A:
 // slots [0, n1max), phase B: [n1max, n1max + n2max)), so a band needs no accumulator recycling; phase B sub-tile j starts
 // as soon as the MID rows it reads have been written (per-sub-tile "mid ready" barriers), which pipelines conv1 ->
 // epilogue 1 -> conv2 inside a band.  Barriers that are used once per band keep their phase parity in a per-role bit
@@ -86,13 +86,13 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     ptx::mbar_init(bar_w, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_xfull + 8 * b, 1);
-      ptx::mbar_init(bar_xempty + 8 * b, 2 + BLK_EPI_WARPS);   // both issuers (phase-A reads) + the epilogue warps (residual reads)
+      ptx::mbar_init(bar_xempty + 8 * b, 2 + 8);               // both issuers (phase-A reads) + the 8 epilogue-2 warps (residual reads)
     }
     ptx::mbar_init(bar_midfree, 2);                             // both issuers: phase-B reads of MID complete
     for (int a = 0; a < BLK_MAX_ACC; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);
-      ptx::mbar_init(bar_tempty + 8 * a, 128);
-      ptx::mbar_init(bar_midrdy + 8 * a, 128);
+      ptx::mbar_init(bar_tempty + 8 * a, a < p.n1max ? 256 : 128);    // phase-A slots: both E1 groups; phase-B slots: one E2 group
+      ptx::mbar_init(bar_midrdy + 8 * a, 256);
     }
     ptx::fence_mbar_init();
   }
@@ -217,34 +217,30 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================================== epilogues =========================================
+    // Epilogue 1 is on the critical path (conv2 cannot start before the MID rows exist), epilogue 2 is not: when all
+    // groups took sub-tiles round-robin, an E1 queued behind two E2s of the previous band and the issuers idled 10-25 %
+    // of a band.  So the roles are dedicated: groups 0 and 1 BOTH work on every phase-A sub-tile (16 of the 32 channels
+    // each: half the latency), groups 2 and 3 alternate on the phase-B sub-tiles.
     const int q = warp & 3, grp = (warp - 4) >> 2;
     T* out = reinterpret_cast<T*>(p.out);
     const uint64_t pol_out = ptx::policy_evict_last();
     int img = img0, bin = band0 - img0 * p.bands_per_img;
-    uint32_t k = 0, pm = 0, gseq = 0;
+    uint32_t k = 0, pm = 0;
     for (int band = band0; band < band1; ++band, ++k) {
       const uint32_t buf = k & 1u;
       const int y0 = bin * p.bh;
       const int bh_eff = min(p.bh, p.H - y0);
       const int n1 = ((bh_eff + 2) * p.Wp + 127) >> 7, n2 = (bh_eff * p.Wp + 127) >> 7;
-      uint8_t* const xg = gen + (smem_x - base) + buf * (uint32_t)p.x_bytes;
-      uint8_t* const mg = gen + (smem_mid - base);
-      bool mid_checked = k == 0;
-      for (int s = 0; s < n1 + n2; ++s) {
-        if ((gseq + (uint32_t)s) % BLK_GROUPS != (uint32_t)grp) continue;
-        if (s < n1) {
-          // ---- epilogue 1: relu(acc + b1), zero outside the image, 16-bit, into MID (shifted by one pixel) ----
-          const int j = s;
+      if (grp < 2) {
+        // ---- epilogue 1: relu(acc + b1), zero outside the image, 16-bit, into MID (shifted by one pixel) ----
+        uint8_t* const mg = gen + (smem_mid - base);
+        const int ch0 = 16 * grp;                                       // this group's 16 channels = 2 chunks of the pixel row
+        if (k > 0) ptx::mbar_wait(bar_midfree, (k - 1u) & 1u);          // conv2 of the previous band has finished reading MID
+        for (int j = 0; j < n1; ++j) {
           ptx::mbar_wait(bar_tfull + 8 * j, (pm >> j) & 1u);
           ptx::tc_fence_after();
-          if (!mid_checked) {                                           // conv2 of the previous band has finished reading MID
-            ptx::mbar_wait(bar_midfree, (k - 1u) & 1u);
-            mid_checked = true;
-          }
-          uint32_t a0[16], a1[16];
-          const uint32_t taddr = tmem_base + (uint32_t)(j * BLK_C) + ((uint32_t)(q * 32) << 16);
-          ptx::tmem_ld16(taddr, a0);
-          ptx::tmem_ld16(taddr + 16u, a1);
+          uint32_t a0[16];
+          ptx::tmem_ld16(tmem_base + (uint32_t)(j * BLK_C + ch0) + ((uint32_t)(q * 32) << 16), a0);
           ptx::tmem_ld_wait();
           const int mp = j * 128 + q * 32 + lane;
           const int iy = blk_div_wp(mp, p.wp_magic), ix = mp - iy * p.Wp;
@@ -253,23 +249,23 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           if (mp < (bh_eff + 2) * p.Wp) {
             const uint32_t h = (uint32_t)mp + 1u;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
               float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float acc = __uint_as_float(c < 2 ? a0[8 * c + e] : a1[8 * (c - 2) + e]);
-                f[e] = valid ? fmaxf(acc + sbias[8 * c + e], 0.f) : 0.f;
-              }
-              *reinterpret_cast<uint4*>(mg + blk_chunk(h, (uint32_t)c)) = pack8<T>(f);
+              for (int e = 0; e < 8; ++e) f[e] = valid ? fmaxf(__uint_as_float(a0[8 * c + e]) + sbias[ch0 + 8 * c + e], 0.f) : 0.f;
+              *reinterpret_cast<uint4*>(mg + blk_chunk(h, (uint32_t)(2 * grp + c))) = pack8<T>(f);
             }
           }
           ptx::tc_fence_before();
           ptx::mbar_arrive(bar_tempty + 8 * j);
           ptx::fence_proxy_async();                                     // generic-proxy writes of MID -> tensor-pipe reads
           ptx::mbar_arrive(bar_midrdy + 8 * j);
-        } else {
-          // ---- epilogue 2: relu(acc + b2 + x), 16-bit, staged, coalesced stores -------------------------------
-          const int j = s - n1, a = p.n1max + j;
+        }
+      } else {
+        // ---- epilogue 2: relu(acc + b2 + x), 16-bit, 64 bytes per pixel straight from registers -------------------
+        uint8_t* const xg = gen + (smem_x - base) + buf * (uint32_t)p.x_bytes;
+        for (int j = grp - 2; j < n2; j += 2) {
+          const int a = p.n1max + j;
           ptx::mbar_wait(bar_tfull + 8 * a, (pm >> a) & 1u);
           ptx::tc_fence_after();
           uint32_t a0[16], a1[16];
@@ -296,19 +292,16 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           }
           ptx::tc_fence_before();
           ptx::mbar_arrive(bar_tempty + 8 * a);
-          // the pixel's 64 output bytes straight from registers: four 16-byte stores per thread (the four stores of a
-          // thread fill its two 32-byte sectors in L2); no staging tile, no shuffles -- the epilogue warps are the
-          // critical resource of this kernel, not the LSU
+          // four 16-byte stores per thread (they fill the pixel's two 32-byte sectors in L2); no staging tile, no shuffles
           if (live) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) ptx::st_global_v4_hint(out + myoff + c * 8, o[c], pol_out);
           }
         }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_xempty + 8 * buf);          // this warp no longer reads X[buf] (residuals)
       }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_xempty + 8 * buf);            // this warp no longer reads X[buf] (residuals)
       pm ^= ((1u << n1) - 1u) | (((1u << n2) - 1u) << p.n1max);
-      gseq += (uint32_t)(n1 + n2);
       if (++bin == p.bands_per_img) { bin = 0; ++img; }
     }
   }
