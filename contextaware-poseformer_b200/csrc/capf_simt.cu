@@ -1216,7 +1216,7 @@ __device__ __forceinline__ void deform_gather(const DSample* __restrict__ samp, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) deform_sample16_kernel(SampP p, const float* __restrict__ ref, const float* __restrict__ ow,
+__global__ void __launch_bounds__(256, 3) deform_sample16_kernel(SampP p, const float* __restrict__ ref, const float* __restrict__ ow,
                                                               T* __restrict__ out, int* __restrict__ rec) {
   pdl_wait();
   __shared__ DSample ssamp[8][16];
