@@ -49,7 +49,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi needs a
+    few hundred ms to produce its first line, longer than a short timed region, so the sampler is started early (before the
+    warm-up) and `stop(t_begin, t_end)` keeps the samples whose arrival time falls inside the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -59,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -67,15 +69,24 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
+        rows = self.rows
+        window = "timed region"
+        if t_begin is not None:
+            inside = [r for r in rows if t_begin <= r[0] <= t_end + 0.06]
+            if inside:
+                rows = inside
+            else:       # region shorter than the sampling period: the samples closest to it (under load: the warm-up / e2e loop)
+                rows = sorted(rows, key=lambda r: abs(r[0] - 0.5 * (t_begin + t_end)))[:3]
+                window = "nearest samples (timed region shorter than the sampling period)"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for _, r in rows:
             c = [x.strip() for x in r.split(",")]
             if len(c) < 9:
                 continue
@@ -88,7 +99,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def build_model(backbone, precision, device, graph):
@@ -173,6 +184,9 @@ def run_native(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     B, H, W = args.batch, args.height, args.width
     model, weights, cfg = build_model(args.backbone, args.precision, dev, graph=not args.no_graph)
     images, kp2d, crop = capf_b200.synth.make_inputs(B, H, W, 1234 + rank)
@@ -199,17 +213,15 @@ def run_native(args):
             out = step_resident()
         barrier()
         # ---- timed region 1: device-resident inputs ------------------------------------------------------
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        wall0 = time.time()
         e0.record()
         for _ in range(args.steps):
             out = step_resident()
         e1.record()
         barrier()
-        clocks = sampler.stop() if rank == 0 else None
+        wall1 = time.time()
         ms_total = e0.elapsed_time(e1)
 
         # ---- timed region 2: end to end from pinned host memory ------------------------------------------
@@ -255,6 +267,7 @@ def run_native(args):
         t1.record()
         barrier()
         ms_e2e = t0.elapsed_time(t1)
+        clocks = sampler.stop(wall0, wall1) if rank == 0 else None
 
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
