@@ -626,6 +626,69 @@ __global__ void __launch_bounds__(256) layernorm_kernel(int rows, int D, int per
   }
 }
 
+// Narrow rows (D <= 128, the 128-wide LayerNorms of the context / res blocks: 16 of the 24 launches of a step): one
+// float4 per lane covers a row, so a warp takes RPW rows at once -- RPW independent loads and RPW interleaved shuffle
+// reductions in flight instead of one dependent chain per warp (the one-row version ran at ~1.3 TB/s, latency-bound).
+template <typename TO, int RPW>
+__global__ void __launch_bounds__(256) layernorm_narrow_kernel(int rows, int D, int period, float eps, const float* __restrict__ x,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const float* __restrict__ x0, TO* __restrict__ y) {
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int row0 = warp * RPW;
+  if (row0 >= rows) return;
+  const int c = lane * 4;
+  const bool on = c < D;
+  float4 v[RPW];
+  float s[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int row = row0 + r;
+    if (on && row < rows) {
+      v[r] = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * D + c));
+      if (period > 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)(row % period) * D + c));
+        v[r].x += a.x; v[r].y += a.y; v[r].z += a.z; v[r].w += a.w;
+      }
+    }
+    s[r] = (v[r].x + v[r].y) + (v[r].z + v[r].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  }
+  float mean[RPW], q[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    mean[r] = s[r] / (float)D;
+    const float a = v[r].x - mean[r], b = v[r].y - mean[r], cc = v[r].z - mean[r], d = v[r].w - mean[r];
+    q[r] = on ? (a * a + b * b) + (cc * cc + d * d) : 0.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+  }
+  if (!on) return;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+    if (row < rows) {
+      const float rstd = rsqrtf(q[r] / (float)D + eps);
+      float4 o;
+      o.x = (v[r].x - mean[r]) * rstd * g.x + bb.x;
+      o.y = (v[r].y - mean[r]) * rstd * g.y + bb.y;
+      o.z = (v[r].z - mean[r]) * rstd * g.z + bb.z;
+      o.w = (v[r].w - mean[r]) * rstd * g.w + bb.w;
+      st4<TO>(y + (size_t)row * D + c, o);
+    }
+  }
+}
+
 // LayerNorm + narrow Linear (the head, pose_dformer.py:205-208,240): one warp per row, everything in fp32.
 template <int MAXV, int MAXP>
 __global__ void __launch_bounds__(256) layernorm_proj_kernel(int rows, int D, int nproj, float eps, const float* __restrict__ x,
@@ -704,6 +767,17 @@ int launch_layernorm(const capf_op& op, cudaStream_t st) {
   if (period > 0 && !op.in[3]) return set_error(CAPF_ERR_ARG, "layernorm: period without x0");
   int blocks = (rows + 7) / 8;
   const float *x = (const float*)op.in[0], *g = (const float*)op.in[1], *b = (const float*)op.in[2], *x0 = (const float*)op.in[3];
+  if (D <= 128) {            // same arithmetic (sum / variance association per lane, shuffle order) as the one-row kernel
+    constexpr int RPW = 4;
+    const int nb = (rows + 8 * RPW - 1) / (8 * RPW);
+    switch (op.dtype_out) {
+      case CAPF_F32: launch_k(layernorm_narrow_kernel<float, RPW>, dim3(nb), dim3(256), 0, st, rows, D, period, op.f[0], x, g, b, x0, (float*)op.out[0]); break;
+      case CAPF_F16: launch_k(layernorm_narrow_kernel<__half, RPW>, dim3(nb), dim3(256), 0, st, rows, D, period, op.f[0], x, g, b, x0, (__half*)op.out[0]); break;
+      case CAPF_BF16: launch_k(layernorm_narrow_kernel<__nv_bfloat16, RPW>, dim3(nb), dim3(256), 0, st, rows, D, period, op.f[0], x, g, b, x0, (__nv_bfloat16*)op.out[0]); break;
+      default: return set_error(CAPF_ERR_UNSUPPORTED, "layernorm: dtype_out");
+    }
+    return check_launch("layernorm_narrow");
+  }
   switch (op.dtype_out) {
     case CAPF_F32: launch_k(layernorm_kernel<float, 8>, dim3(blocks), dim3(256), 0, st, rows, D, period, op.f[0], x, g, b, x0, (float*)op.out[0]); break;
     case CAPF_F16: launch_k(layernorm_kernel<__half, 8>, dim3(blocks), dim3(256), 0, st, rows, D, period, op.f[0], x, g, b, x0, (__half*)op.out[0]); break;

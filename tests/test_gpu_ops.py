@@ -132,14 +132,16 @@ def test_bilinear_16bit_vector_path(dt):
         assert rel_l2(out.float().cpu(), want) < (5e-4 if dt == torch.float16 else 4e-3)
 
 
-@pytest.mark.parametrize("D,period", [(128, 0), (640, 0), (128, 34)])
-def test_layernorm(D, period):
+@pytest.mark.parametrize("D,period", [(128, 0), (640, 0), (128, 34), (96, 0), (64, 17), (480, 0), (320, 0)])
+@pytest.mark.parametrize("rows", [136, 137, 3])
+def test_layernorm(D, period, rows):
+    """Wide rows (one warp per row), narrow rows (D <= 128: four rows per warp, ragged row counts), the x + x0 broadcast
+    of DeformableBlock (:120), and the MPI-INF-3DHP widths that are not multiples of 128."""
     g = _gen(4)
-    rows = 136
     x = torch.randn(rows, D, generator=g) * 3 + 1
     gamma, beta = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g)
     x0 = torch.randn(period, D, generator=g) if period else None
-    xin = x + (x0.repeat(rows // period, 1) if period else 0)
+    xin = x + (x0.repeat((rows + period - 1) // period, 1)[:rows] if period else 0)
     for eps in (1e-5, 1e-6):
         want = F.layer_norm(xin, (D,), gamma, beta, eps)
         out = torch.empty(rows, D, device=DEV)
