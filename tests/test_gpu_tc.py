@@ -51,6 +51,32 @@ def test_two_cta_gemm_matches_fp32_reference(case, dt):
     assert bad_rows == 0.0 and rel < tol
 
 
+def test_two_cta_gemm_at_benchmark_size_is_deterministic():
+    """QKV-sized GEMM on CTA pairs (every pair busy for two tiles, both accumulator stages, remote accumulator release):
+    repeated launches agree bit for bit and match the 1-CTA kernel to output rounding."""
+    import ctypes
+    from capf_b200 import lib
+    M, K, N = 4352, 640, 1920
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    outs = []
+    for two in (2, 2, 2, 1):
+        out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        op = lib.CapfOp()
+        op.kind, op.dtype_in, op.dtype_out = lib.OP_CONV2D, lib.F16, lib.F16
+        for n, v in enumerate([M, 1, 1, K, N, 1, 1, 1, 0, 1, 1, lib.ACT_NONE, lib.IMPL_TCGEN05, 0, 0, 0, 0, two]):
+            op.i[n] = v
+        op.inp[0], op.inp[1], op.inp[2] = a.data_ptr(), w.data_ptr(), bias.data_ptr()
+        op.out[0] = out.data_ptr()
+        lib.check(lib.load().capf_op_run(ctypes.byref(op), 0, torch.cuda.current_stream().cuda_stream), "linear")
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert (outs[0].float() - outs[3].float()).abs().max().item() <= 8e-3      # one fp16 rounding step at |y| <= 8
+
+
 @pytest.mark.parametrize("bn", [16, 48, 80, 240], ids=lambda v: f"bn{v}")
 def test_two_cta_gemm_column_tiles(bn):
     case = ("rows2_bn_sweep", (1100, 1, 1, 128, 240, 1, 1), 0, True, False)
