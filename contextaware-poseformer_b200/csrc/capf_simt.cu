@@ -1299,7 +1299,9 @@ __global__ void __launch_bounds__(256, 3) deform_sample16_kernel(SampP p, const 
   const long long warp = (long long)blockIdx.x * 8 + wib;
   const int R = p.B * p.J;
   if (warp >= (long long)R * p.nl) return;
-  const int rj = (int)(warp / p.nl), l = (int)(warp - (long long)rj * p.nl);   // level fastest: every block mixes light and heavy levels
+  // level-major, widest level first: the warps of a block do equal work (a block lives as long as its slowest warp; C = 256
+  // gathers 8x the bytes of C = 32) and the long blocks are scheduled before the short ones
+  const int l = p.nl - 1 - (int)(warp / R), rj = (int)(warp % R);
   const int b = rj / p.J;
   const int H = p.H[l], W = p.W[l], C = p.C[l];
   const float* row = ow + ((size_t)l * R + rj) * 48;
