@@ -541,6 +541,19 @@ def op_clocks(prog: Program):
 # ------------------------------------------------------------------------------------------------------
 # memory planning: greedy reuse of dead activation buffers (exact-size pools)
 # ------------------------------------------------------------------------------------------------------
+def _dying_residual(op, k, last_use, keep_alive):
+    """The root buffer of op's residual operand if this conv / Linear is its last reader and it may be overwritten."""
+    if op.kind != lib.OP_CONV2D or len(op.ins) < 4 or not isinstance(op.ins[3], Buf) or not op.outs:
+        return None
+    res = op.ins[3]
+    root = res.root
+    if (last_use.get(root) != k or root in keep_alive or res.root_offset != 0 or res.numel * _ITEMSIZE[res.dtype] != root.nbytes
+            or any(isinstance(x, Buf) and x.root is root for n, x in enumerate(op.ins) if n != 3)
+            or any(isinstance(o, Buf) and o.root is root for o in op.outs)):
+        return None
+    return root
+
+
 def plan_memory(prog: Program):
     """Returns (assignment: root Buf -> pool slot id, slots: list of (nbytes)).
 
@@ -556,9 +569,19 @@ def plan_memory(prog: Program):
     assign, slots, free = {}, [], {}
     slot_users = []                 # slot -> per-lane latest op index that touched it
     for k, op in enumerate(prog.ops):
+        donor = _dying_residual(op, k, last_use, keep_alive)
         for b in op.outs:
             if isinstance(b, Buf) and b.root not in assign:
                 r = b.root
+                if (donor is not None and r not in keep_alive and r.nbytes == donor.nbytes and b.root_offset == 0
+                        and all(vc[k][l] >= slot_users[assign[donor]][l] for l in range(MAX_LANES))):
+                    # y = act(conv(x) + res) with res read for the last time here: update res in place.  Every kernel
+                    # reads a residual element in the thread group that later writes it (tests: residual_updated_in_place),
+                    # and the write then lands on lines the read just brought into L2.
+                    assign[r] = assign[donor]
+                    last_use[donor] = -1                      # the slot now belongs to the output; do not free it below
+                    donor = None
+                    continue
                 pool = free.get(r.nbytes, [])
                 pick = None
                 if r not in keep_alive:

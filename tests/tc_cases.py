@@ -53,8 +53,9 @@ HALO_CASES = [
 ]
 
 
-def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=0, two=0):
-    """Returns (rel_l2, max_abs, frac_bad_rows) of the tcgen05 kernel against the fp32 reference."""
+def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=0, two=0, inplace=False):
+    """Returns (rel_l2, max_abs, frac_bad_rows) of the tcgen05 kernel against the fp32 reference.
+    inplace: the output buffer IS the residual buffer (how plan_memory runs a residual whose last reader is this op)."""
     name, (N, H, W, Cin, Cout, k, stride), act, use_res, out_f32 = case
     g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % (1 << 31))
     pad = k // 2
@@ -84,8 +85,12 @@ def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=
     else:
         wp = w.permute(2, 3, 1, 0).reshape(-1, Cout).contiguous().to(dt).to(DEV)
     out = torch.full((N, Ho, Wo, Cout), float("nan"), dtype=odt, device=DEV)
+    res_dev = res.to(odt).to(DEV) if use_res else None
+    if inplace:
+        assert use_res
+        out = res_dev
     run_op(lib.OP_CONV2D, dt, odt, [N, H, W, Cin, Cout, k, k, stride, pad, Ho, Wo, act, impl, variant, epi, msub, bn, two], [],
-           [x.to(dt).to(DEV), wp, bias.to(DEV), res.to(odt).to(DEV) if use_res else None], [out])
+           [x.to(dt).to(DEV), wp, bias.to(DEV), res_dev], [out])
     o = out.float()
     diff = (o - y)
     bad = ~torch.isfinite(o)

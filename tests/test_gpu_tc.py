@@ -94,6 +94,28 @@ def test_tc_gemm_column_tiles(bn):
         assert bad == 0.0 and rel < 1.5e-3, (msub, bn, rel)
 
 
+INPLACE_CASES = [   # (case, variant, two): every kernel a residual conv / Linear of the program can be dispatched to
+    (("inplace_layer1_conv3", (6, 64, 64, 64, 256, 1, 1), 1, True, False), 0, 0),
+    (("inplace_conv3_c128", (9, 16, 16, 128, 128, 3, 1), 1, True, False), 1, 0),
+    (("inplace_conv3_c256", (7, 8, 8, 256, 256, 3, 1), 1, True, False), 1, 0),
+    (("inplace_halo_c64", (150, 32, 32, 64, 64, 3, 1), 1, True, False), 2, 0),
+    (("inplace_halo_c32", (40, 64, 64, 32, 32, 3, 1), 1, True, False), 2, 0),
+    (("inplace_halo_c48_odd", (3, 9, 7, 48, 48, 3, 1), 1, True, False), 2, 0),
+    (("inplace_two_cta_f32", (4352, 1, 1, 640, 640, 1, 1), 0, True, True), 0, 2),
+]
+
+
+@pytest.mark.parametrize("spec", INPLACE_CASES, ids=[c[0][0] for c in INPLACE_CASES])
+def test_residual_updated_in_place(spec):
+    """out aliases the residual (plan_memory hands a dying residual's slot to the op's output): every epilogue reads a
+    residual element before the same thread group overwrites it, on all three kernels."""
+    case, variant, two = spec
+    for dt in (torch.float16, torch.bfloat16):
+        rel, max_abs, bad_rows = run_tc_case(case, dt, variant=variant, two=two, inplace=True)
+        tol = 2e-5 if case[4] else (1.5e-3 if dt == torch.float16 else 8e-3)
+        assert bad_rows == 0.0 and rel < tol, (case[0], dt, rel, max_abs)
+
+
 def test_tc_gemm_in_place_residual_at_benchmark_size():
     """x += Linear(t) in place on the fp32 token stream (pose_dformer.py:77-78 as the lifter runs it), every SM busy;
     repeated launches from the same input agree bit for bit and match the fp32 reference."""

@@ -35,6 +35,8 @@ def main():
     op.dtype_out = lib.F32 if f32out else lib.F16
     for n, v in enumerate([N, H, W, Cin, Cout, k, k, stride, pad, Ho, Wo, lib.ACT_RELU, lib.IMPL_TCGEN05, variant]):
         op.i[n] = v
+    op.i[15] = int(os.environ.get("ONE_MSUB", "0"))      # tile hints (0 = chooser)
+    op.i[16] = int(os.environ.get("ONE_BN", "0"))
     op.inp[0], op.inp[1], op.inp[2] = x.data_ptr(), w.data_ptr(), bias.data_ptr()
     op.inp[3] = res.data_ptr() if use_res else None
     op.out[0] = out.data_ptr()
