@@ -69,6 +69,7 @@ static int dispatch(const capf_op& op, const TcConvState* tc, cudaStream_t st) {
     case CAPF_OP_CROP_NORMALIZE: return launch_crop_normalize(op, st);
     case CAPF_OP_CAST: return launch_cast(op, st);
     case CAPF_OP_PREPROCESS_U8: return launch_preprocess_u8(op, st);
+    case CAPF_OP_WARP_AFFINE_U8: return launch_warp_affine_u8(op, st);
     default: return set_errorf(CAPF_ERR_ARG, "unknown op kind %d", op.kind);
   }
 }
@@ -183,6 +184,7 @@ int capf_plan_op_kernel(const capf_plan* plan, int k, char* buf, int cap) {
     case CAPF_OP_CROP_NORMALIZE: snprintf(buf, cap, "crop_normalize_kernel"); break;
     case CAPF_OP_CAST: snprintf(buf, cap, "cast_kernel"); break;
     case CAPF_OP_PREPROCESS_U8: snprintf(buf, cap, "preprocess_u8_kernel"); break;
+    case CAPF_OP_WARP_AFFINE_U8: snprintf(buf, cap, "warp_affine_u8_kernel"); break;
     default: snprintf(buf, cap, "?");
   }
   return CAPF_OK;

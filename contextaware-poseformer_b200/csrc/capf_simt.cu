@@ -1561,4 +1561,82 @@ int launch_preprocess_u8(const capf_op& op, cudaStream_t st) {
   return check_launch("preprocess_u8");
 }
 
+// =======================================================================================================
+// crop_image (mvn/utils/img.py:51-69): cv2.warpAffine(image, trans, (Wo, Ho), flags=INTER_LINEAR) on uint8 BGR frames,
+// constant (0) border -- the per-frame CPU work of Human36MSingleViewDataset.__getitem__ (human36m.py:554-584).
+// OpenCV's algorithm (imgproc/imgwarp.cpp, WarpAffineInvoker + remapBilinear, restated from its published source; the
+// restatement is pinned against cv2 itself in oracle/capf_oracle.py::warp_affine_u8) is integer past the first step:
+//   X = (round((M1*y + M2) * 1024) + 16 + round(M0*x*1024)) >> 5      (source x in 1/32 pixel; Y alike with M3..M5)
+//   corner (X >> 5, Y >> 5), weights (32-fx, fx) x (32-fy, fy) with fx = X & 31, fy = Y & 31 (sum 1024)
+//   value = (sum of corner * weight + 512) >> 10, corners outside the frame count as 0
+// where M is the INVERSE (crop -> frame) map in fp64 and round() is round-half-even.  The fp64 products are formed
+// with explicit _rn intrinsics so that no FMA contraction changes a rounding.  Result: the same bytes as cv2.
+// mode 1 writes the normalised fp32 RGB pixel of data_prefetcher.preload instead (optionally mirrored along W), i.e.
+// crop + CAPF_OP_PREPROCESS_U8 in one pass without the uint8 round trip.
+// =======================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(256) warp_affine_u8_kernel(int Hs, int Ws, int Ho, int Wo, unsigned total, int mirror, int apply_std,
+                                                             const uint8_t* __restrict__ frames, const double* __restrict__ minv,
+                                                             const int* __restrict__ sizes, const float* __restrict__ ms, void* __restrict__ outp) {
+  pdl_wait();
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= total) return;
+  const unsigned per = (unsigned)(Ho * Wo);
+  const unsigned b = i / per, r = i - b * per;
+  const int y = (int)(r / (unsigned)Wo), xo = (int)(r - (unsigned)y * (unsigned)Wo);
+  const int x = (MODE == 1 && mirror) ? (Wo - 1 - xo) : xo;          // crop column this output pixel shows
+  const double* M = minv + 6 * (size_t)b;
+  const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(M[0], (double)x), 1024.0));
+  const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(M[3], (double)x), 1024.0));
+  const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]), 1024.0)) + 16;
+  const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[4], (double)y), M[5]), 1024.0)) + 16;
+  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));     // saturate_cast<short>
+  const int fx = X & 31, fy = Y & 31;
+  const int h = sizes ? sizes[2 * b] : Hs, w = sizes ? sizes[2 * b + 1] : Ws;               // live part of the padded frame
+  const uint8_t* f = frames + (size_t)b * Hs * Ws * 3;
+  int v[3] = {0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int yy = sy + (c >> 1), xx = sx + (c & 1);
+    const int wgt = ((c & 1) ? fx : 32 - fx) * ((c >> 1) ? fy : 32 - fy);
+    if (wgt != 0 && yy >= 0 && yy < h && xx >= 0 && xx < w) {
+      const uint8_t* px = f + ((size_t)yy * Ws + xx) * 3;
+      v[0] += wgt * (int)__ldg(px);
+      v[1] += wgt * (int)__ldg(px + 1);
+      v[2] += wgt * (int)__ldg(px + 2);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] = (v[c] + 512) >> 10;
+  if (MODE == 0) {
+    uint8_t* o = reinterpret_cast<uint8_t*>(outp) + (size_t)i * 3;
+    o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
+  } else {
+    float* o = reinterpret_cast<float*>(outp) + (size_t)i * 3;
+    o[0] = prep_px((uint8_t)v[2], __ldg(ms), __ldg(ms + 3), apply_std);        // R <- byte 2
+    o[1] = prep_px((uint8_t)v[1], __ldg(ms + 1), __ldg(ms + 4), apply_std);
+    o[2] = prep_px((uint8_t)v[0], __ldg(ms + 2), __ldg(ms + 5), apply_std);    // B <- byte 0
+  }
+}
+
+int launch_warp_affine_u8(const capf_op& op, cudaStream_t st) {
+  const int B = op.i[0], Hs = op.i[1], Ws = op.i[2], Ho = op.i[3], Wo = op.i[4], mode = op.i[5];
+  if (B <= 0 || Hs <= 0 || Ws <= 0 || Ho <= 0 || Wo <= 0 || !op.in[0] || !op.in[1] || !op.out[0]) return set_error(CAPF_ERR_ARG, "warp_affine_u8: bad arguments");
+  if (mode != 0 && mode != 1) return set_error(CAPF_ERR_ARG, "warp_affine_u8: mode must be 0 (uint8 crop) or 1 (normalised fp32)");
+  if (mode == 1 && !op.in[3]) return set_error(CAPF_ERR_ARG, "warp_affine_u8: mode 1 needs the mean/std vector");
+  if (Hs > 32767 || Ws > 32767) return set_error(CAPF_ERR_UNSUPPORTED, "warp_affine_u8: frames larger than 32767 pixels a side (OpenCV's own limit)");
+  if (((uintptr_t)op.in[1]) & 7) return set_error(CAPF_ERR_ARG, "warp_affine_u8: matrices must be 8-byte aligned fp64");
+  const long long total = (long long)B * Ho * Wo;
+  if (total >= (1ll << 32)) return set_error(CAPF_ERR_UNSUPPORTED, "warp_affine_u8: too many output pixels");
+  const dim3 grid((unsigned)((total + 255) / 256));
+  if (mode == 0)
+    launch_k(warp_affine_u8_kernel<0>, grid, dim3(256), 0, st, Hs, Ws, Ho, Wo, (unsigned)total, 0, 0, (const uint8_t*)op.in[0], (const double*)op.in[1],
+             (const int*)op.in[2], (const float*)nullptr, (void*)op.out[0]);
+  else
+    launch_k(warp_affine_u8_kernel<1>, grid, dim3(256), 0, st, Hs, Ws, Ho, Wo, (unsigned)total, op.i[6] ? 1 : 0, op.i[7] ? 1 : 0, (const uint8_t*)op.in[0],
+             (const double*)op.in[1], (const int*)op.in[2], (const float*)op.in[3], (void*)op.out[0]);
+  return check_launch("warp_affine_u8");
+}
+
 }  // namespace capf

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 6
+#define CAPF_ABI_VERSION 7
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -59,7 +59,8 @@ typedef enum capf_op_kind {
   CAPF_OP_CROP_NORMALIZE = 11,
   CAPF_OP_CAST = 12,
   CAPF_OP_PREPROCESS_U8 = 13,
-  CAPF_OP_BASICBLOCK = 14
+  CAPF_OP_BASICBLOCK = 14,
+  CAPF_OP_WARP_AFFINE_U8 = 15
 } capf_op_kind;
 
 /*
@@ -154,6 +155,17 @@ typedef enum capf_op_kind {
  *                    with the torch expression), optionally mirrored along W (torch.flip(images, [2])).
  *     i[0..2]=B,H,W  i[3]=mirror(0|1)  i[4]=apply_std(1: HRNet, 0: CPN `x / 255 - mean`)
  *     in[0]=uint8 [B,H,W,3] (B,G,R)  in[1]=f32[6] device: mean R,G,B then std R,G,B   out[0]=f32 [B,H,W,3] (R,G,B)
+ *
+ * CAPF_OP_WARP_AFFINE_U8 -- crop_image (mvn/utils/img.py:51-69): cv2.warpAffine(frame, trans, (Wo, Ho), INTER_LINEAR),
+ *                    constant 0 border, on a batch of uint8 HWC frames; the same bytes as OpenCV (1/32-pixel source
+ *                    coordinates, 10-bit weights, round-half-up of the weighted sum).  The host passes the INVERSE
+ *                    (crop -> frame) 2x3 matrices in fp64, computed from `trans` as OpenCV does (host mirror:
+ *                    mvn/utils/img.py::invert_affine).  Frames share one padded [Hs,Ws] storage; in[2] optionally gives
+ *                    each frame's live (h, w) -- Human3.6M cameras deliver 1000x1000 and 1002x1000.
+ *     i[0]=B  i[1..2]=Hs,Ws  i[3..4]=Ho,Wo  i[5]=mode  (mode 1 only: i[6]=mirror along W, i[7]=apply_std)
+ *     in[0]=uint8 [B,Hs,Ws,3]  in[1]=f64 [B,6] device  in[2]=int32 [B,2] (h,w) device or NULL  in[3]=f32[6] mean|std (mode 1)
+ *     out[0]: mode 0 = uint8 [B,Ho,Wo,3] (channel order kept); mode 1 = f32 [B,Ho,Wo,3] RGB normalised like
+ *             CAPF_OP_PREPROCESS_U8 applied to the mode-0 result (crop + data_prefetcher.preload in one pass)
  */
 typedef struct capf_op {
   int32_t kind;

@@ -356,3 +356,75 @@ def flip_test_merge(pred, pred_flip):
     pred_flip[:, :, :, 0] *= -1
     pred_flip[:, :, JOINTS_LEFT + JOINTS_RIGHT] = pred_flip[:, :, JOINTS_RIGHT + JOINTS_LEFT]
     return torch.mean(torch.cat((pred, pred_flip), dim=1), dim=1, keepdim=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# f4: crop_image (mvn/utils/img.py:16-69) -- the per-frame CPU work of Human36MSingleViewDataset.__getitem__
+# (human36m.py:554-584).  The arithmetic lives in OpenCV (cv2.getAffineTransform / cv2.warpAffine; opencv-python is a
+# reference dependency, 4.13.0 in this image): restated from its published algorithm (imgproc/imgwarp.cpp,
+# WarpAffineInvoker + remapBilinear with the 15-bit bilinear table) and PINNED two ways: tests/golden/crop_cases.npz
+# holds outputs of the reference's own crop_image (oracle/gen_golden_crop.py), and tests/test_crop.py compares against
+# cv2.warpAffine directly wherever cv2 imports.
+# ------------------------------------------------------------------------------------------------------
+def affine_transform(center, scale, output_size):
+    """get_affine_transform(center, scale, 0, output_size) (img.py:16-48): the 2x3 frame -> crop map through three point
+    pairs held in float32, solved in float64 like cv2.getAffineTransform."""
+    center = np.array(center)
+    scale_tmp = np.array(scale) * 200.0
+    src_w, dst_w, dst_h = scale_tmp[0], output_size[0], output_size[1]
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0] = center
+    src[1] = center + np.array([0, (src_w - 1) * -0.5], np.float32)
+    dst[0] = [(dst_w - 1) * 0.5, (dst_h - 1) * 0.5]
+    dst[1] = np.array([(dst_w - 1) * 0.5, (dst_h - 1) * 0.5]) + np.array([0, (dst_w - 1) * -0.5], np.float32)
+    for p in (src, dst):                                   # get_3rd_point: b + (-(a-b).y, (a-b).x), float32
+        d = p[0] - p[1]
+        p[2] = p[1] + np.array([-d[1], d[0]], dtype=np.float32)
+    a = np.zeros((6, 6))
+    b = np.zeros(6)
+    for i in range(3):
+        a[i, 0:2], a[i, 2] = src[i], 1.0
+        a[i + 3, 3:5], a[i + 3, 5] = src[i], 1.0
+        b[i], b[i + 3] = dst[i, 0], dst[i, 1]
+    return np.linalg.solve(a, b).reshape(2, 3)
+
+
+def invert_affine(trans):
+    """The crop -> frame map cv2.warpAffine derives from `trans` (no WARP_INVERSE_MAP), same operation order, float64."""
+    m = np.array(trans, dtype=np.float64).reshape(6).copy()
+    d = m[0] * m[4] - m[1] * m[3]
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22 = m[4] * d, m[0] * d
+    m[0], m[1], m[3], m[4] = a11, m[1] * -d, m[3] * -d, a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return m
+
+
+def warp_affine_u8(image, trans, dsize):
+    """cv2.warpAffine(image, trans, dsize, flags=cv2.INTER_LINEAR) for uint8 HWC images, constant 0 border: bit-exact."""
+    wo, ho = int(dsize[0]), int(dsize[1])
+    m = invert_affine(trans)
+    rnd = lambda v: np.rint(v).astype(np.int64)            # cvRound: half to even
+    x, y = np.arange(wo), np.arange(ho)
+    adelta, bdelta = rnd(m[0] * x * 1024), rnd(m[3] * x * 1024)
+    x0, y0 = rnd((m[1] * y + m[2]) * 1024) + 16, rnd((m[4] * y + m[5]) * 1024) + 16
+    xf, yf = (x0[:, None] + adelta[None, :]) >> 5, (y0[:, None] + bdelta[None, :]) >> 5
+    sx, sy = np.clip(xf >> 5, -32768, 32767), np.clip(yf >> 5, -32768, 32767)
+    fx, fy = (xf & 31)[..., None], (yf & 31)[..., None]
+    h, w = image.shape[:2]
+
+    def corner(yy, xx):
+        ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+        return image[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)].astype(np.int64) * ok[..., None]
+
+    t = (corner(sy, sx) * ((32 - fx) * (32 - fy)) + corner(sy, sx + 1) * (fx * (32 - fy))
+         + corner(sy + 1, sx) * ((32 - fx) * fy) + corner(sy + 1, sx + 1) * (fx * fy))
+    return ((t + 512) >> 10).astype(np.uint8)
+
+
+def crop_image(image, center, scale, output_size):
+    """img.py:51-69."""
+    return warp_affine_u8(image, affine_transform(center, scale, output_size), output_size)
