@@ -14,6 +14,7 @@ of 2*B frames (frames are independent), i.e. one CUDA graph launch instead of tw
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import lib
@@ -91,6 +92,30 @@ def flip_test_forward(model, images_u8: torch.Tensor, kp2d: torch.Tensor, kp2d_c
     static = model.static_inputs(2 * B, H, W, dev)["images"]          # write both halves straight into the plan's input
     preprocess(images_u8, backbone, mirror=False, out=static[:B])
     preprocess(images_u8, backbone, mirror=True, out=static[B:])
+    kf, cf = flip_keypoints(kp2d.float(), kp2d_crop.float())
+    kp2 = torch.cat([kp2d.float(), kf], dim=0)
+    crop2 = torch.cat([kp2d_crop.float().clone(), cf], dim=0)
+    pred2 = model(static, kp2, crop2)
+    return merge_flip_test(pred2[:B], pred2[B:])
+
+
+def flip_test_forward_from_frames(model, frames_u8: torch.Tensor, trans, kp2d: torch.Tensor, kp2d_crop: torch.Tensor,
+                                  sizes: torch.Tensor = None, image_shape=(CROP_WIDTH, 256)) -> torch.Tensor:
+    """The whole per-batch chain of an evaluation step from decoded camera frames: crop_image (human36m.py:569-571) +
+    data_prefetcher.preload(flip_test=True) + both model calls + merge (train.py:170-181).
+
+    frames_u8: uint8 [B,Hs,Ws,3] BGR on the GPU (as cv2.imread delivers them), trans: [B,2,3] frame -> crop maps
+    (mvn.utils.img.get_affine_transform(center, scale, 0, image_shape)), image_shape = (W, H) of the crop.  Two kernels
+    write the straight and the mirrored normalised crops into the plan's input; nothing uint8 or fp32 is staged between."""
+    from .mvn.utils import img
+    B = frames_u8.shape[0]
+    dev = frames_u8.device
+    wo, ho = int(image_shape[0]), int(image_shape[1])
+    backbone = model.backbone_type
+    static = model.static_inputs(2 * B, ho, wo, dev)["images"]
+    minv = torch.from_numpy(np.stack([img.invert_affine(t) for t in np.asarray(trans, dtype=np.float64).reshape(B, 2, 3)])).to(dev)
+    img.crop_images(frames_u8, None, image_shape, sizes=sizes, normalise=backbone, mirror=False, out=static[:B], minv=minv)
+    img.crop_images(frames_u8, None, image_shape, sizes=sizes, normalise=backbone, mirror=True, out=static[B:], minv=minv)
     kf, cf = flip_keypoints(kp2d.float(), kp2d_crop.float())
     kp2 = torch.cat([kp2d.float(), kf], dim=0)
     crop2 = torch.cat([kp2d_crop.float().clone(), cf], dim=0)

@@ -82,3 +82,28 @@ def test_flip_test_forward_matches_two_pass_reference_recipe():
     want = capf_oracle.flip_test_merge(preds[0], preds[1])
     rel = float((got.cpu() - want).norm() / want.norm())
     assert got.shape == (B, 1, 17, 3) and rel < 1e-4, rel
+
+
+@pytest.mark.gpu
+def test_flip_test_forward_from_frames_equals_crop_then_flip_test():
+    """Camera frames -> prediction in one call == crop_image on every frame (bit-exact with cv2, tests/test_crop.py)
+    followed by the flip-test forward from uint8 crops."""
+    import numpy as np
+    from capf_b200.mvn.utils import img as host
+    B = 3
+    cfg = capf_b200.make_config("hrnet_32")
+    model = capf_b200.CA_PF(cfg, precision="fp16").eval()
+    w = protocol.make_weights([(k, tuple(v.shape)) for k, v in model.state_dict().items()], 4)
+    model.load_state_dict(w, strict=True)
+    model = model.cuda()
+    g = torch.Generator().manual_seed(8)
+    frames = torch.randint(0, 256, (B, 150, 170, 3), generator=g, dtype=torch.uint8).cuda()
+    sizes = torch.tensor([[150, 170], [148, 170], [150, 160]], dtype=torch.int32).cuda()
+    trans = np.stack([host.get_affine_transform(np.float32([80 + 5 * b, 70 - 3 * b]), np.float32([0.45, 0.6]), 0, (96, 128)) for b in range(B)])
+    kp = (torch.rand(B, 17, 2, generator=g) * 2 - 1).cuda()
+    crop = (torch.rand(B, 17, 2, generator=g) * torch.tensor([191.0, 255.0])).cuda()
+    with torch.no_grad():
+        got = frontend.flip_test_forward_from_frames(model, frames, trans, kp, crop, sizes=sizes, image_shape=(96, 128)).clone()
+        crops_u8 = host.crop_images(frames, trans, (96, 128), sizes=sizes)
+        want = frontend.flip_test_forward(model, crops_u8, kp, crop)
+    assert got.shape == (B, 1, 17, 3) and torch.isfinite(got).all() and torch.equal(got, want)
