@@ -70,6 +70,7 @@ static int dispatch(const capf_op& op, const TcConvState* tc, cudaStream_t st) {
     case CAPF_OP_CAST: return launch_cast(op, st);
     case CAPF_OP_PREPROCESS_U8: return launch_preprocess_u8(op, st);
     case CAPF_OP_WARP_AFFINE_U8: return launch_warp_affine_u8(op, st);
+    case CAPF_OP_POSE_ERRORS: return launch_pose_errors(op, st);
     default: return set_errorf(CAPF_ERR_ARG, "unknown op kind %d", op.kind);
   }
 }
@@ -185,6 +186,7 @@ int capf_plan_op_kernel(const capf_plan* plan, int k, char* buf, int cap) {
     case CAPF_OP_CAST: snprintf(buf, cap, "cast_kernel"); break;
     case CAPF_OP_PREPROCESS_U8: snprintf(buf, cap, "preprocess_u8_kernel"); break;
     case CAPF_OP_WARP_AFFINE_U8: snprintf(buf, cap, "warp_affine_u8_kernel"); break;
+    case CAPF_OP_POSE_ERRORS: snprintf(buf, cap, "pose_errors_kernel"); break;
     default: snprintf(buf, cap, "?");
   }
   return CAPF_OK;

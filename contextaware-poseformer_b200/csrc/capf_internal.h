@@ -26,6 +26,7 @@ int launch_crop_normalize(const capf_op& op, cudaStream_t st);
 int launch_cast(const capf_op& op, cudaStream_t st);
 int launch_preprocess_u8(const capf_op& op, cudaStream_t st);
 int launch_warp_affine_u8(const capf_op& op, cudaStream_t st);
+int launch_pose_errors(const capf_op& op, cudaStream_t st);
 
 // tensor-pipe HRNet stem conv1 (capf_stem.cu): fp32 NHWC image -> 64 channels, 3x3 / stride 2
 int stem_tc_supported(const capf_op& op);

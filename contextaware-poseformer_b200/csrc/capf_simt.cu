@@ -1639,4 +1639,166 @@ int launch_warp_affine_u8(const capf_op& op, cudaStream_t st) {
   return check_launch("warp_affine_u8");
 }
 
+// =======================================================================================================
+// Evaluation errors per frame (mvn/models/loss.py:16-22 MPJPE, :25-68 P_MPJPE, :87-101 MPJVE; reduced per action by
+// evaluate_using_pred, mvn/datasets/human36m.py:358-422).  One thread per frame, fp64 inside:
+//   out[n][0] = mean_j |pred - gt|
+//   out[n][1] = the same after the similarity (scale, rotation, translation) that best maps pred onto gt.  The reference
+//               takes numpy's SVD of H = X0^T Y0; here V and the singular values come from a Jacobi eigen-decomposition
+//               of H^T H and U from H V, with u3 = u1 x u2 and v3 = v1 x v2, which makes R = V U^T a proper rotation and
+//               gives the third singular value the sign the reference's det(R) fix-up produces.
+//   out[n][2] = mean_j |(pred_n - pred_p) - (gt_n - gt_p)| with p = prev[n] (the frame before n inside its action, the
+//               np.diff of the action-masked sequence), 0 when prev[n] < 0.
+// =======================================================================================================
+__device__ __forceinline__ void jacobi_rot(double (&a)[3][3], double (&v)[3][3], int p, int q) {
+  if (fabs(a[p][q]) < 1e-300) return;
+  const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+  const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {            // A <- A J
+    const double akp = a[k][p], akq = a[k][q];
+    a[k][p] = c * akp - sn * akq;
+    a[k][q] = sn * akp + c * akq;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {            // A <- J^T A
+    const double apk = a[p][k], aqk = a[q][k];
+    a[p][k] = c * apk - sn * aqk;
+    a[q][k] = sn * apk + c * aqk;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {            // V <- V J
+    const double vkp = v[k][p], vkq = v[k][q];
+    v[k][p] = c * vkp - sn * vkq;
+    v[k][q] = sn * vkp + c * vkq;
+  }
+}
+
+__global__ void __launch_bounds__(128) pose_errors_kernel(int n_frames, int J, const float* __restrict__ pred, const float* __restrict__ gt,
+                                                          const int* __restrict__ prev, double* __restrict__ out) {
+  pdl_wait();
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  if (n >= n_frames) return;
+  const float* Y = pred + (size_t)n * J * 3;
+  const float* X = gt + (size_t)n * J * 3;
+  double mx[3] = {0, 0, 0}, my[3] = {0, 0, 0}, e1 = 0;
+  for (int j = 0; j < J; ++j) {
+    double d2 = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double x = X[3 * j + c], y = Y[3 * j + c];
+      mx[c] += x; my[c] += y;
+      d2 += (y - x) * (y - x);
+    }
+    e1 += sqrt(d2);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { mx[c] /= J; my[c] /= J; }
+  double nx = 0, ny = 0, h[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < J; ++j) {
+    double x[3], y[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { x[c] = X[3 * j + c] - mx[c]; y[c] = Y[3 * j + c] - my[c]; nx += x[c] * x[c]; ny += y[c] * y[c]; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) h[a][b] += x[a] * y[b];
+  }
+  nx = sqrt(nx); ny = sqrt(ny);
+  const double inv = 1.0 / (nx * ny);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) h[a][b] *= inv;          // H = X0^T Y0 of the normalised point sets
+  double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) A[a][b] = h[0][a] * h[0][b] + h[1][a] * h[1][b] + h[2][a] * h[2][b];
+  for (int sweep = 0; sweep < 10; ++sweep) { jacobi_rot(A, V, 0, 1); jacobi_rot(A, V, 0, 2); jacobi_rot(A, V, 1, 2); }
+  // order the two largest eigenvalues first
+  int i0 = 0, i1 = 1, i2 = 2;
+  if (A[i0][i0] < A[i1][i1]) { const int t = i0; i0 = i1; i1 = t; }
+  if (A[i0][i0] < A[i2][i2]) { const int t = i0; i0 = i2; i2 = t; }
+  if (A[i1][i1] < A[i2][i2]) { const int t = i1; i1 = i2; i2 = t; }
+  double v1[3], v2[3], v3[3], u1[3], u2[3], u3[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { v1[c] = V[c][i0]; v2[c] = V[c][i1]; }
+  v3[0] = v1[1] * v2[2] - v1[2] * v2[1]; v3[1] = v1[2] * v2[0] - v1[0] * v2[2]; v3[2] = v1[0] * v2[1] - v1[1] * v2[0];
+  auto mulH = [&](const double (&v)[3], double (&o)[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) o[a] = h[a][0] * v[0] + h[a][1] * v[1] + h[a][2] * v[2];
+  };
+  double hv1[3], hv2[3], hv3[3];
+  mulH(v1, hv1); mulH(v2, hv2); mulH(v3, hv3);
+  const double s1 = sqrt(hv1[0] * hv1[0] + hv1[1] * hv1[1] + hv1[2] * hv1[2]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) u1[c] = hv1[c] / s1;
+  const double d12 = u1[0] * hv2[0] + u1[1] * hv2[1] + u1[2] * hv2[2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) u2[c] = hv2[c] - d12 * u1[c];
+  double s2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+  if (s2 > 1e-150) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) u2[c] /= s2;
+  } else {                                  // rank-1 H (collinear points): any unit vector orthogonal to u1
+    s2 = 0;
+    const int k = fabs(u1[0]) < fabs(u1[1]) ? (fabs(u1[0]) < fabs(u1[2]) ? 0 : 2) : (fabs(u1[1]) < fabs(u1[2]) ? 1 : 2);
+    double e[3] = {0, 0, 0};
+    e[k] = 1.0;
+    const double d = u1[k];
+    double nn = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { u2[c] = e[c] - d * u1[c]; nn += u2[c] * u2[c]; }
+    nn = sqrt(nn);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) u2[c] /= nn;
+  }
+  u3[0] = u1[1] * u2[2] - u1[2] * u2[1]; u3[1] = u1[2] * u2[0] - u1[0] * u2[2]; u3[2] = u1[0] * u2[1] - u1[1] * u2[0];
+  const double s3 = u3[0] * hv3[0] + u3[1] * hv3[1] + u3[2] * hv3[2];        // signed: negative = the reflection case
+  double R[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) R[a][b] = v1[a] * u1[b] + v2[a] * u2[b] + v3[a] * u3[b];
+  const double scale = (s1 + s2 + s3) * nx / ny;
+  double t[3];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) t[b] = mx[b] - scale * (my[0] * R[0][b] + my[1] * R[1][b] + my[2] * R[2][b]);
+  double e2 = 0, e3 = 0;
+  const int p = prev ? prev[n] : -1;
+  const float* Yp = pred + (size_t)(p < 0 ? 0 : p) * J * 3;
+  const float* Xp = gt + (size_t)(p < 0 ? 0 : p) * J * 3;
+  for (int j = 0; j < J; ++j) {
+    const double y0 = Y[3 * j], y1 = Y[3 * j + 1], y2 = Y[3 * j + 2];
+    double d2 = 0, dv = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double al = scale * (y0 * R[0][b] + y1 * R[1][b] + y2 * R[2][b]) + t[b] - (double)X[3 * j + b];
+      d2 += al * al;
+      if (p >= 0) {
+        // the reference differences fp32 arrays (np.diff) before subtracting: keep those two roundings
+        const float vy = Y[3 * j + b] - Yp[3 * j + b], vx = X[3 * j + b] - Xp[3 * j + b];
+        const double w = (double)(vy - vx);
+        dv += w * w;
+      }
+    }
+    e2 += sqrt(d2);
+    e3 += sqrt(dv);
+  }
+  out[3 * (size_t)n] = e1 / J;
+  out[3 * (size_t)n + 1] = e2 / J;
+  out[3 * (size_t)n + 2] = p >= 0 ? e3 / J : 0.0;
+}
+
+int launch_pose_errors(const capf_op& op, cudaStream_t st) {
+  const int N = op.i[0], J = op.i[1];
+  if (N <= 0 || J < 3 || !op.in[0] || !op.in[1] || !op.out[0]) return set_error(CAPF_ERR_ARG, "pose_errors: bad arguments");
+  if (((uintptr_t)op.out[0]) & 7) return set_error(CAPF_ERR_ARG, "pose_errors: output must be 8-byte aligned fp64");
+  launch_k(pose_errors_kernel, dim3((unsigned)((N + 127) / 128)), dim3(128), 0, st, N, J, (const float*)op.in[0], (const float*)op.in[1], (const int*)op.in[2],
+           (double*)op.out[0]);
+  return check_launch("pose_errors");
+}
+
 }  // namespace capf

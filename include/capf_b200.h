@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 7
+#define CAPF_ABI_VERSION 8
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -60,7 +60,8 @@ typedef enum capf_op_kind {
   CAPF_OP_CAST = 12,
   CAPF_OP_PREPROCESS_U8 = 13,
   CAPF_OP_BASICBLOCK = 14,
-  CAPF_OP_WARP_AFFINE_U8 = 15
+  CAPF_OP_WARP_AFFINE_U8 = 15,
+  CAPF_OP_POSE_ERRORS = 16
 } capf_op_kind;
 
 /*
@@ -166,6 +167,13 @@ typedef enum capf_op_kind {
  *     in[0]=uint8 [B,Hs,Ws,3]  in[1]=f64 [B,6] device  in[2]=int32 [B,2] (h,w) device or NULL  in[3]=f32[6] mean|std (mode 1)
  *     out[0]: mode 0 = uint8 [B,Ho,Wo,3] (channel order kept); mode 1 = f32 [B,Ho,Wo,3] RGB normalised like
  *             CAPF_OP_PREPROCESS_U8 applied to the mode-0 result (crop + data_prefetcher.preload in one pass)
+ *
+ * CAPF_OP_POSE_ERRORS -- the per-frame terms of evaluate_using_pred (mvn/datasets/human36m.py:358-422): MPJPE
+ *                    (mvn/models/loss.py:16-22), P_MPJPE (:25-68, Procrustes-aligned) and MPJVE (:87-101) of frame n against
+ *                    the frame prev[n] that precedes it inside its action.  fp64 arithmetic, one row per frame; the host
+ *                    sums rows per action.
+ *     i[0]=N frames  i[1]=J joints
+ *     in[0]=pred f32 [N,J,3]  in[1]=gt f32 [N,J,3]  in[2]=int32 [N] prev (or NULL: no velocity term)   out[0]=f64 [N,3]
  */
 typedef struct capf_op {
   int32_t kind;

@@ -428,3 +428,57 @@ def warp_affine_u8(image, trans, dsize):
 def crop_image(image, center, scale, output_size):
     """img.py:51-69."""
     return warp_affine_u8(image, affine_transform(center, scale, output_size), output_size)
+
+
+# ------------------------------------------------------------------------------------------------------
+# f4: evaluation reducer -- evaluate_using_pred (mvn/datasets/human36m.py:358-422) over MPJPE / P_MPJPE / MPJVE
+# (mvn/models/loss.py:16-22, :25-68, :87-101).  Pinned by tests/golden/eval_cases.npz (oracle/gen_golden_eval.py ran the
+# reference's own method on seeded poses).
+# ------------------------------------------------------------------------------------------------------
+H36M_ACTIONS = ["Directions", "Discussion", "Eating", "Greeting", "Phoning", "Posing", "Purchases", "Sitting", "SittingDown",
+                "Smoking", "TakingPhoto", "Waiting", "Walking", "WalkingDog", "WalkingTogether"]
+H36M_ACTION_NAMES = [f"{a}-{t}" for a in H36M_ACTIONS for t in (1, 2)]       # human36m.py:18-33
+
+
+def mpjpe(pred, gt):
+    """loss.py:16-22 (torch, fp32)."""
+    return float(torch.mean(torch.norm(pred - gt, dim=len(gt.shape) - 1)))
+
+
+def p_mpjpe(pred, gt):
+    """loss.py:25-68 on numpy arrays [F,J,3] (fp32 in the reference's call, human36m.py:373)."""
+    mu_x, mu_y = np.mean(gt, axis=1, keepdims=True), np.mean(pred, axis=1, keepdims=True)
+    x0, y0 = gt - mu_x, pred - mu_y
+    norm_x = np.sqrt(np.sum(x0 ** 2, axis=(1, 2), keepdims=True))
+    norm_y = np.sqrt(np.sum(y0 ** 2, axis=(1, 2), keepdims=True))
+    x0, y0 = x0 / norm_x, y0 / norm_y
+    u, s, vt = np.linalg.svd(np.matmul(x0.transpose(0, 2, 1), y0))
+    v = vt.transpose(0, 2, 1)
+    sign = np.sign(np.expand_dims(np.linalg.det(np.matmul(v, u.transpose(0, 2, 1))), axis=1))
+    v[:, :, -1] *= sign
+    s[:, -1] *= sign.flatten()
+    r = np.matmul(v, u.transpose(0, 2, 1))
+    a = np.expand_dims(np.sum(s, axis=1, keepdims=True), axis=2) * norm_x / norm_y
+    t = mu_x - a * np.matmul(mu_y, r)
+    return np.mean(np.linalg.norm(a * np.matmul(pred, r) + t - gt, axis=len(gt.shape) - 1))
+
+
+def mpjve(pred, gt):
+    """loss.py:87-101."""
+    return np.mean(np.linalg.norm(np.diff(pred, axis=0) - np.diff(gt, axis=0), axis=len(gt.shape) - 1))
+
+
+def evaluate_using_pred(keypoints_gt, keypoints_3d_predicted, labels_action_idx, action_names=None):
+    """human36m.py:358-422: per-action scores with the two trials of an action merged (frame-count weighted)."""
+    action_names = action_names or H36M_ACTION_NAMES
+    scores = {}
+    for k, name in enumerate(action_names):
+        m = torch.from_numpy(labels_action_idx == k)
+        n = int(m.sum())
+        p, g = keypoints_3d_predicted[m], keypoints_gt[m]
+        pn, gn = p.squeeze().cpu().numpy(), g.squeeze().cpu().numpy()
+        scores[name] = {"MPJPE": n * mpjpe(p, g), "P_MPJPE": n * p_mpjpe(pn, gn), "MPJVE": n * mpjve(pn, gn), "frame_count": n}
+    for base in [x[:-2] for x in action_names if x.endswith("-1")]:
+        both = [scores.pop(f"{base}-{t}") for t in (1, 2)]
+        scores[base] = {k: both[0][k] + both[1][k] for k in both[0]}
+    return {k: {m: v[m] / v["frame_count"] for m in ("MPJPE", "P_MPJPE", "MPJVE")} for k, v in scores.items()}
