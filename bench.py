@@ -317,11 +317,13 @@ def run_native(args):
         ridge = peak_tf_sus * 1e12 / (peak_bw * 1e9)
         dom_tflops = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
         dom_gbps = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
-        traffic = None
+        traffic = traffic_detail = None          # measured DRAM bytes per launch (one ncu --set full capture), or null
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(dom_kernel.split("[")[0])
+                traffic_detail = json.load(f).get(dom_kernel.split("[")[0])
+            if traffic_detail:
+                traffic = traffic_detail.get("traffic_bytes_per_launch")
         conv = [g for (kn, _), g in groups.items() if kn.startswith("tc_") or kn.startswith("stem_tc")]
         conv_ms, conv_fl = sum(g["ms"] for g in conv), sum(g["flops"] for g in conv)
         # joint-block QKV GEMM (the path north_star quotes): 20 back-to-back launches of each of the 4 ops between two
@@ -340,7 +342,7 @@ def run_native(args):
             "achieved": dom_gbps if hbm_bound else dom_tflops, "peak": peak_bw if hbm_bound else peak_tf_sus,
             "unit": "GB/s" if hbm_bound else "TFLOP/s",
             "frac": (dom_gbps / peak_bw) if hbm_bound else (dom_tflops / peak_tf_sus),
-            "traffic": traffic,
+            "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)", "traffic_detail": traffic_detail,
             "peak_source": f"{peaks['_source']} " + ("hbm_gbs (copy, read+write bytes)" if hbm_bound else "bf16_tflops_sustained"),
             "arithmetic_intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
             "launches_per_step": dom["launches"], "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
