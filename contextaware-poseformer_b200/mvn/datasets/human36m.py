@@ -8,6 +8,7 @@ a [30,3] table comes back to the host, which merges the two trials of an action 
 There is no CPU path: CPU tensors are rejected.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -66,9 +67,81 @@ def evaluate_using_pred(keypoints_gt: torch.Tensor, keypoints_3d_predicted: torc
     count = np.bincount(labels, minlength=len(names)).astype(np.float64)
     with np.errstate(divide="ignore", invalid="ignore"):
         # frame_count * mean(...) of the reference: MPJPE / P_MPJPE average F frames, MPJVE averages the F - 1 differences
-        scores = {name: {"MPJPE": sums[k, 0], "P_MPJPE": sums[k, 1], "MPJVE": count[k] * (sums[k, 2] / (count[k] - 1) if count[k] != 1 else np.nan),
+        # (a trial without frames scores nan like the reference's 0 * mean(empty); with ONE frame the reference's .squeeze()
+        # breaks, here MPJVE is nan and the two position errors are that frame's)
+        scores = {name: {"MPJPE": sums[k, 0] if count[k] else np.nan, "P_MPJPE": sums[k, 1] if count[k] else np.nan,
+                         "MPJVE": count[k] * (sums[k, 2] / (count[k] - 1)) if count[k] > 1 else np.nan,
                          "frame_count": count[k]} for k, name in enumerate(names)}
         for base in [x[:-2] for x in names if x.endswith("-1")]:
             both = [scores.pop(f"{base}-{t}") for t in (1, 2)]
             scores[base] = {k: both[0][k] + both[1][k] for k in both[0]}
         return {k: {m: float(v[m] / v["frame_count"]) for m in ("MPJPE", "P_MPJPE", "MPJVE")} for k, v in scores.items()}
+
+
+class Human36MSingleViewDataset:
+    """Batched, GPU-side counterpart of the reference class of the same name (human36m.py:482-584) over the SAME on-disk
+    formats: the pickled list of label dicts (keys ``joints_3d, joints_2d_cpn, joints_2d_cpn_crop, center, scale, subject,
+    action, subaction, camera_id, image_id, video_id``) and JPEG frames under
+    ``root/s_SS_act_AA_subact_BB_ca_CC/s_SS_act_AA_subact_BB_ca_CC_NNNNNN.jpg``.
+
+    Where the reference decodes AND crops one frame per ``__getitem__`` on a DataLoader worker, ``batch(indices, device)``
+    decodes on the host (``cv2.imread`` -- JPEG decode is a library call in both), uploads the raw frames once and leaves
+    the crop (``mvn.utils.img.crop_images`` = CAPF_OP_WARP_AFFINE_U8) and everything after it to the GPU.  ``rank`` /
+    ``world_size`` slice the labels like ``prepare_labels`` (:536-552: ``n // world`` per rank, the remainder on the last);
+    as in the reference ``labels_action_idx`` keeps covering the WHOLE table, because evaluation runs on the all-gathered
+    predictions (train.py:216-235)."""
+
+    def __init__(self, root, labels_path, image_shape=(192, 256), rank=None, world_size=None):
+        import pickle
+        self.root = root
+        self.image_shape = tuple(image_shape)
+        with open(labels_path, "rb") as f:
+            self.labels = pickle.loads(f.read())
+        self.labels_action_idx = (np.array([s["action"] for s in self.labels]) - 2) * 2 + (np.array([s["subaction"] for s in self.labels]) - 1)
+        self.dist_size = self.prepare_labels(rank, world_size)
+        self.video_idx = np.array([s["video_id"] for s in self.labels])
+
+    def prepare_labels(self, rank, world_size):
+        if rank is None or world_size is None:
+            return None
+        total = len(self.labels)
+        n = total // world_size
+        start = n * rank
+        self.labels = self.labels[start:(total if rank == world_size - 1 else start + n)]
+        return [n if i < world_size - 1 else total - n * (world_size - 1) for i in range(world_size)]
+
+    def __len__(self):
+        return len(self.labels)
+
+    def image_path(self, idx) -> str:
+        s = self.labels[idx]
+        sub = "s_{:02d}_act_{:02d}_subact_{:02d}_ca_{:02d}".format(s["subject"], s["action"], s["subaction"], s["camera_id"] + 1)
+        return os.path.join(self.root, sub, "{}_{:06d}.jpg".format(sub, s["image_id"]))
+
+    def read_frame(self, idx) -> np.ndarray:
+        import cv2
+        frame = cv2.imread(self.image_path(idx), cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+        if frame is None:
+            raise FileNotFoundError(self.image_path(idx))
+        return frame
+
+    def batch(self, indices, device) -> dict:
+        """What ``__getitem__`` returns for `indices` (collated), with the crop done on `device`:
+        images uint8 [B,H,W,3] BGR crops, keypoints_3d_gt [B,1,17,3], keypoints_2d_cpn [B,17,2], keypoints_2d_cpn_crop [B,17,2];
+        plus the raw material (`frames`, `sizes`, `trans`) for frontend.flip_test_forward_from_frames."""
+        from ..utils import img
+        frames = [self.read_frame(i) for i in indices]
+        hs, ws = max(f.shape[0] for f in frames), max(f.shape[1] for f in frames)
+        stack = np.zeros((len(frames), hs, ws, 3), dtype=np.uint8)
+        for k, f in enumerate(frames):
+            stack[k, :f.shape[0], :f.shape[1]] = f
+        sizes = torch.tensor([[f.shape[0], f.shape[1]] for f in frames], dtype=torch.int32)
+        shots = [self.labels[i] for i in indices]
+        trans = np.stack([img.get_affine_transform(s["center"], s["scale"], 0, self.image_shape) for s in shots])
+        frames_dev, sizes_dev = torch.from_numpy(stack).to(device), sizes.to(device)
+        as_t = lambda key, extra=(): torch.from_numpy(np.stack([np.asarray(s[key], dtype=np.float32) for s in shots]).reshape(len(shots), *extra, 17, -1)).to(device)
+        return {"images": img.crop_images(frames_dev, trans, self.image_shape, sizes=sizes_dev), "frames": frames_dev, "sizes": sizes_dev, "trans": trans,
+                "keypoints_3d_gt": as_t("joints_3d", (1,)), "keypoints_2d_cpn": as_t("joints_2d_cpn"), "keypoints_2d_cpn_crop": as_t("joints_2d_cpn_crop")}
+
+    def evaluate_using_pred(self, keypoints_gt, keypoints_3d_predicted):
+        return evaluate_using_pred(keypoints_gt, keypoints_3d_predicted, self.labels_action_idx)

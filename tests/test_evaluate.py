@@ -75,3 +75,21 @@ def test_gpu_pose_errors_per_frame_including_reflections_and_planar_poses():
     np.testing.assert_allclose(rows[:, 0], want[:, 0], rtol=1e-12)
     np.testing.assert_allclose(rows[:, 1], want[:, 1], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(rows[:, 2], want[:, 2], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_reducer_scores_nan_for_an_action_with_an_empty_trial():
+    from capf_b200.mvn.datasets import human36m as host
+    (gt, pred, labels), _, _ = next(cases())
+    keep = labels != 5                                        # drop trial 2 of "Eating": 0 * mean(empty) = nan in the reference
+    # (with BOTH trials missing the reference divides by a zero frame count and raises)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = capf_oracle.evaluate_using_pred(torch.from_numpy(gt[keep]), torch.from_numpy(pred[keep]), labels[keep])
+    res = host.evaluate_using_pred(torch.from_numpy(gt[keep]).cuda(), torch.from_numpy(pred[keep]).cuda(), labels[keep])
+    assert all(np.isnan(res["Eating"][m]) and np.isnan(want["Eating"][m]) for m in ("MPJPE", "P_MPJPE", "MPJVE"))
+    for a in res:
+        if a != "Eating":
+            for m in ("MPJPE", "P_MPJPE", "MPJVE"):
+                assert abs(res[a][m] - want[a][m]) <= RTOL * abs(want[a][m])
