@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcapf_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # enums (mirror capf_b200.h)
 F32, F16, BF16 = 0, 1, 2
@@ -61,6 +61,10 @@ def load():
     lib.capf_plan_destroy.argtypes = [C.c_void_p]
     lib.capf_op_run.argtypes = [C.POINTER(CapfOp), C.c_int, C.c_void_p]
     lib.capf_crop_normalize.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.capf_jpeg_available.restype = C.c_int
+    lib.capf_jpeg_info.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.capf_jpeg_decode_batch.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                           C.POINTER(C.c_int), C.c_int, C.c_void_p]
     if lib.capf_abi_version() != ABI_VERSION:
         raise CapfError(f"libcapf_b200.so ABI {lib.capf_abi_version()} != binding {ABI_VERSION}: rebuild")
     _lib = lib
@@ -82,4 +86,5 @@ def device_info(device: int = 0):
 def exported_symbols():
     """Names declared in include/capf_b200.h (used by the CPU-side ABI test)."""
     return ["capf_abi_version", "capf_last_error", "capf_device_info", "capf_plan_create", "capf_plan_run",
-            "capf_plan_num_launches", "capf_plan_op_kernel", "capf_plan_destroy", "capf_op_run", "capf_crop_normalize"]
+            "capf_plan_num_launches", "capf_plan_op_kernel", "capf_plan_destroy", "capf_op_run", "capf_crop_normalize",
+            "capf_jpeg_available", "capf_jpeg_info", "capf_jpeg_decode_batch"]

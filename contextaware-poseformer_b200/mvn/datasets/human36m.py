@@ -125,20 +125,55 @@ class Human36MSingleViewDataset:
             raise FileNotFoundError(self.image_path(idx))
         return frame
 
-    def batch(self, indices, device) -> dict:
+    def decode_frames(self, indices, device):
+        """JPEG files -> (uint8 [B,Hs,Ws,3] BGR frames on `device`, int32 [B,2] live (h, w)) through nvJPEG: the compressed
+        bytes cross PCIe and each frame is decoded straight into the padded storage the crop reads (capf_jpeg_decode_batch).
+        nvJPEG and libjpeg (cv2.imread) are different decoders of the same streams: pixels agree to a few grey levels."""
+        L = lib.load()
+        if not L.capf_jpeg_available():
+            raise lib.CapfError("decode_frames: libnvjpeg could not be loaded on this machine (use decode='cv2')")
+        dev = torch.device(device)
+        blobs = []
+        for i in indices:
+            with open(self.image_path(i), "rb") as f:
+                blobs.append(f.read())
+        n = len(blobs)
+        sizes = np.zeros((n, 2), dtype=np.int32)
+        h, w = ctypes.c_int(), ctypes.c_int()
+        for k, b in enumerate(blobs):
+            lib.check(L.capf_jpeg_info(b, len(b), dev.index or 0, ctypes.byref(h), ctypes.byref(w)), "capf_jpeg_info")
+            sizes[k] = (h.value, w.value)
+        hs, ws = int(sizes[:, 0].max()), int(sizes[:, 1].max())
+        frames = torch.zeros(n, hs, ws, 3, dtype=torch.uint8, device=dev)
+        data = (ctypes.c_char_p * n)(*blobs)
+        lens = (ctypes.c_size_t * n)(*[len(b) for b in blobs])
+        got = (ctypes.c_int * (2 * n))()
+        lib.check(L.capf_jpeg_decode_batch(data, lens, n, frames.data_ptr(), hs, ws, got, dev.index or 0, torch.cuda.current_stream(dev).cuda_stream),
+                  "capf_jpeg_decode_batch")
+        torch.cuda.current_stream(dev).synchronize()            # `blobs` must outlive the decode
+        return frames, torch.from_numpy(sizes).to(dev)
+
+    def batch(self, indices, device, decode: str = "cv2") -> dict:
         """What ``__getitem__`` returns for `indices` (collated), with the crop done on `device`:
         images uint8 [B,H,W,3] BGR crops, keypoints_3d_gt [B,1,17,3], keypoints_2d_cpn [B,17,2], keypoints_2d_cpn_crop [B,17,2];
-        plus the raw material (`frames`, `sizes`, `trans`) for frontend.flip_test_forward_from_frames."""
+        plus the raw material (`frames`, `sizes`, `trans`) for frontend.flip_test_forward_from_frames.
+        decode="cv2": frames decoded on the host by cv2.imread like the reference (bit-identical frames);
+        decode="nvjpeg": decoded on the GPU (decode_frames)."""
         from ..utils import img
-        frames = [self.read_frame(i) for i in indices]
-        hs, ws = max(f.shape[0] for f in frames), max(f.shape[1] for f in frames)
-        stack = np.zeros((len(frames), hs, ws, 3), dtype=np.uint8)
-        for k, f in enumerate(frames):
-            stack[k, :f.shape[0], :f.shape[1]] = f
-        sizes = torch.tensor([[f.shape[0], f.shape[1]] for f in frames], dtype=torch.int32)
         shots = [self.labels[i] for i in indices]
         trans = np.stack([img.get_affine_transform(s["center"], s["scale"], 0, self.image_shape) for s in shots])
-        frames_dev, sizes_dev = torch.from_numpy(stack).to(device), sizes.to(device)
+        if decode == "nvjpeg":
+            frames_dev, sizes_dev = self.decode_frames(indices, device)
+        elif decode == "cv2":
+            frames = [self.read_frame(i) for i in indices]
+            hs, ws = max(f.shape[0] for f in frames), max(f.shape[1] for f in frames)
+            stack = np.zeros((len(frames), hs, ws, 3), dtype=np.uint8)
+            for k, f in enumerate(frames):
+                stack[k, :f.shape[0], :f.shape[1]] = f
+            sizes = torch.tensor([[f.shape[0], f.shape[1]] for f in frames], dtype=torch.int32)
+            frames_dev, sizes_dev = torch.from_numpy(stack).to(device), sizes.to(device)
+        else:
+            raise ValueError("batch: decode must be 'cv2' or 'nvjpeg'")
         as_t = lambda key, extra=(): torch.from_numpy(np.stack([np.asarray(s[key], dtype=np.float32) for s in shots]).reshape(len(shots), *extra, 17, -1)).to(device)
         return {"images": img.crop_images(frames_dev, trans, self.image_shape, sizes=sizes_dev), "frames": frames_dev, "sizes": sizes_dev, "trans": trans,
                 "keypoints_3d_gt": as_t("joints_3d", (1,)), "keypoints_2d_cpn": as_t("joints_2d_cpn"), "keypoints_2d_cpn_crop": as_t("joints_2d_cpn_crop")}

@@ -20,13 +20,14 @@
 #ifndef CAPF_B200_H_
 #define CAPF_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 8
+#define CAPF_ABI_VERSION 9
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -207,6 +208,16 @@ int capf_plan_op_kernel(const capf_plan* plan, int k, char* buf, int cap);
 int capf_plan_destroy(capf_plan* plan);
 /* One-off execution of a single op (builds a throw-away plan): used by the per-operator parity tests. */
 int capf_op_run(const capf_op* op, int device, void* stream);
+
+/* Frame decode (mvn/datasets/human36m.py:565-567, cv2.imread(..., IMREAD_COLOR)) --------------------------
+ * JPEG streams in host memory -> interleaved BGR uint8 frames in the padded device storage [n,Hs,Ws,3] that
+ * CAPF_OP_WARP_AFFINE_U8 crops from, decoded by nvJPEG (loaded with dlopen on first use; without it these return
+ * CAPF_ERR_UNSUPPORTED and capf_jpeg_available() 0).  sizes_hw (host, [n,2], may be NULL) receives each frame's (h, w).
+ * Work is enqueued on `stream`; the decoder is bound to the device of its first use (one process per GPU). */
+int capf_jpeg_available(void);
+int capf_jpeg_info(const unsigned char* data, size_t length, int device, int* height, int* width);
+int capf_jpeg_decode_batch(const unsigned char* const* data, const size_t* lengths, int n, unsigned char* frames, int Hs, int Ws,
+                           int* sizes_hw, int device, void* stream);
 
 /* Convenience wrappers over capf_op_run mirroring the reference call sites ------------------------------ */
 int capf_crop_normalize(float* crop_xy, int n_points, void* stream);          /* conpose.py:34-35 */
