@@ -72,6 +72,15 @@ def flip_keypoints(kp2d: torch.Tensor, kp2d_crop: torch.Tensor):
     return k, c
 
 
+def root_relative(keypoints_3d_gt: torch.Tensor) -> torch.Tensor:
+    """The 3D target as the prefetcher hands it on (utils.py:52-53): joints 1.. relative to joint 0, joint 0 zeroed.
+    [B,1,17,3] -> new fp32 tensor (the reference edits the loader's tensor in place)."""
+    gt = keypoints_3d_gt.clone()
+    gt[:, :, 1:] -= gt[:, :, :1]
+    gt[:, :, 0] = 0
+    return gt.float()
+
+
 def merge_flip_test(pred: torch.Tensor, pred_flip: torch.Tensor) -> torch.Tensor:
     """train.py:177-180: un-mirror the second prediction and average.  pred, pred_flip: [B,1,17,3]."""
     pf = pred_flip.clone()

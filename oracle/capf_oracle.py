@@ -315,9 +315,10 @@ def ca_pf_forward(sd, backbone, bb_cfg, images, kp2d, crop, trace=None):
 
 
 # ------------------------------------------------------------------------------------------------------
-# f1: pre-processing + flip-test front end (TEST-ONLY restatement; parity UNPINNED: the reference's data_prefetcher
-# needs a CUDA device to run at all (.cuda() calls, mvn/datasets/utils.py:18-29,41), so it cannot be executed in the
-# authoring container; this follows its source line by line)
+# f1: pre-processing + flip-test front end (TEST-ONLY restatement of mvn/datasets/utils.py:15-88).  PINNED:
+# oracle/gen_golden_prefetch.py runs the reference's own data_prefetcher on the CPU with its CUDA entry points stubbed
+# and tests/test_frontend.py checks these functions against its outputs exactly (tests/golden/prefetch_cases.npz).
+# flip_test_merge (train.py:177-180, code inside a script function) is a line-by-line restatement.
 # ------------------------------------------------------------------------------------------------------
 JOINTS_LEFT = [4, 5, 6, 11, 12, 13]      # mvn/datasets/utils.py:12
 JOINTS_RIGHT = [1, 2, 3, 14, 15, 16]     # mvn/datasets/utils.py:13
@@ -348,6 +349,14 @@ def prefetch_flip_test(images_u8, kp2d, kp2d_crop, backbone):
     c[:, :, 0] = 192 - c[:, :, 0] - 1
     c[:, JOINTS_LEFT + JOINTS_RIGHT] = c[:, JOINTS_RIGHT + JOINTS_LEFT]
     return images, torch.stack([kp2d, k], dim=1), torch.stack([kp2d_crop, c], dim=1)
+
+
+def prefetch_targets(keypoints_3d_gt):
+    """mvn/datasets/utils.py:52-53: the 3D target made root-relative (joint 0 subtracted from joints 1.., then zeroed)."""
+    gt = keypoints_3d_gt.clone()
+    gt[:, :, 1:] -= gt[:, :, :1]
+    gt[:, :, 0] = 0
+    return gt.float()
 
 
 def flip_test_merge(pred, pred_flip):

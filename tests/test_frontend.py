@@ -107,3 +107,25 @@ def test_flip_test_forward_from_frames_equals_crop_then_flip_test():
         crops_u8 = host.crop_images(frames, trans, (96, 128), sizes=sizes)
         want = frontend.flip_test_forward(model, crops_u8, kp, crop)
     assert got.shape == (B, 1, 17, 3) and torch.isfinite(got).all() and torch.equal(got, want)
+
+
+def test_oracle_prefetch_is_pinned_to_the_reference_prefetcher():
+    """tests/golden/prefetch_cases.npz = the reference's own data_prefetcher (utils.py:15-88) run on CPU by
+    oracle/gen_golden_prefetch.py (its four CUDA entry points stubbed, arithmetic untouched): the restatement and the host
+    mirror reproduce it exactly -- images, flip-test stacks of both keypoint tensors, root-relative targets."""
+    import os
+    from gen_golden_prefetch import make_batch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prefetch_cases.npz"))
+    for k in range(int(g["n"])):
+        seed, is_cpn, flip = (int(v) for v in g[f"p{k}_cfg"])
+        backbone = "cpn" if is_cpn else "hrnet_32"
+        images, gt, kp, crop = make_batch(seed)
+        want = [torch.from_numpy(g[f"p{k}_{n}"]) for n in ("images", "gt", "kp", "crop")]
+        if flip:
+            got_img, got_kp, got_crop = capf_oracle.prefetch_flip_test(images, kp, crop, backbone)
+            kf, cf = frontend.flip_keypoints(kp, crop)
+            assert torch.equal(torch.stack([kp, kf], 1), want[2]) and torch.equal(torch.stack([crop, cf], 1), want[3])
+        else:
+            got_img, got_kp, got_crop = capf_oracle.prefetch_images(images, backbone), kp, crop
+        assert torch.equal(got_img, want[0]) and torch.equal(got_kp, want[2]) and torch.equal(got_crop, want[3])
+        assert torch.equal(capf_oracle.prefetch_targets(gt), want[1]) and torch.equal(frontend.root_relative(gt), want[1])
