@@ -125,6 +125,14 @@ class Human36MSingleViewDataset:
             raise FileNotFoundError(self.image_path(idx))
         return frame
 
+    def read_frames(self, indices, workers: int = 8) -> list:
+        """read_frame for many indices on a thread pool (cv2.imread releases the GIL), in the order asked."""
+        if workers <= 1 or len(indices) <= 1:
+            return [self.read_frame(i) for i in indices]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(workers, len(indices))) as pool:
+            return list(pool.map(self.read_frame, indices))
+
     def decode_frames(self, indices, device):
         """JPEG files -> (uint8 [B,Hs,Ws,3] BGR frames on `device`, int32 [B,2] live (h, w)) through nvJPEG: the compressed
         bytes cross PCIe and each frame is decoded straight into the padded storage the crop reads (capf_jpeg_decode_batch).
@@ -165,7 +173,7 @@ class Human36MSingleViewDataset:
         if decode == "nvjpeg":
             frames_dev, sizes_dev = self.decode_frames(indices, device)
         elif decode == "cv2":
-            frames = [self.read_frame(i) for i in indices]
+            frames = self.read_frames(indices)
             hs, ws = max(f.shape[0] for f in frames), max(f.shape[1] for f in frames)
             stack = np.zeros((len(frames), hs, ws, 3), dtype=np.uint8)
             for k, f in enumerate(frames):

@@ -34,6 +34,17 @@ def test_label_table_paths_and_rank_slices_match_reference(tag, rank, world):
         assert np.array_equal(s["joints_2d_cpn"], g[f"{tag}_kp"][i]) and np.array_equal(s["joints_2d_cpn_crop"], g[f"{tag}_kp_crop"][i])
 
 
+def test_threaded_frame_reads_keep_order():
+    pytest.importorskip("cv2")
+    ds = open_ds()
+    idx = [3, 0, 6, 6, 1]
+    a, b = ds.read_frames(idx, workers=4), [ds.read_frame(i) for i in idx]
+    assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+    with pytest.raises(FileNotFoundError):
+        ds.labels[0]["image_id"] = 999999
+        ds.read_frame(0)
+
+
 @pytest.mark.gpu
 def test_gpu_batches_equal_reference_items():
     pytest.importorskip("cv2")
