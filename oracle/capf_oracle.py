@@ -491,3 +491,37 @@ def evaluate_using_pred(keypoints_gt, keypoints_3d_predicted, labels_action_idx,
         both = [scores.pop(f"{base}-{t}") for t in (1, 2)]
         scores[base] = {k: both[0][k] + both[1][k] for k in both[0]}
     return {k: {m: v[m] / v["frame_count"] for m in ("MPJPE", "P_MPJPE", "MPJVE")} for k, v in scores.items()}
+
+
+# ------------------------------------------------------------------------------------------------------
+# f2 groundwork: one training step of volume_net (train.py:186-201; optimiser train.py:337-345: AdamW over
+# volume_net.parameters(), lr = config.train.volume_net_lr, weight_decay 0.1, no gradient clipping by default).
+# Gradients come from autograd over the restated forward above (every op there is a differentiable torch op; the backbone
+# is frozen, conpose.py:23-25).  DropPath is the identity here (eval-mode blocks): the stochastic-depth mask of train mode
+# is a separate, seeded concern.  Pinned by tests/golden/grad_hrnet32_b2_128x96.npz (oracle/gen_golden_grad.py ran
+# autograd and torch.optim.AdamW on the unmodified reference model).
+# ------------------------------------------------------------------------------------------------------
+def volume_net_loss_and_grads(sd, backbone, bb_cfg, images, kp2d, crop, gt):
+    """MPJPE loss (loss.py:16-22) of the forward and d loss / d volume_net parameters.  Returns (loss, {name: grad})."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if k.startswith("volume_net.") and v.is_floating_point()}
+    sd2 = dict(sd)
+    sd2.update(leaves)
+    with torch.no_grad():                                   # frozen backbone (conpose.py:23-25): features are constants
+        x = images.permute(0, 3, 1, 2).contiguous()
+        ref = normalize_crop_(crop.clone())
+        feats = cpn_forward(sd, x) if backbone == "cpn" else hrnet_forward(sd, x, bb_cfg)
+    with torch.enable_grad():
+        pred = lifter_forward(sd2, kp2d, ref, feats)
+        loss = torch.mean(torch.norm(pred - gt, dim=len(gt.shape) - 1))
+    grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+    return float(loss.detach()), {k: (g if g is not None else torch.zeros_like(v)) for (k, v), g in zip(leaves.items(), grads)}
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr, weight_decay=0.1, betas=(0.9, 0.999), eps=1e-8):
+    """torch.optim.AdamW's update (decoupled weight decay; the defaults train.py:345 leaves in place), one tensor, step
+    counted from 1.  Returns (param, exp_avg, exp_avg_sq)."""
+    param = param * (1 - lr * weight_decay)
+    exp_avg = exp_avg * betas[0] + grad * (1 - betas[0])
+    exp_avg_sq = exp_avg_sq * betas[1] + grad * grad * (1 - betas[1])
+    denom = (exp_avg_sq.sqrt() / (1 - betas[1] ** step) ** 0.5) + eps
+    return param - (lr / (1 - betas[0] ** step)) * exp_avg / denom, exp_avg, exp_avg_sq
