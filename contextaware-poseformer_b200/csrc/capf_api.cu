@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
 #include <new>
 #include <vector>
 
@@ -10,9 +11,10 @@
 
 namespace capf {
 
-int g_num_sms = 148;
 int g_use_pdl = []() { const char* e = getenv("CAPF_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
 static thread_local char g_err[512] = "";
+static thread_local int g_sel_device = 0;                 // innermost DeviceGuard of this thread
+static std::atomic<int> g_sms[CAPF_MAX_DEVICES];          // per-device SM count (0 = not probed yet)
 
 int set_error(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -33,22 +35,49 @@ int check_launch(const char* name) {
   return CAPF_OK;
 }
 
-static int use_device(int device) {
+int current_device() { return g_sel_device; }
+
+int num_sms() {
+  int n = g_sms[g_sel_device].load(std::memory_order_relaxed);
+  return n > 0 ? n : 148;
+}
+
+// Validates `device` (an sm_100 GPU), makes it current for the lifetime of the guard and restores the caller's device.
+DeviceGuard::DeviceGuard(int device) : status(CAPF_OK), prev_cuda_(-1), prev_sel_(g_sel_device), switched_(false) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n <= 0)
-    return set_errorf(CAPF_ERR_CUDA, "no CUDA device (%s): libcapf_b200 has no CPU path", cudaGetErrorString(e));
-  if (device < 0 || device >= n) return set_errorf(CAPF_ERR_ARG, "device %d out of range (%d devices)", device, n);
-  int cur = -1;
-  cudaGetDevice(&cur);
-  if (cur != device && (e = cudaSetDevice(device)) != cudaSuccess)
-    return set_errorf(CAPF_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
-  int sms = 0, major = 0;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
-  if (major != 10) return set_errorf(CAPF_ERR_UNSUPPORTED, "device %d is sm_%dx; this library is built for sm_100a only", device, major);
-  g_num_sms = sms > 0 ? sms : 148;
-  return CAPF_OK;
+  if (e != cudaSuccess || n <= 0) {
+    status = set_errorf(CAPF_ERR_CUDA, "no CUDA device (%s): libcapf_b200 has no CPU path", cudaGetErrorString(e));
+    return;
+  }
+  if (device < 0 || device >= n || device >= CAPF_MAX_DEVICES) {
+    status = set_errorf(CAPF_ERR_ARG, "device %d out of range (%d devices)", device, n);
+    return;
+  }
+  if (g_sms[device].load(std::memory_order_relaxed) <= 0) {
+    int sms = 0, major = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) {
+      status = set_errorf(CAPF_ERR_UNSUPPORTED, "device %d is sm_%dx; this library is built for sm_100a only", device, major);
+      return;
+    }
+    g_sms[device].store(sms > 0 ? sms : 148, std::memory_order_relaxed);
+  }
+  cudaGetDevice(&prev_cuda_);
+  if (prev_cuda_ != device) {
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+      status = set_errorf(CAPF_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+      return;
+    }
+    switched_ = true;
+  }
+  g_sel_device = device;
+}
+
+DeviceGuard::~DeviceGuard() {
+  g_sel_device = prev_sel_;
+  if (switched_) cudaSetDevice(prev_cuda_);
 }
 
 static int dispatch(const capf_op& op, const TcConvState* tc, cudaStream_t st) {
@@ -109,7 +138,8 @@ int capf_device_info(int device, int64_t* out4) {
 
 int capf_plan_create(const capf_op* ops, int n_ops, int device, capf_plan** out_plan) {
   if (!ops || n_ops <= 0 || !out_plan) return set_error(CAPF_ERR_ARG, "capf_plan_create: bad arguments");
-  int e = use_device(device);
+  DeviceGuard guard(device);
+  int e = guard.status;
   if (e) return e;
   capf_plan* pl = new (std::nothrow) capf_plan();
   if (!pl) return set_error(CAPF_ERR_ARG, "capf_plan_create: out of host memory");
@@ -150,6 +180,8 @@ int capf_plan_run(const capf_plan* plan, int first, int count, void* stream) {
   int n = (int)plan->ops.size();
   if (count < 0) count = n - first;
   if (first < 0 || first + count > n) return set_error(CAPF_ERR_ARG, "capf_plan_run: range out of bounds");
+  DeviceGuard guard(plan->device);     // launches go to the plan's device whatever the caller's current device is
+  if (guard.status) return guard.status;
   cudaStream_t st = (cudaStream_t)stream;
   for (int k = first; k < first + count; ++k) {
     int e = dispatch(plan->ops[k], plan->tc[k], st);
@@ -201,6 +233,8 @@ int capf_plan_destroy(capf_plan* plan) {
 }
 
 int capf_op_run(const capf_op* op, int device, void* stream) {
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   capf_plan* pl = nullptr;
   int e = capf_plan_create(op, 1, device, &pl);
   if (e) return e;
@@ -220,9 +254,16 @@ int capf_crop_normalize(float* crop_xy, int n_points, void* stream) {
   op.kind = CAPF_OP_CROP_NORMALIZE;
   op.i[0] = n_points;
   op.out[0] = crop_xy;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  return capf_op_run(&op, dev, stream);
+  // the device is the one that owns the caller's tensor, not whatever happens to be current
+  if (!crop_xy || n_points < 0) return set_error(CAPF_ERR_ARG, "capf_crop_normalize: bad arguments");
+  if (((uintptr_t)crop_xy & 7) != 0) return set_error(CAPF_ERR_ARG, "capf_crop_normalize: pointer must be 8-byte aligned (float2 access)");
+  cudaPointerAttributes at;
+  cudaError_t ce = cudaPointerGetAttributes(&at, crop_xy);
+  if (ce != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return set_error(CAPF_ERR_ARG, "capf_crop_normalize: crop_xy is not a device pointer (there is no CPU path)");
+  }
+  return capf_op_run(&op, at.device, stream);
 }
 
 }  // extern "C"

@@ -2,11 +2,34 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "../../include/capf_b200.h"
 
 namespace capf {
 
-extern int g_num_sms;  // SM count of the device the current plan/op targets (148 on B200)
+// Device selection.  Every extern "C" entry point that touches the GPU opens a DeviceGuard for the device it targets
+// (the plan's device, or the device that owns the caller's pointer) and restores the caller's current device on
+// exit, so the library never changes the current device behind torch's back and a process may drive several GPUs.
+constexpr int CAPF_MAX_DEVICES = 64;
+struct DeviceGuard {
+  explicit DeviceGuard(int device);   // status != CAPF_OK: device unusable (message recorded)
+  ~DeviceGuard();
+  int status;
+ private:
+  int prev_cuda_, prev_sel_;
+  bool switched_;
+};
+int current_device();   // ordinal selected by the innermost DeviceGuard of this thread
+int num_sms();          // SM count of current_device() (148 on B200)
+
+// Per-device state of a kernel instantiation: function attributes (the > 48 KB dynamic shared-memory opt-in) belong to
+// a (function, device) pair, not to the process.  Races are benign (the guarded action is idempotent).
+template <typename T>
+struct PerDevice {
+  std::atomic<T> v[CAPF_MAX_DEVICES];
+  std::atomic<T>& get() { return v[current_device()]; }
+};
 
 int set_error(int code, const char* msg);       // records thread-local message, returns code
 int set_errorf(int code, const char* fmt, ...);

@@ -423,7 +423,7 @@ int launch_fuse_sum(const capf_op& op, cudaStream_t st) {
   if (total >= (1ull << 31)) return set_error(CAPF_ERR_UNSUPPORTED, "fuse_sum: tensor too large for 32-bit indexing");
   for (int t = 0; t < p.nt; ++t)
     if ((uintptr_t)p.t[t] & 15) return set_error(CAPF_ERR_ARG, "fuse_sum: terms must be 16-byte aligned");
-  int blocks = (int)((total + 255) / 256 < (size_t)g_num_sms * 16 ? (total + 255) / 256 : (size_t)g_num_sms * 16);
+  int blocks = (int)((total + 255) / 256 < (size_t)num_sms() * 16 ? (total + 255) / 256 : (size_t)num_sms() * 16);
   if (blocks < 1) blocks = 1;
   switch (op.dtype_out) {
     case CAPF_F32: launch_k(fuse_sum_kernel<float>, dim3(blocks), dim3(256), 0, st, p, (float*)op.out[0]); break;
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(256) bilinear_ac16_kernel(int N, int H, int W,
 }
 
 static int ew_blocks(size_t total) {
-  size_t b = (total + 255) / 256, cap = (size_t)g_num_sms * 16;
+  size_t b = (total + 255) / 256, cap = (size_t)num_sms() * 16;
   if (b > cap) b = cap;
   return b < 1 ? 1 : (int)b;
 }
@@ -1042,7 +1042,8 @@ static int attention_dispatch(const capf_op& op, cudaStream_t st) {
   TO* out = (TO*)op.out[0];
   // opt in to > 48 KB dynamic smem once per instantiation (not a stream operation; done outside graph capture
   // because Plan.capture() always runs one eager warm-up pass first)
-  static size_t max5 = 0, max17 = 0;
+  static PerDevice<size_t> max5_, max17_;
+  std::atomic<size_t>&max5 = max5_.get(), &max17 = max17_.get();
   if (seq == 5) {
     if (smem > max5) {
       cudaFuncSetAttribute(attention_small_kernel<TI, TO, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

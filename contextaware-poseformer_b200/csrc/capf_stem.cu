@@ -265,13 +265,14 @@ int stem_tc_supported(const capf_op& op) {
 template <typename TO, int KS, bool SPLIT>
 static int stem_launch_typed(const StemP& p, cudaStream_t st) {
   using G = StemGeo<KS, SPLIT>;
-  static bool opted = false;
+  static PerDevice<bool> opted_;
+  std::atomic<bool>& opted = opted_.get();
   if (!opted) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<TO, KS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "stem_tc_kernel smem opt-in: %s", cudaGetErrorString(e));
     opted = true;
   }
-  int grid = G::CTAS_PER_SM * g_num_sms;
+  int grid = G::CTAS_PER_SM * num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   launch_k(stem_tc_kernel<TO, KS, SPLIT>, dim3(grid), dim3(STEM_THREADS), G::SMEM, st, p);
   return check_launch("stem_tc_kernel");

@@ -584,7 +584,7 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
       if (stages < 2) continue;
       const int nacc = 2 * msub * bn <= 512 ? 2 : 1;
       const long long tiles = m_tiles * (g.Cout / bn);
-      const long long grid = tiles < g_num_sms ? tiles : g_num_sms;
+      const long long grid = tiles < num_sms() ? tiles : num_sms();
       const double per_cta = (double)((tiles + grid - 1) / grid);
       const double k16 = K / 16.0;
       const double t_mma = msub * k16 * ((bn / 2.0) > ((128 + bn) / 4.0) ? (bn / 2.0) : ((128 + bn) / 4.0));
@@ -643,7 +643,7 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   p.tmem_cols = cols;
   p.idesc = tc_idesc(op.dtype_in == CAPF_BF16, p.BN);
   p.desc_hi = tc_desc_hi(swz, 8 * swz);
-  s->grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  s->grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   s->dtype_out = op.dtype_out;
 
   // ---- tensor maps -------------------------------------------------------------------------------------
@@ -675,7 +675,8 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
 
 template <typename TO, int MODE>
 static int tc_launch_mode(const TcConvState* s, cudaStream_t st) {
-  static int max_smem = 0;   // opt-in once per instantiation (outside graph capture: Plan.capture warms up first)
+  static PerDevice<int> max_smem_;   // opt-in once per instantiation and device (outside graph capture: Plan.capture warms up first)
+  std::atomic<int>& max_smem = max_smem_.get();
   if (s->smem_bytes > max_smem) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<TO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_gemm_kernel smem opt-in: %s", cudaGetErrorString(e));

@@ -322,7 +322,7 @@ int tc2_prepare(const capf_op& op, Tc2State** out) {
   const int osz = op.dtype_out == CAPF_F32 ? 4 : 2;
   p.stg_bufs = p.res ? 2 : 1;
   const int stg_bytes = 8 * p.stg_bufs * T2_STG_BYTES + 8 * 128 * 4;
-  const int pairs = g_num_sms / 2;
+  const int pairs = num_sms() / 2;
   const int m_tiles = ceil_div2(p.M, 256);
   // column tile: multiple of 16 (each CTA holds BN / 2 rows of B, whole 8-row swizzle groups) dividing Cout, <= 256; cost = rounds of
   // pair tiles x per-tile tensor time (+ an epilogue term), with the i[16] override used by the tests
@@ -394,7 +394,8 @@ int tc2_prepare(const capf_op& op, Tc2State** out) {
 
 template <typename TO, int MODE>
 static int tc2_launch_mode(const Tc2State* s, cudaStream_t st) {
-  static bool opted = false;
+  static PerDevice<bool> opted_;
+  std::atomic<bool>& opted = opted_.get();
   if (!opted) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm2_kernel<TO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_gemm2_kernel smem opt-in: %s", cudaGetErrorString(e));

@@ -389,7 +389,7 @@ int tc_block_prepare(const capf_op& op, TcBlockState** out) {
   p.bias2 = (const float*)op.in[4];
   p.out = op.out[0];
   p.trace = (long long*)op.in[5];      // debug only (NULL in every program the host layer builds)
-  s->grid = p.num_bands < g_num_sms ? p.num_bands : g_num_sms;
+  s->grid = p.num_bands < num_sms() ? p.num_bands : num_sms();
   s->dtype = op.dtype_in;
   const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   for (int w = 0; w < 2 && !e; ++w) {
@@ -413,7 +413,8 @@ int tc_block_prepare(const capf_op& op, TcBlockState** out) {
 
 template <typename T>
 static int block_launch_typed(const TcBlockState* s, cudaStream_t st) {
-  static bool opted = false;
+  static PerDevice<bool> opted_;
+  std::atomic<bool>& opted = opted_.get();
   if (!opted) {
     cudaError_t e = cudaFuncSetAttribute(tc_block32_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_block32_kernel smem opt-in: %s", cudaGetErrorString(e));

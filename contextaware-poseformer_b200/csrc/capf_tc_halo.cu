@@ -461,7 +461,7 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
   p.out = op.out[0];
   { const char* e = getenv("CAPF_L2_HINTS"); p.l2_hints = (e && e[0] == '0') ? 0 : 1; }
   p.trace = (long long*)op.in[4];     // debug only (NULL in every program the host layer builds)
-  s->grid = p.num_bands < g_num_sms ? p.num_bands : g_num_sms;
+  s->grid = p.num_bands < num_sms() ? p.num_bands : num_sms();
   s->dtype_in = op.dtype_in;
   s->dtype_out = op.dtype_out;
   const int K = 9 * p.C;
@@ -487,7 +487,8 @@ int tc_halo_prepare(const capf_op& op, TcHaloState** out) {
 
 template <int C, int NV, typename TI, typename TO, bool RES>
 static int halo_launch_cnr(const TcHaloState* s, cudaStream_t st) {
-  static bool opted = false;
+  static PerDevice<bool> opted_;
+  std::atomic<bool>& opted = opted_.get();
   if (!opted) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv3_halo_kernel<C, NV, TI, TO, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_conv3_halo_kernel smem opt-in: %s", cudaGetErrorString(e));

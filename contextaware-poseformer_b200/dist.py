@@ -38,6 +38,32 @@ class OutputGatherer:
         self.tail = tuple(tail_shape)
         self.buf = torch.zeros((self.world * self.max_rows,) + self.tail, device=device, dtype=dtype)
         self.pad = None if self.equal else torch.zeros((self.max_rows,) + self.tail, device=device, dtype=dtype)
+        self.attached = False
+
+    def attach(self, model, B, H, W):
+        """Make the all-gather part of `model`'s forward for the (B, H, W) geometry: it is enqueued on the forward's
+        stream right after the last kernel, reading the plan's output buffer in place -- and therefore becomes the last
+        node of the forward's CUDA graph when the model replays one (no separate launch per step).  Equal shards only.
+        After ``model(...)`` returns, ``result()`` is the gathered ``[world * B, ...]`` tensor (valid in stream order)."""
+        if not self.equal or self.sizes[0] != B:
+            raise ValueError("attach() needs equal shards of the plan's batch size")
+        dev = self.buf.device
+        plan = model.plan_for(B, H, W, dev)
+        src = plan.tensor(plan.prog.outputs["out"]).view((B,) + self.tail)
+        dist.all_gather_into_tensor(self.buf, src, group=self.group)      # communicator set-up happens here, outside any capture
+        torch.cuda.synchronize(dev)
+
+        def post(stream):
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(self.buf, src, group=self.group)
+
+        plan.post = post
+        plan._graph = None          # re-capture with the collective inside
+        self.attached = True
+        return self
+
+    def result(self) -> torch.Tensor:
+        return self.buf
 
     def __call__(self, local: torch.Tensor) -> torch.Tensor:
         if self.world == 1:

@@ -24,8 +24,19 @@ JOINTS_RIGHT = [1, 2, 3, 14, 15, 16]     # mvn/datasets/utils.py:13
 CROP_WIDTH = 192                          # the hard-coded crop width of the flip (utils.py:56,75)
 
 
+_NORM_CACHE = {}
+
+
 def normalisation_params(backbone: str, device) -> torch.Tensor:
-    """[mean R,G,B | std R,G,B] exactly as data_prefetcher.__init__ builds them (utils.py:24-29), fp32."""
+    """[mean R,G,B | std R,G,B] exactly as data_prefetcher.__init__ builds them (utils.py:24-29), fp32.  Built once per
+    (backbone, device) like the prefetcher does in its constructor: the upload is a synchronous pageable copy."""
+    key = (backbone, str(torch.device(device)))
+    if key not in _NORM_CACHE:
+        _NORM_CACHE[key] = _normalisation_params(backbone, device)
+    return _NORM_CACHE[key]
+
+
+def _normalisation_params(backbone: str, device) -> torch.Tensor:
     if backbone in ("hrnet_32", "hrnet_48"):
         mean = torch.tensor([0.485, 0.456, 0.406])
         std = torch.tensor([0.229, 0.224, 0.225])

@@ -16,16 +16,48 @@ def default_use_tc():
 
 
 def state_version(module: torch.nn.Module):
-    """Cheap change detector: sum of tensor version counters + storage pointers of the first/last tensors."""
-    v = 0
-    for t in module.parameters():
-        v += t._version
-    for t in module.buffers():
-        v += t._version
-    return v
+    """Change detector for the packed weights of a plan: a fingerprint of every parameter and buffer -- identity of the
+    tensor object, address of its storage and its autograd version counter.  It changes when a tensor is replaced
+    (``load_state_dict(assign=True)``, ``.to()``), re-allocated, or written in place through the tensor itself
+    (``load_state_dict``, ``p.copy_()``, optimiser steps).  Writes that bypass the version counter -- ``p.data.add_(1)``,
+    ``p.data.copy_(w)`` -- are invisible to any cheap check: call ``invalidate_weights()`` on the model after such edits."""
+    return hash(tuple((id(t), t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers())))
 
 
-class BackboneRuntimeMixin:
+class PlanCacheMixin:
+    """Device plans hold ctypes handles, CUDA streams and events: they are a cache, not state.  They are dropped when the
+    parameters move (``_apply``), never copied or pickled (``copy.deepcopy(model)`` / ``torch.save(model)`` work after a
+    forward), and ``invalidate_weights()`` forces the next forward to repack every weight blob."""
+
+    def invalidate_weights(self):
+        """Force a repack of the packed device weights on the next forward.  Needed only after edits that bypass the
+        tensors' version counters (``p.data.<op>_()``, raw pointer writes); every other change is detected."""
+        for ent in self.__dict__.get("_plans", {}).values():
+            ent[1] = None
+        for m in self.children():
+            if isinstance(m, PlanCacheMixin):
+                m.invalidate_weights()
+
+    def _apply(self, fn, *a, **k):
+        self.__dict__["_plans"] = {}            # .to()/.cuda()/.half() move the parameters: drop device plans
+        return super()._apply(fn, *a, **k)
+
+    def __getstate__(self):
+        st = dict(super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__)
+        st["_plans"] = {}
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_plans" else copy.deepcopy(v, memo)
+        return new
+
+
+class BackboneRuntimeMixin(PlanCacheMixin):
     """Lets a backbone be called on its own: NCHW in -> list of 4 NCHW maps (reference signature)."""
 
     def forward(self, x):

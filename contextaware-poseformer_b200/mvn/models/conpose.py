@@ -3,14 +3,15 @@
 Same constructor (``CA_PF(config, device)``, conpose.py:11-27), attributes (``backbone``, ``volume_net``),
 ``state_dict`` layout and ``forward(images[B,H,W,3], keypoints_2d_cpn[B,17,2], keypoints_2d_cpn_crop[B,17,2])
 -> [B,1,17,3]`` including the in-place normalisation of the caller's crop tensor (conpose.py:34-35).
-Inference only: the reference's training step (volume_net backward) is not part of this path.
+Inference only: outputs are detached (non-differentiable); the reference's training step (volume_net backward,
+SURVEY.md section 8 f2) goes through ``capf_b200.train`` instead.
 """
 import torch
 from torch import nn
 
 from ... import lib, program
 from . import pose_hrnet
-from ._runtime import default_precision, default_use_tc, state_version
+from ._runtime import PlanCacheMixin, default_precision, default_use_tc, state_version
 from .networks import network
 from .pose_dformer import PoseTransformer
 
@@ -18,7 +19,7 @@ CPN_OUTPUT_SHAPE = (64, 48)     # cpn/test_config.py:24
 CPN_NUM_CLASS = 17              # cpn/test_config.py:16
 
 
-class CA_PF(nn.Module):
+class CA_PF(PlanCacheMixin, nn.Module):
     _variant = "h36m"          # program variant; the MPI-INF-3DHP subclass (capf_b200.mpi) overrides it
 
     def __init__(self, config, device="cuda:0", precision=None, use_cuda_graph=False):
@@ -41,6 +42,7 @@ class CA_PF(nn.Module):
         self.precision = precision or default_precision()
         self.use_cuda_graph = use_cuda_graph
         self._plans = {}
+        self._warned_train = False
 
     # -- plans -------------------------------------------------------------------------------------------
     def plan_for(self, B, H, W, device, debug_records=False):
@@ -68,27 +70,35 @@ class CA_PF(nn.Module):
         plan = self.plan_for(B, H, W, device)
         return {k: plan.tensor(b) for k, b in plan.prog.inputs.items()}
 
-    def _apply(self, fn, *a, **k):
-        self._plans = {}            # .to()/.cuda()/.half() move the parameters: drop device plans
-        return super()._apply(fn, *a, **k)
-
     # -- forward -----------------------------------------------------------------------------------------
     def forward(self, images, keypoints_2d_cpn, keypoints_2d_cpn_crop):
         if not (images.is_cuda and keypoints_2d_cpn.is_cuda and keypoints_2d_cpn_crop.is_cuda):
             raise lib.CapfError("CA_PF runs on a B200 through libcapf_b200; got CPU tensors (there is no CPU path)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.volume_net.parameters()) and self.training:
-            raise NotImplementedError("training (volume_net backward) is outside this inference path; "
-                                      "call under torch.no_grad() / model.eval()")
+        if self.volume_net.training:
+            # the reference in train() mode applies DropPath and returns a differentiable tensor (train.py:186-201); this
+            # path has eval semantics only (folded BN running statistics, no DropPath) and its output carries no graph
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.volume_net.parameters()):
+                raise NotImplementedError("training (volume_net backward) is outside this inference path; "
+                                          "call under torch.no_grad() / model.eval()")
+            if not self._warned_train:
+                import warnings
+                warnings.warn("CA_PF.forward: volume_net is in train() mode, but this path always runs with eval semantics "
+                              "(no DropPath, BN running statistics); outputs are not differentiable", stacklevel=2)
+                self._warned_train = True
         B, H, W, C = images.shape
-        if C != 3 or tuple(keypoints_2d_cpn.shape) != (B, self.num_joints, 2):
+        J = self.num_joints
+        if C != 3 or tuple(keypoints_2d_cpn.shape) != (B, J, 2):
             raise ValueError("expected images [B,H,W,3] and keypoints [B,17,2]")
+        if tuple(keypoints_2d_cpn_crop.shape) != (B, J, 2):
+            # conpose.py:34-35 normalises [..., :2]; anything but a [B,17,2] tensor would be mis-strided by the float2 kernel
+            raise ValueError(f"keypoints_2d_cpn_crop must be [B,{J},2], got {tuple(keypoints_2d_cpn_crop.shape)}")
         dev = images.device
         plan = self.plan_for(B, H, W, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
 
         # conpose.py:34-35 mutates the caller's tensor in place; keep that contract.
         crop = keypoints_2d_cpn_crop
-        if crop.dtype == torch.float32 and crop.is_contiguous():
+        if crop.dtype == torch.float32 and crop.is_contiguous() and crop.data_ptr() % 8 == 0:
             lib.check(lib.load().capf_crop_normalize(crop.data_ptr(), B * self.num_joints, stream), "capf_crop_normalize")
             ref_src = crop
         else:

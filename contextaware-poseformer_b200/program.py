@@ -677,6 +677,7 @@ class Plan:
         self._h = h
         self._L = L
         self._graph = None
+        self.post = None           # optional callable(torch stream): enqueued after every full run (e.g. the output all-gather)
 
     def _ptr(self, b):
         if b is None:
@@ -747,6 +748,8 @@ class Plan:
         segs = self._schedule() if full else None
         if not full or not self._side:
             lib.check(self._L.capf_plan_run(self._h, first, count, s), "capf_plan_run")
+            if full and self.post is not None:
+                self.post(st)
             return
         streams = [st] + self._side
         for lane, k0, n, waits, record in segs:
@@ -758,6 +761,8 @@ class Plan:
                 self._events[k0 + n - 1].record(ls)
         for k in self._tails:                                   # join: the caller's stream owns the result again
             st.wait_event(self._events[k])
+        if self.post is not None:
+            self.post(st)
 
     def op_kernel(self, k: int) -> str:
         """Name (and tile shape) of the kernel op k launches, as reported by the library."""
@@ -813,7 +818,8 @@ class Plan:
             self.run()                      # warm-up outside capture (lazy module load, func attributes)
         side.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=side):
+        # thread_local: a collective in `post` keeps NCCL's watchdog thread alive next to the capture
+        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local" if self.post is not None else "global"):
             self.run(stream=side)
         self._graph = g
         return g

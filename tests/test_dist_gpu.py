@@ -1,0 +1,71 @@
+"""GPU, 2 ranks over NCCL: the gathered [N*B,1,17,3] of the frame-sharded forward equals the single-GPU forward of the
+same frames -- with the all-gather as a separate launch and as the last node of the forward's CUDA graph.
+Skipped on a one-GPU box (the driver's 1-GPU test tier); `gpurun --gpus 2` runs it."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import capf_b200
+    import protocol
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        B, H, W = 6, 64, 64
+        cfg = capf_b200.make_config("hrnet_32")
+        res = []
+        for graph in (False, True):
+            model = capf_b200.CA_PF(cfg, precision="fp16", use_cuda_graph=graph).eval()
+            w = protocol.make_weights([(k, tuple(v.shape)) for k, v in model.state_dict().items()], 0)
+            model.load_state_dict(w, strict=True)
+            model = model.to(dev)
+            images, kp2d, crop = protocol.make_inputs(world * B, H, W, 21)
+            with torch.no_grad():
+                # (a) sharded_forward: eager all_gather_into_tensor after the local forward
+                full_a = capf_b200.dist.sharded_forward(model, images.to(dev), kp2d.to(dev), crop.clone().to(dev)).clone()
+                # (b) the gather attached to the plan (inside the CUDA graph when graph=True)
+                gat = capf_b200.dist.OutputGatherer([B] * world, (1, 17, 3), dev).attach(model, B, H, W)
+                s, e = capf_b200.dist.shard_bounds(world * B, rank, world)
+                for _ in range(2):          # second call replays the captured graph
+                    model(images[s:e].to(dev), kp2d[s:e].to(dev), crop[s:e].clone().to(dev))
+                    full_b = gat.result().clone()
+                torch.cuda.synchronize(dev)
+                # single-GPU forward of ALL frames on this rank
+                solo = capf_b200.CA_PF(cfg, precision="fp16").eval()
+                solo.load_state_dict(w, strict=True)
+                want = solo.to(dev)(images.to(dev), kp2d.to(dev), crop.clone().to(dev))
+            res.append((graph, bool(torch.equal(full_a, want)), bool(torch.equal(full_b, want)), tuple(full_b.shape)))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_nccl_gather_equals_single_gpu_forward():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+    for rank, rows in res:
+        for graph, eq_a, eq_b, shape in rows:
+            assert eq_a and eq_b and shape == (12, 1, 17, 3), (rank, graph, eq_a, eq_b, shape)

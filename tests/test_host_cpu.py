@@ -170,3 +170,45 @@ def test_lane_parallel_memory_plan_is_race_free():
         for b in op.outs:
             if isinstance(b, program.Buf):
                 writer[b.root] = k
+
+
+def test_state_fingerprint_and_plan_cache_hygiene():
+    """the weight-change detector must see tensor replacement and in-place loads (a sum of version counters
+    cancels / misses them); plans are a cache -- never deep-copied or pickled; invalidate_weights() forces a repack."""
+    import pickle
+    import capf_b200
+    from capf_b200.mvn.models._runtime import state_version
+    m = capf_b200.CA_PF(capf_b200.make_config("hrnet_32"))
+    v0 = state_version(m)
+    assert state_version(m) == v0
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)                                   # in-place copy_: version counters move
+    v1 = state_version(m)
+    assert v1 != v0
+    m.load_state_dict(sd, assign=True)                      # tensors replaced: ids / storage move
+    v2 = state_version(m)
+    assert v2 != v1
+    p, q = list(m.volume_net.parameters())[:2]
+    with torch.no_grad():
+        p.add_(1.0)
+    assert state_version(m) != v2
+    # a fake cached plan (ctypes handles cannot be pickled / deep-copied)
+    import ctypes
+    m._plans[("fake",)] = [ctypes.c_void_p(1), state_version(m)]
+    m.backbone.__dict__.setdefault("_plans", {})[("fake",)] = [ctypes.c_void_p(2), 0]
+    c = copy.deepcopy(m)
+    assert c._plans == {} and c.backbone.__dict__.get("_plans", {}) == {} and len(m._plans) == 1
+    assert torch.equal(c.volume_net.head[1].weight, m.volume_net.head[1].weight)
+    r = pickle.loads(pickle.dumps(m))
+    assert r._plans == {} and r.backbone.__dict__.get("_plans", {}) == {}
+    m.invalidate_weights()
+    assert m._plans[("fake",)][1] is None and m.backbone._plans[("fake",)][1] is None
+    m.to("cpu")
+    assert m._plans == {}
+
+
+def test_forward_rejects_misshaped_crop_without_gpu():
+    import capf_b200
+    m = capf_b200.CA_PF(capf_b200.make_config("hrnet_32")).eval()
+    with pytest.raises(lib.CapfError):           # CPU tensors: there is no CPU path
+        m(torch.zeros(1, 64, 64, 3), torch.zeros(1, 17, 2), torch.zeros(1, 17, 2))
