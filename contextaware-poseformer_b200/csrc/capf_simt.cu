@@ -1464,6 +1464,27 @@ __global__ void __launch_bounds__(256) cast_kernel(size_t n, const TI* __restric
     y[i] = from_f<TO>(to_f<TI>(x[i]));
 }
 
+// fp32 -> bf16 hi | lo planes: row r of x ([rows][C]) becomes [hi(x) (C) | bf16(x - hi) (C)] -- the A operand of the
+// split-operand (bf16x3) tcgen05 GEMMs: hi * Wh + lo * Wh + hi * Wl reproduces the fp32 product to ~2^-16.
+__global__ void __launch_bounds__(256) cast_split_kernel(size_t groups, int C8, const float* __restrict__ x, __nv_bfloat16* __restrict__ y) {
+  pdl_wait();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < groups; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / C8;
+    const int c = (int)(i - row * C8) * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + i * 8)), b = __ldg(reinterpret_cast<const float4*>(x + i * 8) + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      hi[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+      lo[e] = __fsub_rn(v[e], hi[e]);
+    }
+    __nv_bfloat16* dst = y + row * (size_t)(16 * C8) + c;
+    *reinterpret_cast<uint4*>(dst) = pack8<__nv_bfloat16>(hi);
+    *reinterpret_cast<uint4*>(dst + 8 * C8) = pack8<__nv_bfloat16>(lo);
+  }
+}
+
 int launch_embed_coord(const capf_op& op, cudaStream_t st) {
   int B = op.i[0], J = op.i[1], D = op.i[2], slabs = op.i[3];
   if (B <= 0 || J <= 0 || D <= 0 || slabs <= 0 || !op.in[0] || !op.in[1] || !op.in[2] || !op.in[3] || !op.out[0])
@@ -1492,6 +1513,12 @@ int launch_cast(const capf_op& op, cudaStream_t st) {
   size_t n = (size_t)(uint32_t)op.i[0] | ((size_t)(uint32_t)op.i[1] << 31);
   if (!n || !op.in[0] || !op.out[0]) return set_error(CAPF_ERR_ARG, "cast: bad arguments");
   int blocks = ew_blocks(n);
+  if (op.i[2] > 0) {                       // split planes: i[2] = channels per row
+    if (op.dtype_in != CAPF_F32 || op.dtype_out != CAPF_BF16 || (op.i[2] & 7) || n % (size_t)op.i[2])
+      return set_error(CAPF_ERR_UNSUPPORTED, "cast (split planes): needs f32 -> bf16 and a channel count that is a multiple of 8");
+    launch_k(cast_split_kernel, dim3(ew_blocks(n / 8)), dim3(256), 0, st, n / 8, op.i[2] / 8, (const float*)op.in[0], (__nv_bfloat16*)op.out[0]);
+    return check_launch("cast_split");
+  }
   if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_F16)
     launch_k(cast_kernel<float, __half>, dim3(blocks), dim3(256), 0, st, n, (const float*)op.in[0], (__half*)op.out[0]);
   else if (op.dtype_in == CAPF_F32 && op.dtype_out == CAPF_BF16)

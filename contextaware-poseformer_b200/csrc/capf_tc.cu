@@ -43,7 +43,9 @@ struct TcP {
   int Cout, BN, n_tiles_n;
   int num_chunks;           // K chunks = taps * (Cin / kb)
   int kb;                   // elements per chunk: 16 | 32 | 64  (32 | 64 | 128-byte swizzled rows)
-  int cpt;                  // chunks per filter tap = Cin / kb
+  int cpt;                  // chunks per filter tap = Cin / kb (split operands: pass 0 walks the hi|lo planes, 2 * C / kb)
+  int cpt1;                 // split operands only: chunks per tap of pass 1 (the hi plane alone, C / kb); else 0
+  int KH;
   int cps;                  // chunks per pipeline stage = 64 / kb
   int KW, stride, pad;
   int bw, bh, bn;           // conv mode: output-pixel box (x, y, image) of one 128-row tile, bw*bh*bn <= 128
@@ -167,6 +169,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int ix_base = w.tx * p.bw * p.stride - p.pad, iy_base = w.ty * p.bh * p.stride - p.pad, n0 = w.tn * p.bn;
         const int nb0 = w.n_tile * p.BN;
         int r = 0, sx = 0, cc = 0, kcol = 0;       // filter tap (r, sx), channel chunk inside the tap, B column
+        int cpt = p.cpt;                           // split operands: a second pass over the taps with the hi plane only
         for (int c0 = 0; c0 < p.num_chunks; c0 += p.cps) {
           ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const int nc = min(p.cps, p.num_chunks - c0);
@@ -176,14 +179,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           uint32_t b_dst = a_dst + p.a_stage_bytes;
           for (int j = 0; j < nc; ++j) {
             if (p.mode == 1) ptx::tma_load_4d(&mapA, full, a_dst, cc * p.kb, ix_base + sx, iy_base + r, n0);
-            else ptx::tma_load_2d(&mapA, full, a_dst, kcol, m0);
+            else ptx::tma_load_2d(&mapA, full, a_dst, cc * p.kb, m0);
             ptx::tma_load_2d(&mapB, full, b_dst, kcol, nb0);
             a_dst += p.a_chunk_bytes;
             b_dst += p.b_chunk_bytes;
             kcol += p.kb;
-            if (++cc == p.cpt) {
+            if (++cc == cpt) {
               cc = 0;
-              if (++sx == p.KW) { sx = 0; ++r; }
+              if (++sx == p.KW) {
+                sx = 0;
+                if (++r == p.KH && p.cpt1) { r = 0; cpt = p.cpt1; }
+              }
             }
           }
           if (tr) { const int n = (tile - t0) * ((p.num_chunks + p.cps - 1) / p.cps) + c0 / p.cps; if (n < 64) p.trace[64 + n] = clock64(); }
@@ -456,6 +462,7 @@ int tc_conv_supported(const capf_op& op) {
   if (op.dtype_out != CAPF_F16 && op.dtype_out != CAPF_BF16 && op.dtype_out != CAPF_F32) return 0;
   const ConvGeo g = geo_of(op);
   if (g.Cin <= 0 || g.Cin % 16 || g.Cout <= 0 || g.Cout % 16) return 0;
+  if (op.i[18] != 0 && (op.i[18] != 1 || op.dtype_in != CAPF_BF16)) return 0;     // split operands are bf16 hi|lo planes
   if (g.KH < 1 || g.KW < 1 || g.KH > 7 || g.KW > 7 || g.stride < 1 || g.stride > 2 || g.pad < 0) return 0;
   if (g.N <= 0 || g.H <= 0 || g.W <= 0) return 0;
   if (g.Ho != (g.H + 2 * g.pad - g.KH) / g.stride + 1 || g.Wo != (g.W + 2 * g.pad - g.KW) / g.stride + 1) return 0;
@@ -515,14 +522,15 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   const ConvGeo g = geo_of(op);
   TcConvState* s = new (std::nothrow) TcConvState();
   if (!s) return set_error(CAPF_ERR_ARG, "tc_conv_prepare: out of host memory");
-  if (op.i[13] == 0 && tc2_supported(op)) {     // wide Linears over many rows: CTA pairs (cta_group::2)
+  const bool split = op.i[18] == 1;             // A = [.., 2 * Cin] bf16 (hi | lo planes), B = [Cout][taps * 3 * Cin], see capf_b200.h
+  if (!split && op.i[13] == 0 && tc2_supported(op)) {     // wide Linears over many rows: CTA pairs (cta_group::2)
     e = tc2_prepare(op, &s->two);
     if (e) { delete s; return e; }
     *out = s;
     return CAPF_OK;
   }
   // i[13]: kernel variant hint (0 = automatic, 1 = per-tap TMA GEMM, 2 = halo band); tests use it for A/B parity
-  if (op.i[13] != 1 && tc_halo_supported(op)) {
+  if (!split && op.i[13] != 1 && tc_halo_supported(op)) {
     e = tc_halo_prepare(op, &s->halo);
     if (e) { delete s; return e; }
     *out = s;
@@ -534,10 +542,11 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   const bool rows = (g.KH == 1 && g.KW == 1 && g.stride == 1 && g.pad == 0);
   p.mode = rows ? 0 : 1;
   p.kb = g.Cin % 64 == 0 ? 64 : g.Cin % 32 == 0 ? 32 : 16;
-  p.cpt = g.Cin / p.kb;
+  p.cpt = (split ? 2 : 1) * g.Cin / p.kb;
+  p.cpt1 = split ? g.Cin / p.kb : 0;
   p.cps = 64 / p.kb;
-  p.num_chunks = g.KH * g.KW * p.cpt;
-  p.KW = g.KW; p.stride = g.stride; p.pad = g.pad;
+  p.num_chunks = g.KH * g.KW * (p.cpt + p.cpt1);
+  p.KW = g.KW; p.KH = g.KH; p.stride = g.stride; p.pad = g.pad;
   p.Cout = g.Cout; p.Ho = g.Ho; p.Wo = g.Wo; p.Nimg = g.N;
   p.act = g.act;
   p.bias = (const float*)op.in[2];
@@ -546,7 +555,8 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   p.trace = (long long*)op.in[4];     // debug only (NULL in every program the host layer builds)
   p.M = g.N * g.Ho * g.Wo;
   const int swz = p.kb * 2;
-  const int K = g.KH * g.KW * g.Cin;
+  const int K = g.KH * g.KW * g.Cin * (split ? 3 : 1);      // GEMM depth (3x with split operands: hi*Wh + lo*Wh + hi*Wl)
+  const int Ca = g.Cin * (split ? 2 : 1);                   // channels of the A tensor in memory
   const int osz = op.dtype_out == CAPF_F32 ? 4 : 2;
 
   // ---- epilogue staging: two tiles per warp with a residual (one being filled by cp.async), else one ------------
@@ -649,14 +659,14 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   // ---- tensor maps -------------------------------------------------------------------------------------
   const CUtensorMapDataType dt = op.dtype_in == CAPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   if (rows) {
-    cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)p.M};
-    cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)Ca, (cuuint64_t)p.M};
+    cuuint64_t strides[1] = {(cuuint64_t)Ca * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.kb, (cuuint32_t)(128 * p.msub)};
     cuuint32_t es[2] = {1, 1};
     e = tc_encode_map(&s->mapA, dt, 2, op.in[0], dims, strides, box, es, swz, "A rows");
   } else {
-    cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
-    cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.W * g.Cin * 2, (cuuint64_t)g.H * g.W * g.Cin * 2};
+    cuuint64_t dims[4] = {(cuuint64_t)Ca, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)Ca * 2, (cuuint64_t)g.W * Ca * 2, (cuuint64_t)g.H * g.W * Ca * 2};
     cuuint32_t box[4] = {(cuuint32_t)p.kb, (cuuint32_t)(p.bw * g.stride), (cuuint32_t)(p.bh * g.stride), (cuuint32_t)p.bn};
     cuuint32_t es[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
     e = tc_encode_map(&s->mapA, dt, 4, op.in[0], dims, strides, box, es, swz, "A conv");
@@ -715,7 +725,7 @@ void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
   if (s->blk) { tc_block_describe(s->blk, buf, cap); return; }
   if (s->two) { tc2_describe(s->two, buf, cap); return; }
   if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
-  snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages]", 128 * s->p.msub, s->p.BN, s->p.num_stages);
+  snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages%s]", 128 * s->p.msub, s->p.BN, s->p.num_stages, s->p.cpt1 ? ", bf16x3 split operands" : "");
 }
 
 void tc_conv_release(TcConvState* s) {

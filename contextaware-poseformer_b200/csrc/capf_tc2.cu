@@ -36,6 +36,7 @@ struct Tc2P {
   const float* bias;
   const void* res;
   void* out;
+  long long* trace;          // optional (debug, op.in[4]): clock64 timeline of the leader CTA of pair 0, tools/gemm_trace.py
 };
 
 namespace ptx2 {
@@ -101,6 +102,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx2::cluster_ctarank();
   const bool leader = rank == 0;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[0] = clock64();
+    p.trace[1] = (long long)gt;
+  }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapA);
@@ -126,8 +134,12 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   ptx2::cluster_sync();               // barriers of both CTAs initialised, TMEM of both allocated
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (tr && threadIdx.x == 0) p.trace[2] = clock64();
   pdl_trigger();
-  pdl_wait();
+  // griddepcontrol.wait is per thread: every role waits before it touches anything the predecessor produced (A, the
+  // residual, the output).  The producer first requests the WEIGHT halves of its first stages -- they do not depend
+  // on the predecessor -- so their HBM/L2 latency overlaps the predecessor's tail.
+  if (warp != 0) pdl_wait();
 
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int t0 = (int)(((long long)p.num_tiles * pair) / n_pairs);
@@ -137,18 +149,31 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =========================
     if (ptx::elect_one()) {
+      int pre = 0;                                  // stages of the first tile whose B half is already in flight
+      if (t0 < t1) {
+        const int nb0 = (t0 % p.n_tiles_n) * p.BN + (int)rank * half_bn;
+        pre = min(p.num_stages, p.num_k);
+        for (int ks = 0; ks < pre; ++ks) {
+          if (leader) ptx::mbar_arrive_expect_tx(bar_full + 8 * ks, (uint32_t)(2 * p.stage_bytes));
+          ptx2::tma_load_2d_2sm(&mapB, ptx2::mapa(bar_full + 8 * ks, 0u), stage0 + ks * p.stage_bytes + T2_A_BYTES, ks * 64, nb0);
+        }
+      }
+      pdl_wait();
+      if (tr) p.trace[3] = clock64();
       uint32_t stage = 0, phase = 0;
       for (int tile = t0; tile < t1; ++tile) {
         const int n_tile = tile % p.n_tiles_n, m_tile = tile / p.n_tiles_n;
         const int m0 = m_tile * 256 + (int)rank * 128;
         const int nb0 = n_tile * p.BN + (int)rank * half_bn;
         for (int ks = 0; ks < p.num_k; ++ks) {
-          ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          const bool primed = tile == t0 && ks < pre;
+          if (!primed) ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t full_leader = ptx2::mapa(bar_full + 8 * stage, 0u);
-          if (leader) ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(2 * p.stage_bytes));
+          if (leader && !primed) ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(2 * p.stage_bytes));
           const uint32_t a_dst = stage0 + stage * p.stage_bytes;
           ptx2::tma_load_2d_2sm(&mapA, full_leader, a_dst, ks * 64, m0);
-          ptx2::tma_load_2d_2sm(&mapB, full_leader, a_dst + T2_A_BYTES, ks * 64, nb0);
+          if (!primed) ptx2::tma_load_2d_2sm(&mapB, full_leader, a_dst + T2_A_BYTES, ks * 64, nb0);
+          if (tr) { const int n = (tile - t0) * p.num_k + ks; if (n < 64) p.trace[64 + n] = clock64(); }
           if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -172,6 +197,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (int i = 0; i < 4; ++i) ptx2::umma2_f16(d_tmem, a_desc + 2u * i, b_desc + 2u * i, p.idesc, (accumulate | (uint32_t)i) ? 1u : 0u);
             ptx2::umma2_commit_mc(bar_empty + 8 * stage);
             if (ks + 1 == p.num_k) ptx2::umma2_commit_mc(bar_tfull + 8 * acc);
+            if (tr) { const int n = (tile - t0) * p.num_k + ks; if (n < 64) p.trace[128 + n] = clock64(); }
           }
           __syncwarp();
           accumulate = 1;
@@ -223,6 +249,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       __syncwarp();
       ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
       ptx::tc_fence_after();
+      if (tr && warp == 4 && lane == 0 && tile - t0 < 16) p.trace[192 + 2 * (tile - t0)] = clock64();
       uint32_t buf = 0;
       for (int s = 0; s < nslabs; ++s) {
         const int c0 = cbeg + s * SW;
@@ -271,6 +298,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         ptx::tc_fence_before();
         ptx2::mbar_arrive_cluster(tempty_leader0 + 8 * acc);
       }
+      if (tr && warp == 4 && lane == 0 && tile - t0 < 16) p.trace[193 + 2 * (tile - t0)] = clock64();
       if (++acc == (uint32_t)p.nacc) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -279,6 +307,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   __syncthreads();
   ptx2::cluster_sync();               // the peer may still be reading operands of / arriving at this CTA
   if (warp == 2) ptx2::tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+  if (tr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[4] = clock64();
+    p.trace[5] = (long long)gt;
+    p.trace[6] = 2; p.trace[7] = p.BN; p.trace[8] = p.num_stages; p.trace[9] = p.num_tiles; p.trace[10] = gridDim.x; p.trace[11] = p.nacc;
+  }
 }
 
 // =======================================================================================================
@@ -318,6 +353,7 @@ int tc2_prepare(const capf_op& op, Tc2State** out) {
   p.bias = (const float*)op.in[2];
   p.res = op.in[3];
   p.out = op.out[0];
+  p.trace = (long long*)op.in[4];     // debug only (NULL in every program the host layer builds)
   p.num_k = p.K / 64;
   const int osz = op.dtype_out == CAPF_F32 ? 4 : 2;
   p.stg_bufs = p.res ? 2 : 1;

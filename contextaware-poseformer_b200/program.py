@@ -10,6 +10,9 @@ Precision policies
   fp32 : every tensor f32, CUDA-core kernels                        (parity mode, <=1e-5 of the oracle)
   fp16 : backbone activations/weights f16 (f32 accumulate), lifter token stream f32 with f16 GEMM operands
   bf16 : same with bfloat16
+  bf16x3: fp32 storage everywhere, every conv / Linear on the tensor cores with SPLIT operands: x = hi + lo and w = Wh + Wl
+         in bfloat16 (hi = bf16(v), lo = bf16(v - hi)), three products hi*Wh + lo*Wh + hi*Wl accumulated in fp32 -- operand
+         precision 2^-16, the tensor-core mode that meets the reference's fp32 results to 1e-3 (observed ~1e-5)
 """
 import os
 import re
@@ -128,6 +131,27 @@ def conv_weight_packer(wkey, bnkey, dtype, layout):
     return pack
 
 
+def _split_bf16(w):
+    """w (float64/32) -> (hi, lo) bfloat16 with hi + lo == w to ~2^-17."""
+    w32 = w.to(torch.float32)
+    hi = w32.to(torch.bfloat16)
+    lo = (w32 - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi, lo
+
+
+def split_weight_packer(get_w):
+    """B operand of a split-operand GEMM (CAPF_OP_CONV2D i[18] = 1): [Cout][taps * (Wh | Wh)][taps * Wl], matching the A
+    walk of the kernel: pass 0 over the (hi | lo) planes of every tap, pass 1 over the hi plane of every tap."""
+    def pack(state):
+        w = get_w(state)                                    # [Cout, KH, KW, Cin]
+        cout = w.shape[0]
+        hi, lo = _split_bf16(w)
+        p0 = torch.cat([hi, hi], dim=-1).reshape(cout, -1)  # per tap: Wh for the hi plane, Wh for the lo plane
+        p1 = lo.reshape(cout, -1)
+        return torch.cat([p0, p1], dim=1).contiguous()
+    return pack
+
+
 def conv_bias_packer(wkey, bnkey):
     def pack(state):
         return _fold(state, wkey, bnkey)[1].to(torch.float32)
@@ -157,8 +181,10 @@ class ProgramBuilder:
         self.shapes = shapes          # state_dict key -> shape (for channel counts)
         self.prefix = "backbone."
         prec = program.precision
-        self.act_dt = {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[prec]
+        self.act_dt = {"fp32": "f32", "fp16": "f16", "bf16": "bf16", "bf16x3": "f32"}[prec]
         self.use_tc = use_tc and prec != "fp32"
+        self.split = self.use_tc and prec == "bf16x3"
+        self._split_cache = {}
         self._n = 0
 
     # -- helpers ---------------------------------------------------------------------------------------
@@ -173,6 +199,8 @@ class ProgramBuilder:
 
     def _conv_impl(self, cin, cout, k, stride, dt_in):
         """Kernel family for a conv/linear.  tcgen05 needs 16-bit operands and TMA-friendly channel counts."""
+        if self.split and dt_in == "f32":      # fp32 tensors, split into bf16 hi|lo planes in front of the GEMM
+            return lib.IMPL_TCGEN05 if (cin % 16 == 0 and cout % 16 == 0 and stride <= 2 and k <= 7) else lib.IMPL_SIMT
         if not self.use_tc or dt_in == "f32":
             return lib.IMPL_SIMT
         if cin % 16 or cout % 16 or stride > 2 or k > 7:
@@ -194,16 +222,36 @@ class ProgramBuilder:
         wdt = "f32" if dt_in == "f32" else dt_in
         layout = "ck" if impl == lib.IMPL_TCGEN05 else "kc"
         K = k * k * x.C
-        w = WSlot(f"w:{cname}", (K, cout) if layout == "kc" else (cout, K), wdt, conv_weight_packer(wkey, bnkey, wdt, layout))
         b = WSlot(f"b:{cname}", (cout,), "f32", conv_bias_packer(wkey, bnkey))
         out = self._buf(cname, (B, Ho, Wo, cout), dt_out)
         acode = {arch.NONE: lib.ACT_NONE, arch.RELU: lib.ACT_RELU, arch.GELU: lib.ACT_GELU}[act]
+        extra = []
+        if self.split and impl == lib.IMPL_TCGEN05 and dt_in == "f32":
+            # backbone tensors are written once (every conv gets a fresh buffer): share the planes between the consumers
+            key = id(src)
+            if key not in self._split_cache:
+                self._split_cache[key] = self._split_planes(src, B * x.H * x.W, x.C, (B, x.H, x.W, 2 * x.C), self.prefix + cname)
+            src = self._split_cache[key]
+            dt_in = wdt = "bf16"
+            w = WSlot(f"w:{cname}", (cout, 3 * K), "bf16",
+                      split_weight_packer(lambda st: _fold(st, wkey, bnkey)[0].permute(0, 2, 3, 1)))
+            extra = [1, 0, 0, 0, 0, 1]              # i[13] = per-tap kernel, i[18] = split operands
+        else:
+            w = WSlot(f"w:{cname}", (K, cout) if layout == "kc" else (cout, K), wdt, conv_weight_packer(wkey, bnkey, wdt, layout))
         self._emit(lib.OP_CONV2D, dt_in, dt_out,
-                   [B, x.H, x.W, x.C, cout, k, k, stride, pad, Ho, Wo, acode, impl], [],
+                   [B, x.H, x.W, x.C, cout, k, k, stride, pad, Ho, Wo, acode, impl] + extra, [],
                    [src, w, b, residual.ref if residual is not None else None], [out],
                    tag=self.prefix + cname, flops=2 * B * Ho * Wo * cout * K)
         self.p.ops[-1].nbytes = src.nbytes + out.nbytes + (out.nbytes if residual is not None else 0) + K * cout * _ITEMSIZE[wdt] + 4 * cout
         return arch.T(Ho, Wo, cout, out)
+
+    def _split_planes(self, src: Buf, rows, C, shape, tag):
+        """CAPF_OP_CAST in split mode: fp32 [rows][C] -> bf16 [rows][hi (C) | lo (C)], the A operand of a split GEMM."""
+        out = self._buf("split", shape, "bf16")
+        n = rows * C
+        self._emit(lib.OP_CAST, "f32", "bf16", [n & 0x7fffffff, n >> 31, C], [], [src], [out], tag=tag + ".split")
+        self.p.ops[-1].nbytes = 8 * n
+        return out
 
     def fuse(self, terms, relu=True):
         B = self.p.B
@@ -245,12 +293,20 @@ class ProgramBuilder:
         impl = self._conv_impl(cin, cout, 1, 1, dt_in)
         wdt = "f32" if dt_in == "f32" else dt_in
         layout = "ck" if impl == lib.IMPL_TCGEN05 else "kc"
-        w = WSlot(f"w:{tag}", (cin, cout) if layout == "kc" else (cout, cin), wdt, linear_weight_packer(wkeys, wdt, layout))
         b = WSlot(f"b:{tag}", (cout,), "f32", vec_packer(bkeys)) if bkeys else None
         if out is None:
             out = self._buf(tag, (rows, cout), dt_out)
         acode = {arch.NONE: lib.ACT_NONE, arch.RELU: lib.ACT_RELU, arch.GELU: lib.ACT_GELU}[act]
-        self._emit(lib.OP_CONV2D, dt_in, dt_out, [rows, 1, 1, cin, cout, 1, 1, 1, 0, 1, 1, acode, impl], [],
+        extra = []
+        if self.split and impl == lib.IMPL_TCGEN05 and dt_in == "f32":
+            x = self._split_planes(x, rows, cin, (rows, 2 * cin), tag)
+            dt_in = wdt = "bf16"
+            w = WSlot(f"w:{tag}", (cout, 3 * cin), "bf16", split_weight_packer(
+                lambda st: torch.cat([st[k].detach().to("cpu", torch.float32) for k in wkeys], dim=0).view(cout, 1, 1, cin)))
+            extra = [1, 0, 0, 0, 0, 1]
+        else:
+            w = WSlot(f"w:{tag}", (cin, cout) if layout == "kc" else (cout, cin), wdt, linear_weight_packer(wkeys, wdt, layout))
+        self._emit(lib.OP_CONV2D, dt_in, dt_out, [rows, 1, 1, cin, cout, 1, 1, 1, 0, 1, 1, acode, impl] + extra, [],
                    [x, w, b, residual], [out], tag=tag, flops=2 * rows * cin * cout)
         self.p.ops[-1].nbytes = rows * cin * _ITEMSIZE[dt_in] + rows * cout * _ITEMSIZE[dt_out] * (2 if residual is not None else 1) + \
             cin * cout * _ITEMSIZE[wdt] + 4 * cout
@@ -276,7 +332,7 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
              kp2d [B*17,2] f32, ref [B*17,2] f32 (already normalised, conpose.py:34-35)
     output : out [B*17,3] f32  (== [B,1,17,3])
     """
-    if precision not in ("fp32", "fp16", "bf16"):
+    if precision not in ("fp32", "fp16", "bf16", "bf16x3"):
         raise ValueError(f"precision {precision!r}")
     prog = Program(backbone, precision, B, H, W)
     pb = ProgramBuilder(prog, shapes, use_tc)
@@ -777,19 +833,22 @@ class Plan:
 
     def time_ops(self, passes: int = 2):
         """Per-op device time (ms) of one in-order pass, CUDA events on the launching stream around every op.
-        The last of `passes` passes is returned, so caches are in their steady in-step state (not warm per op)."""
+        The passes are enqueued back to back WITHOUT synchronising in between and the last one is returned: while the
+        GPU works through the earlier passes the host runs ahead, so the measured pass is not host-launch-bound (the gap
+        between two events is the kernel's own duration incl. its launch latency, not the host's issue interval) and
+        caches are in their steady in-step state (not warm per op)."""
         st = torch.cuda.current_stream(self.device)
         n = len(self.prog.ops)
-        ms = [0.0] * n
-        for _ in range(passes):
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        passes = max(1, passes)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n + 1)] for _ in range(passes)]
+        for ev in evs:
             ev[0].record(st)
             for k in range(n):
                 lib.check(self._L.capf_plan_run(self._h, k, 1, st.cuda_stream), "capf_plan_run")
                 ev[k + 1].record(st)
-            st.synchronize()
-            ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(n)]
-        return ms
+        st.synchronize()
+        ev = evs[-1]
+        return [ev[k].elapsed_time(ev[k + 1]) for k in range(n)]
 
     def time_op_repeated(self, k: int, reps: int = 20):
         """Average device time (ms) of `reps` back-to-back launches of op k (must be idempotent: no in-place residual)

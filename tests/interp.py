@@ -34,13 +34,25 @@ class Interp:
     # ---- ops -------------------------------------------------------------------------------------------
     def _op1(self, op):   # CONV2D
         N, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, act, impl = op.i[:13]
-        x = self.t(op.ins[0]).reshape(N, H, W, Cin).float().permute(0, 3, 1, 2)
-        w = self.t(op.ins[1]).float()
-        if impl == lib.IMPL_TCGEN05:
-            w = w.reshape(Cout, KH, KW, Cin).permute(0, 3, 1, 2)
+        if len(op.i) > 18 and op.i[18] == 1:      # split operands (bf16x3): hi * Wh + lo * Wh + hi * Wl, fp32 accumulation
+            xs = self.t(op.ins[0]).reshape(N, H, W, 2 * Cin).float()
+            hi, lo = xs[..., :Cin].permute(0, 3, 1, 2), xs[..., Cin:].permute(0, 3, 1, 2)
+            wp = self.t(op.ins[1]).float().reshape(Cout, -1)
+            T = KH * KW
+            wh = wp[:, :2 * T * Cin].reshape(Cout, KH, KW, 2, Cin)
+            assert torch.equal(wh[:, :, :, 0], wh[:, :, :, 1])
+            wh = wh[:, :, :, 0].permute(0, 3, 1, 2).contiguous()
+            wl = wp[:, 2 * T * Cin:].reshape(Cout, KH, KW, Cin).permute(0, 3, 1, 2).contiguous()
+            y = (F.conv2d((hi + lo).double(), wh.double(), None, stride, pad) + F.conv2d(hi.double(), wl.double(), None, stride, pad))
+            y = y.float().permute(0, 2, 3, 1)
         else:
-            w = w.reshape(KH, KW, Cin, Cout).permute(3, 2, 0, 1)
-        y = F.conv2d(x, w.contiguous(), None, stride, pad).permute(0, 2, 3, 1)
+            x = self.t(op.ins[0]).reshape(N, H, W, Cin).float().permute(0, 3, 1, 2)
+            w = self.t(op.ins[1]).float()
+            if impl == lib.IMPL_TCGEN05:
+                w = w.reshape(Cout, KH, KW, Cin).permute(0, 3, 1, 2)
+            else:
+                w = w.reshape(KH, KW, Cin, Cout).permute(3, 2, 0, 1)
+            y = F.conv2d(x, w.contiguous(), None, stride, pad).permute(0, 2, 3, 1)
         if op.ins[2] is not None:
             y = y + self.t(op.ins[2])
         if act == lib.ACT_GELU:
@@ -176,4 +188,11 @@ class Interp:
 
     def _op12(self, op):  # CAST
         out = self.t(op.outs[0])
+        if len(op.i) > 2 and op.i[2] > 0:         # split planes: rows of C fp32 -> [hi (C) | lo (C)] bf16
+            C = op.i[2]
+            x = self.t(op.ins[0]).reshape(-1, C).float()
+            hi = x.to(torch.bfloat16)
+            lo = (x - hi.float()).to(torch.bfloat16)
+            out.copy_(torch.cat([hi, lo], dim=1).reshape(out.shape))
+            return
         out.copy_(self.t(op.ins[0]).to(out.dtype))

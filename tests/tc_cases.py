@@ -99,3 +99,35 @@ def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=
     tol_row = 0.05 * float(y.abs().mean()) + 0.02
     bad_rows = float((diff.abs().reshape(-1, Cout).amax(dim=1) > tol_row).float().mean())
     return rel, float(diff.abs().max()), bad_rows
+
+
+def run_split_case(case, msub=0):
+    """bf16x3 split-operand GEMM (CAPF_OP_CAST split planes + CAPF_OP_CONV2D i[18] = 1, fp32 in / out) against the plain fp32
+    PyTorch operator on the UN-rounded inputs.  Returns (rel_l2, max_abs)."""
+    from capf_b200 import program
+    name, (N, H, W, Cin, Cout, k, stride), act, use_res, _ = case
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % (1 << 31))
+    pad = k // 2
+    x = torch.randn(N, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = torch.randn(N, Ho, Wo, Cout, generator=g) if use_res else None
+    y = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), stride, pad).permute(0, 2, 3, 1).float()
+    if act == lib.ACT_GELU:
+        y = F.gelu(y)
+    if use_res:
+        y = y + res
+    if act == lib.ACT_RELU:
+        y = F.relu(y)
+    wp = program.split_weight_packer(lambda st: w.permute(0, 2, 3, 1))(None).to(DEV)
+    assert tuple(wp.shape) == (Cout, 3 * k * k * Cin)
+    xs = torch.empty(N, H, W, 2 * Cin, dtype=torch.bfloat16, device=DEV)
+    n = x.numel()
+    run_op(lib.OP_CAST, torch.float32, torch.bfloat16, [n & 0x7fffffff, n >> 31, Cin], [], [x.to(DEV)], [xs])
+    out = torch.full((N, Ho, Wo, Cout), float("nan"), dtype=torch.float32, device=DEV)
+    ints = [N, H, W, Cin, Cout, k, k, stride, pad, Ho, Wo, act, lib.IMPL_TCGEN05, 1, 0, msub, 0, 0, 1]
+    run_op(lib.OP_CONV2D, torch.bfloat16, torch.float32, ints, [], [xs, wp, bias.to(DEV), res.to(DEV) if use_res else None], [out])
+    d = out.cpu() - y
+    d = torch.where(torch.isfinite(d), d, torch.full_like(d, 1e3))
+    return float(d.double().norm() / y.double().norm()), float(d.abs().max())

@@ -29,6 +29,20 @@ def test_tc_gemm_tile_heights(case, msub):
     assert bad_rows == 0.0 and rel < tol
 
 
+SPLIT_CASES = [c for c in TC_CASES if c[1][3] % 16 == 0]
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES, ids=[c[0] for c in SPLIT_CASES])
+@pytest.mark.parametrize("msub", [0, 1, 2], ids=["auto", "m128", "m256"])
+def test_split_operand_gemm_is_fp32_class(case, msub):
+    """precision "bf16x3": x = hi + lo, w = Wh + Wl in bfloat16, hi*Wh + lo*Wh + hi*Wl on the tensor cores (two passes over
+    the taps inside one launch) -- against the fp32 operator on un-rounded inputs: operand precision 2^-16, so ~1e-5."""
+    from tc_cases import run_split_case
+    rel, max_abs = run_split_case(case, msub)
+    print(f"{case[0]} split msub={msub}: rel-L2 {rel:.3e} max-abs {max_abs:.3e}")
+    assert rel < 3e-5
+
+
 TWO_CTA_CASES = [
     ("rows2_qkv", (4352, 1, 1, 640, 1920, 1, 1), 0, False, False),
     ("rows2_fc2_res_f32", (1000, 1, 1, 1280, 640, 1, 1), 0, True, True),

@@ -86,6 +86,27 @@ def test_program_matches_golden(case, precision):
         assert rel_l2(nchw[torch.from_numpy(g[f"feat{l}_idx"])], g[f"feat{l}_val"]) < (1e-5 if precision == "fp32" else 3e-3)
 
 
+@pytest.mark.parametrize("name", ["hrnet32_b2_128x96", "cpn_b2_256x256"])
+def test_split_operand_program_matches_golden(name):
+    """precision="bf16x3": fp32 storage, every conv / Linear as hi*Wh + lo*Wh + hi*Wl in bfloat16 -- the tensor-core mode held
+    to north_star's 1e-3; the program (split casts, packed [Wh|Wh][Wl] weights, memory plan) reproduces the reference."""
+    case = next(c for c in golden_cases() if c["name"] == name)
+    g = load_golden(name)
+    m, w, cfg = build_case_model(case["backbone"], case["weight_seed"])
+    B, H, W = case["B"], case["H"], case["W"]
+    images, kp2d, crop = protocol.make_inputs(B, H, W, case["input_seed"])
+    prog = program.build_forward_program(case["backbone"], getattr(m.backbone, "cfg", None), m._pf_cfg,
+                                         {k: tuple(v.shape) for k, v in w.items()}, B, H, W, "bf16x3", use_tc=True)
+    convs = [op for op in prog.ops if op.kind == lib.OP_CONV2D]
+    assert sum(op.i[12] == lib.IMPL_TCGEN05 and op.i[18] == 1 for op in convs) == len(convs) - 1      # all but the 3-channel stem
+    it = interp.Interp(prog, w)
+    it.t(prog.inputs["images"]).copy_(images)
+    it.t(prog.inputs["kp2d"]).copy_(kp2d.reshape(-1, 2))
+    it.t(prog.inputs["ref"]).copy_(torch.from_numpy(g["crop_after"]).reshape(-1, 2))
+    it.run()
+    assert rel_l2(it.t(prog.outputs["out"]).view(B, 1, 17, 3), g["out"]) < 1e-4
+
+
 def test_memory_plan_reuses_and_never_aliases_live_buffers():
     m, w, _ = build_case_model("hrnet_32", 0)
     prog = program.build_forward_program("hrnet_32", m.backbone.cfg, m._pf_cfg, {k: tuple(v.shape) for k, v in w.items()},

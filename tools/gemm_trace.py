@@ -16,6 +16,7 @@ use_res = bool(a[7]) if len(a) > 7 else False
 f32out = bool(a[8]) if len(a) > 8 else False
 msub = a[9] if len(a) > 9 else 0
 bn = a[10] if len(a) > 10 else 0
+variant = a[11] if len(a) > 11 else 1     # i[13]: 1 = per-tap tc_gemm_kernel, 0 = automatic (2-CTA kernel for the wide Linears)
 pad = k // 2
 Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
 dev = "cuda:0"
@@ -28,7 +29,7 @@ out = torch.empty(N, Ho, Wo, Co, device=dev, dtype=odt)
 trace = torch.zeros(256, dtype=torch.int64, device=dev)
 op = lib.CapfOp()
 op.kind, op.dtype_in, op.dtype_out = lib.OP_CONV2D, lib.F16, lib.F32 if f32out else lib.F16
-for n, v in enumerate([N, H, W, C, Co, k, k, stride, pad, Ho, Wo, lib.ACT_NONE, lib.IMPL_TCGEN05, 1, 0, msub, bn]):
+for n, v in enumerate([N, H, W, C, Co, k, k, stride, pad, Ho, Wo, lib.ACT_NONE, lib.IMPL_TCGEN05, variant, 0, msub, bn]):
     op.i[n] = v
 op.inp[0], op.inp[1], op.inp[2] = x.data_ptr(), w.data_ptr(), bias.data_ptr()
 op.inp[3] = res.data_ptr() if use_res else None
