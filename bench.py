@@ -55,7 +55,9 @@ CONFIGS = {
     4: dict(backbone="hrnet_48", batch=512, height=384, width=288, precision="bf16", gpus=8,
             text="HRNet-48, 17 joints, bs=4096, 384x288, bf16, 8xB200 with NCCL output all-gather"),
 }
-DT_NAME = {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}
+DT_NAME = {"fp16": "f16", "bf16": "bf16", "fp32": "f32", "bf16x3": "bf16x3"}
+DT_TEXT = {"fp16": "f16 storage, f32 accumulate", "bf16": "bf16 storage, f32 accumulate", "fp32": "f32 (CUDA-core kernels)",
+           "bf16x3": "f32 storage, tensor-core products on split bf16 operands (hi*Wh + lo*Wh + hi*Wl), f32 accumulate"}
 
 
 def resolve_config(args):
@@ -388,7 +390,7 @@ def roofline_of(wl, ms_total, steps, peaks, ops_csv=None):
     plan = wl.plan
     B = wl.a.batch
     with torch.no_grad():
-        op_ms = plan.time_ops(passes=2)
+        op_ms = plan.time_ops(passes=3)
     kern = [plan.op_kernel(k) for k in range(len(plan.prog.ops))]
     groups, fam = {}, {}
 
@@ -549,7 +551,7 @@ def run_native(args, label):
                             "sample": f"oracle/capf_oracle.py (CPU restatement of the reference forward, fp32): {args.backbone}, bs={n}, "
                                       f"{args.height}x{args.width} (BASELINE configs[0] shape for config 1); {len(times)} timed forwards after 1 warm-up, all host threads",
                             "best_fps": n / min(times)}
-                if args.precision != "fp32":
+                if args.precision not in ("fp32", "bf16x3"):
                     # the same frames through the fp32 parity mode of the library (CUDA-core kernels, the mode held to 1e-3)
                     with torch.no_grad():
                         m32, _, _ = build_model(args.backbone, "fp32", dev, graph=False)
@@ -565,7 +567,7 @@ def run_native(args, label):
         line = {
             "metric": metric_name(args), "value": frames / (ms_total / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": DT_NAME[args.precision] + " storage, f32 accumulate",
+            "dtype": DT_TEXT[args.precision],
             "data": "synthetic (seeded randn images, random-init weights of the named architecture)",
             "config": {"workload": label, "baseline_config_index": args.config,
                        "global_batch": B * world, "parallelism": f"frame-sharded x{world}, NCCL all-gather of outputs"
@@ -603,7 +605,7 @@ def run_native(args, label):
                     out2 = w2.step_resident().clone()
                 torch.cuda.synchronize(dev)
                 rec.update({"value": a2.batch * world * st / (ms2 / 1e3), "unit": "frames/s", "n_gpus": world, "steps": st, "warmup": 3,
-                            "ms_per_step": ms2 / st, "dtype": DT_NAME[a2.precision] + " storage, f32 accumulate",
+                            "ms_per_step": ms2 / st, "dtype": DT_TEXT[a2.precision],
                             "e2e": {"value": a2.batch * world * st / (ms2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2},
                             "whole_step_tflops": w2.plan.prog.flops() / (ms2 / st * 1e-3) / 1e12})
                 if rank == 0 and not args.no_cpu:
@@ -637,7 +639,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU")
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
-    ap.add_argument("--precision", default=None, choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--precision", default=None, choices=["fp16", "bf16", "fp32", "bf16x3"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity / yardstick legs")
     ap.add_argument("--no-yardstick", action="store_true", help="skip the PyTorch-eager-CUDA yardstick")

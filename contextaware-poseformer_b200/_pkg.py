@@ -1,11 +1,11 @@
 """Public surface of the package (imported by both ``contextaware-poseformer_b200`` and the ``capf_b200`` alias)."""
 import copy as _copy
 
-from . import lib, program, arch, synth, dist, frontend, mpi  # noqa: F401
+from . import lib, program, arch, synth, dist, frontend, mpi, train  # noqa: F401
 from .mvn.models.conpose import CA_PF
 from .mvn.utils import cfg as _cfg
 
-__all__ = ["CA_PF", "make_config", "lib", "program", "arch", "synth", "dist", "frontend", "mpi"]
+__all__ = ["CA_PF", "make_config", "lib", "program", "arch", "synth", "dist", "frontend", "mpi", "train"]
 
 
 def make_config(backbone: str = "hrnet_32", yaml_path: str = None):

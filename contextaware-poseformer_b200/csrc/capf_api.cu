@@ -100,6 +100,16 @@ static int dispatch(const capf_op& op, const TcConvState* tc, cudaStream_t st) {
     case CAPF_OP_PREPROCESS_U8: return launch_preprocess_u8(op, st);
     case CAPF_OP_WARP_AFFINE_U8: return launch_warp_affine_u8(op, st);
     case CAPF_OP_POSE_ERRORS: return launch_pose_errors(op, st);
+    case CAPF_OP_GEMM_F32: return launch_gemm_f32(op, st);
+    case CAPF_OP_COLSUM: return launch_colsum(op, st);
+    case CAPF_OP_LAYERNORM_BWD: return launch_layernorm_bwd(op, st);
+    case CAPF_OP_GELU:
+    case CAPF_OP_GELU_BWD: return launch_gelu(op, st);
+    case CAPF_OP_ATTENTION_BWD: return launch_attention_bwd(op, st);
+    case CAPF_OP_DEFORM_BWD: return launch_deform_bwd(op, st);
+    case CAPF_OP_ROWS_AXPY: return launch_rows_axpy(op, st);
+    case CAPF_OP_JOINT_TO_LEVELS: return launch_joint_to_levels(op, st);
+    case CAPF_OP_ADAMW: return launch_adamw(op, st);
     default: return set_errorf(CAPF_ERR_ARG, "unknown op kind %d", op.kind);
   }
 }
@@ -219,6 +229,16 @@ int capf_plan_op_kernel(const capf_plan* plan, int k, char* buf, int cap) {
     case CAPF_OP_PREPROCESS_U8: snprintf(buf, cap, "preprocess_u8_kernel"); break;
     case CAPF_OP_WARP_AFFINE_U8: snprintf(buf, cap, "warp_affine_u8_kernel"); break;
     case CAPF_OP_POSE_ERRORS: snprintf(buf, cap, "pose_errors_kernel"); break;
+    case CAPF_OP_GEMM_F32: snprintf(buf, cap, "gemm_f32_kernel"); break;
+    case CAPF_OP_COLSUM: snprintf(buf, cap, "colsum_kernel"); break;
+    case CAPF_OP_LAYERNORM_BWD: snprintf(buf, cap, "layernorm_bwd_kernel"); break;
+    case CAPF_OP_GELU: snprintf(buf, cap, "gelu_kernel"); break;
+    case CAPF_OP_GELU_BWD: snprintf(buf, cap, "gelu_bwd_kernel"); break;
+    case CAPF_OP_ATTENTION_BWD: snprintf(buf, cap, "attention_bwd_kernel"); break;
+    case CAPF_OP_DEFORM_BWD: snprintf(buf, cap, "deform_bwd_kernel"); break;
+    case CAPF_OP_ROWS_AXPY: snprintf(buf, cap, "rows_axpy_kernel"); break;
+    case CAPF_OP_JOINT_TO_LEVELS: snprintf(buf, cap, "joint_to_levels_kernel"); break;
+    case CAPF_OP_ADAMW: snprintf(buf, cap, "adamw_kernel"); break;
     default: snprintf(buf, cap, "?");
   }
   return CAPF_OK;

@@ -51,6 +51,17 @@ int launch_preprocess_u8(const capf_op& op, cudaStream_t st);
 int launch_warp_affine_u8(const capf_op& op, cudaStream_t st);
 int launch_pose_errors(const capf_op& op, cudaStream_t st);
 
+// training step (capf_train.cu)
+int launch_gemm_f32(const capf_op& op, cudaStream_t st);
+int launch_colsum(const capf_op& op, cudaStream_t st);
+int launch_layernorm_bwd(const capf_op& op, cudaStream_t st);
+int launch_gelu(const capf_op& op, cudaStream_t st);
+int launch_attention_bwd(const capf_op& op, cudaStream_t st);
+int launch_deform_bwd(const capf_op& op, cudaStream_t st);
+int launch_rows_axpy(const capf_op& op, cudaStream_t st);
+int launch_joint_to_levels(const capf_op& op, cudaStream_t st);
+int launch_adamw(const capf_op& op, cudaStream_t st);
+
 // tensor-pipe HRNet stem conv1 (capf_stem.cu): fp32 NHWC image -> 64 channels, 3x3 / stride 2
 int stem_tc_supported(const capf_op& op);
 int launch_stem_tc(const capf_op& op, cudaStream_t st);

@@ -3,8 +3,8 @@
 Same constructor (``CA_PF(config, device)``, conpose.py:11-27), attributes (``backbone``, ``volume_net``),
 ``state_dict`` layout and ``forward(images[B,H,W,3], keypoints_2d_cpn[B,17,2], keypoints_2d_cpn_crop[B,17,2])
 -> [B,1,17,3]`` including the in-place normalisation of the caller's crop tensor (conpose.py:34-35).
-Inference only: outputs are detached (non-differentiable); the reference's training step (volume_net backward,
-SURVEY.md section 8 f2) goes through ``capf_b200.train`` instead.
+In ``eval()`` / ``no_grad`` the output is detached.  With ``volume_net.train()`` under autograd the call is a training step
+(SURVEY.md section 8 f2): frozen backbone through its plan, lifter forward/backward through ``capf_b200.train``.
 """
 import torch
 from torch import nn
@@ -74,17 +74,14 @@ class CA_PF(PlanCacheMixin, nn.Module):
     def forward(self, images, keypoints_2d_cpn, keypoints_2d_cpn_crop):
         if not (images.is_cuda and keypoints_2d_cpn.is_cuda and keypoints_2d_cpn_crop.is_cuda):
             raise lib.CapfError("CA_PF runs on a B200 through libcapf_b200; got CPU tensors (there is no CPU path)")
-        if self.volume_net.training:
-            # the reference in train() mode applies DropPath and returns a differentiable tensor (train.py:186-201); this
-            # path has eval semantics only (folded BN running statistics, no DropPath) and its output carries no graph
-            if torch.is_grad_enabled() and any(p.requires_grad for p in self.volume_net.parameters()):
-                raise NotImplementedError("training (volume_net backward) is outside this inference path; "
-                                          "call under torch.no_grad() / model.eval()")
-            if not self._warned_train:
-                import warnings
-                warnings.warn("CA_PF.forward: volume_net is in train() mode, but this path always runs with eval semantics "
-                              "(no DropPath, BN running statistics); outputs are not differentiable", stacklevel=2)
-                self._warned_train = True
+        # train.py:145-148,186-201: volume_net.train() under autograd = a training step (DropPath live, differentiable output,
+        # backbone frozen).  volume_net.train() under no_grad has no meaning here: eval semantics, warn once.
+        train_step = self.volume_net.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.volume_net.parameters())
+        if self.volume_net.training and not train_step and not self._warned_train:
+            import warnings
+            warnings.warn("CA_PF.forward: volume_net is in train() mode but autograd is off; running with eval semantics "
+                          "(no DropPath, non-differentiable output)", stacklevel=2)
+            self._warned_train = True
         B, H, W, C = images.shape
         J = self.num_joints
         if C != 3 or tuple(keypoints_2d_cpn.shape) != (B, J, 2):
@@ -93,7 +90,7 @@ class CA_PF(PlanCacheMixin, nn.Module):
             # conpose.py:34-35 normalises [..., :2]; anything but a [B,17,2] tensor would be mis-strided by the float2 kernel
             raise ValueError(f"keypoints_2d_cpn_crop must be [B,{J},2], got {tuple(keypoints_2d_cpn_crop.shape)}")
         dev = images.device
-        plan = self.plan_for(B, H, W, dev)
+        plan = None if train_step else self.plan_for(B, H, W, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
 
         # conpose.py:34-35 mutates the caller's tensor in place; keep that contract.
@@ -106,6 +103,13 @@ class CA_PF(PlanCacheMixin, nn.Module):
             lib.check(lib.load().capf_crop_normalize(tmp.data_ptr(), B * self.num_joints, stream), "capf_crop_normalize")
             crop.copy_(tmp)
             ref_src = tmp
+        if train_step:
+            if self._variant != "h36m":
+                raise NotImplementedError("the training step is implemented for the Human3.6M model (ContextPose/train.py)")
+            if any(p.requires_grad for p in self.backbone.parameters()):
+                raise NotImplementedError("only volume_net trains (config.model.backbone.fix_weights, conpose.py:22-25)")
+            from ... import train
+            return train.forward_train(self, images, keypoints_2d_cpn, ref_src)
         p = plan.prog
         static_images = plan.tensor(p.inputs["images"])
         if images.data_ptr() != static_images.data_ptr():      # callers may fill static_inputs() directly

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 9
+#define CAPF_ABI_VERSION 10
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -62,7 +62,18 @@ typedef enum capf_op_kind {
   CAPF_OP_PREPROCESS_U8 = 13,
   CAPF_OP_BASICBLOCK = 14,
   CAPF_OP_WARP_AFFINE_U8 = 15,
-  CAPF_OP_POSE_ERRORS = 16
+  CAPF_OP_POSE_ERRORS = 16,
+  /* training step of the lifter (reference train.py:186-201, :337-345), fp32 */
+  CAPF_OP_GEMM_F32 = 17,
+  CAPF_OP_COLSUM = 18,
+  CAPF_OP_LAYERNORM_BWD = 19,
+  CAPF_OP_GELU = 20,
+  CAPF_OP_GELU_BWD = 21,
+  CAPF_OP_ATTENTION_BWD = 22,
+  CAPF_OP_DEFORM_BWD = 23,
+  CAPF_OP_ROWS_AXPY = 24,
+  CAPF_OP_JOINT_TO_LEVELS = 25,
+  CAPF_OP_ADAMW = 26
 } capf_op_kind;
 
 /*
@@ -177,6 +188,33 @@ typedef enum capf_op_kind {
  *                    sums rows per action.
  *     i[0]=N frames  i[1]=J joints
  *     in[0]=pred f32 [N,J,3]  in[1]=gt f32 [N,J,3]  in[2]=int32 [N] prev (or NULL: no velocity term)   out[0]=f64 [N,3]
+ *
+ * ---- training step of `volume_net` (the reference trains it through autograd, train.py:186-201; the backbone is frozen,
+ *      conpose.py:22-25).  All fp32, every reduction in a fixed order (bit-reproducible steps). ----
+ *
+ * CAPF_OP_GEMM_F32 -- C[M][N] = op(A) op(B) [+ bias[N]] [+ C]: forward nn.Linear (tb = 1), dgrad dy W (ta = tb = 0),
+ *                    wgrad dy^T x (ta = 1, split over the rows).
+ *     i[0..2]=M,N,K  i[3]=ta (A stored [K][M])  i[4]=tb (B stored [N][K])  i[5]=lda  i[6]=ldb  i[7]=ldc
+ *     i[8]=K splits (<= 1: none)  i[9]=accumulate into C
+ *     in[0]=A  in[1]=B  in[2]=bias or NULL   out[0]=C   out[1]=partials workspace [splits][M][N] (split-K only)
+ * CAPF_OP_COLSUM -- out[n] = [out[n] +] sum_m x[m * ld + n] (bias gradients, Spatial_pos_embed gradient, partials).
+ *     i[0]=M  i[1]=N  i[2]=ld  i[3]=accumulate   in[0]=x   out[0]=f32[N]   out[1]=workspace f32[256][N] or NULL
+ * CAPF_OP_LAYERNORM_BWD -- nn.LayerNorm backward: dx (optionally accumulated) and per-block partial sums of dy*xhat / dy.
+ *     i[0]=rows  i[1]=D (% 32, <= 640)  i[2]=period of the broadcast x0 rows (0: none)  i[3]=accumulate dx  i[4]=blocks
+ *     f[0]=eps   in[0]=x  in[1]=gamma  in[2]=dy  in[3]=x0 or NULL   out[0]=dx [rows][D]  out[1]=partials [blocks][2][D]
+ * CAPF_OP_GELU / CAPF_OP_GELU_BWD -- nn.GELU() (erf form) on a dense array / its backward.
+ *     i[0],i[1]=element count (lo, hi 31-bit words; % 4)   in[0]=h  (BWD: in[1]=dy)   out[0]=y (BWD: dh)
+ * CAPF_OP_ATTENTION_BWD -- backward of CAPF_OP_ATTENTION (same i[0..5], f[0]); probabilities are recomputed.
+ *     in[0]=qkv f32 [rows][3*heads*hd]  in[1]=d out [rows][heads*hd]   out[0]=d qkv
+ * CAPF_OP_DEFORM_BWD -- backward of CAPF_OP_DEFORM_SAMPLE (same i[0..18], in[0..5]) w.r.t. the attention logits and the
+ *                    sampling offsets (grid_sample w.r.t. its grid, tanh, softmax); the maps are constants.
+ *     out[0]=d ow f32 [levels*B*J][48]   out[1]=d sampled (INPUT, f32, the layout of DEFORM_SAMPLE's out[0])
+ * CAPF_OP_ROWS_AXPY -- y[r][:] = [y[r][:] +] scale[(r % i[2]) / i[3]] * t[r][:]: DropPath residual adds and their backward.
+ *     i[0]=rows  i[1]=D (% 4)  i[2]=mod  i[3]=div  i[4]=accumulate   in[0]=t  in[1]=scale or NULL (= 1)   out[0]=y
+ * CAPF_OP_JOINT_TO_LEVELS -- inverse of CAPF_OP_LEVELS_TO_JOINT.  i[0]=R  i[1]=slabs  i[2]=D   in[0]=dY [R][slabs*D]  out[0]=dX
+ * CAPF_OP_ADAMW -- torch.optim.AdamW update (decoupled weight decay) over one flat parameter buffer.
+ *     i[0],i[1]=element count   in[0]=f32[7] device {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t)}
+ *     in[1]=grad  in[2]=exp_avg_sq (updated)   out[0]=param (updated)  out[1]=exp_avg (updated)
  */
 typedef struct capf_op {
   int32_t kind;

@@ -222,13 +222,21 @@ def _attention(sd, x, p, heads):
     return _lin(sd, (a @ v).transpose(1, 2).reshape(B, N, C), p + ".proj")
 
 
-def _block(sd, x, p, heads=8):
+def _drop(branch, scale):
+    """timm DropPath (pose_dformer.py:71,101) with a given per-sample scale = bernoulli(keep) / keep over the leading dimension of
+    `branch`; None = identity (eval mode, or a block whose rate is 0)."""
+    if scale is None:
+        return branch
+    return branch * scale.view((-1,) + (1,) * (branch.ndim - 1))
+
+
+def _block(sd, x, p, heads=8, drop=(None, None)):
     """Block.forward, pose_dformer.py:76-79 with LayerNorm eps 1e-6 (:166); DropPath is identity in eval."""
-    x = x + _attention(sd, _ln(sd, x, p + ".norm1", 1e-6), p + ".attn", heads)
-    return x + _mlp(sd, _ln(sd, x, p + ".norm2", 1e-6), p + ".mlp")
+    x = x + _drop(_attention(sd, _ln(sd, x, p + ".norm1", 1e-6), p + ".attn", heads), drop[0])
+    return x + _drop(_mlp(sd, _ln(sd, x, p + ".norm2", 1e-6), p + ".mlp"), drop[1])
 
 
-def _context_block(sd, x, ref, feats, p, heads=4, samples=4):
+def _context_block(sd, x, ref, feats, p, heads=4, samples=4, drop=(None, None)):
     """DeformableBlock.forward, pose_dformer.py:115-141 (LayerNorm eps 1e-5: default nn.LayerNorm, :89,:95)."""
     x0, xl = x[:, :1], x[:, 1:]
     b, l, pj, c = xl.shape
@@ -242,17 +250,19 @@ def _context_block(sd, x, ref, feats, p, heads=4, samples=4):
         sampled.append(_lin(sd, s, f"{p}.embed_proj.{idx}"))
     s = torch.stack(sampled, 1)
     s = (w * s.view(b, l, pj, heads, samples, -1)).sum(-2).view(b, l, pj, -1)
-    xl = xl + s
-    xl = xl + _mlp(sd, _ln(sd, xl, p + ".norm2", 1e-5), p + ".mlp")
+    xl = xl + _drop(s, drop[0])
+    xl = xl + _drop(_mlp(sd, _ln(sd, xl, p + ".norm2", 1e-5), p + ".mlp"), drop[1])
     return torch.cat([x0, xl], 1), pos
 
 
-def lifter_forward(sd, kp2d, ref, feats, levels=4, prefix="volume_net.", trace=None, context=True, depth=None):
+def lifter_forward(sd, kp2d, ref, feats, levels=4, prefix="volume_net.", trace=None, context=True, depth=None, drop=None):
     """PoseTransformer.forward, pose_dformer.py:210-241.  kp2d, ref: [B,17,2]; feats: 4 NCHW maps -> [B,1,17,3].
 
     context=False, depth=config.depth restates the MPI-INF-3DHP variant (ContextPose_mpi/model/pose_dformer.py:236-262):
-    no DeformableBlocks, `depth` res / joint blocks; the caller applies that variant's output layout (mpi_output)."""
+    no DeformableBlocks, `depth` res / joint blocks; the caller applies that variant's output layout (mpi_output).
+    drop: train-mode DropPath scales {"context_blocks" | "res_blocks" | "joint_blocks": [(s_branch1, s_branch2)] * depth}."""
     depth = levels if depth is None else depth
+    dp = lambda grp, i: (drop[grp][i] if drop is not None else (None, None))
     S = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     b, p, _ = kp2d.shape
     x = _lin(S, kp2d, "coord_embed")
@@ -262,19 +272,19 @@ def lifter_forward(sd, kp2d, ref, feats, levels=4, prefix="volume_net.", trace=N
     if trace is not None:
         trace["tokens_embed"] = x.clone()
     for i in range(levels if context else 0):
-        x, pos = _context_block(S, x, ref, feats, f"context_blocks.{i}")
+        x, pos = _context_block(S, x, ref, feats, f"context_blocks.{i}", drop=dp("context_blocks", i))
         if trace is not None and i == 0:
             trace["deform_pos0"] = pos.clone()
     if trace is not None:
         trace["tokens_context"] = x.clone()
     x = x.permute(0, 2, 1, 3).reshape(b * p, levels + 1, -1)          # 'b l p c -> (b p) l c'
     for i in range(depth):
-        x = _block(S, x, f"res_blocks.{i}")
+        x = _block(S, x, f"res_blocks.{i}", drop=dp("res_blocks", i))
     if trace is not None:
         trace["tokens_res"] = x.clone()
     x = x.reshape(b, p, -1)                                           # '(b p) l c -> b p (l c)'
     for i in range(depth):
-        x = _block(S, x, f"joint_blocks.{i}")
+        x = _block(S, x, f"joint_blocks.{i}", drop=dp("joint_blocks", i))
     if trace is not None:
         trace["tokens_joint"] = x.clone()
     x = _lin(S, _ln(S, x, "head.0", 1e-5), "head.1")
@@ -501,8 +511,9 @@ def evaluate_using_pred(keypoints_gt, keypoints_3d_predicted, labels_action_idx,
 # is a separate, seeded concern.  Pinned by tests/golden/grad_hrnet32_b2_128x96.npz (oracle/gen_golden_grad.py ran
 # autograd and torch.optim.AdamW on the unmodified reference model).
 # ------------------------------------------------------------------------------------------------------
-def volume_net_loss_and_grads(sd, backbone, bb_cfg, images, kp2d, crop, gt):
-    """MPJPE loss (loss.py:16-22) of the forward and d loss / d volume_net parameters.  Returns (loss, {name: grad})."""
+def volume_net_loss_and_grads(sd, backbone, bb_cfg, images, kp2d, crop, gt, drop=None):
+    """MPJPE loss (loss.py:16-22) of the forward and d loss / d volume_net parameters.  Returns (loss, {name: grad}).
+    drop: DropPath scales of a train-mode step (see lifter_forward); None = eval-mode blocks."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if k.startswith("volume_net.") and v.is_floating_point()}
     sd2 = dict(sd)
     sd2.update(leaves)
@@ -511,7 +522,7 @@ def volume_net_loss_and_grads(sd, backbone, bb_cfg, images, kp2d, crop, gt):
         ref = normalize_crop_(crop.clone())
         feats = cpn_forward(sd, x) if backbone == "cpn" else hrnet_forward(sd, x, bb_cfg)
     with torch.enable_grad():
-        pred = lifter_forward(sd2, kp2d, ref, feats)
+        pred = lifter_forward(sd2, kp2d, ref, feats, drop=drop)
         loss = torch.mean(torch.norm(pred - gt, dim=len(gt.shape) - 1))
     grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
     return float(loss.detach()), {k: (g if g is not None else torch.zeros_like(v)) for (k, v), g in zip(leaves.items(), grads)}

@@ -3,7 +3,9 @@ parameters after one optimiser step, from the UNMODIFIED reference model under a
 train.py:186-201 / :337-345 drive it (MPJPE criterion, lr = volume_net_lr of human36m.yaml, weight_decay 0.1, no clipping).
 Blocks run in eval mode (DropPath = identity, BatchNorm running stats; the backbone is frozen by CA_PF itself).
 Per parameter the fixture keeps the gradient norm, its sum and 64 sampled elements (positions derived from the name).
-Run in the authoring container:  python oracle/gen_golden_grad.py"""
+`--train` writes grad_train_hrnet32_b2_128x96.npz instead: the same step with the model in the state train.py:145-148 puts it in
+(volume_net.train(): DropPath with rates linspace(0, 0.2, 4) is live; masks fixed by torch.manual_seed(TRAIN_SEED)).
+Run in the authoring container:  python oracle/gen_golden_grad.py [--train]"""
 import os
 import sys
 import zlib
@@ -32,13 +34,21 @@ def make_target(B, seed):
     return gt
 
 
-def main():
+TRAIN_SEED = 4321     # torch.manual_seed right before the train-mode forward: fixes the DropPath masks
+
+
+def main(train_mode=False):
     backbone, B, H, W, wseed, iseed = CASE
     torch.manual_seed(0)
     model = ref_import.build_reference_model(backbone)
     spec = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
     model.load_state_dict(protocol.make_weights(spec, wseed), strict=True)
     model.eval()
+    if train_mode:          # train.py:145-148: model.train(); backbone.eval(); volume_net.train()  -> DropPath is live
+        model.train()
+        model.backbone.eval()
+        model.volume_net.train()
+        torch.manual_seed(TRAIN_SEED)
     images, kp2d, crop = protocol.make_inputs(B, H, W, iseed)
     gt = make_target(B, 99)
     from mvn.models.loss import MPJPE
@@ -58,9 +68,10 @@ def main():
         out[f"g{k}_norm"], out[f"g{k}_sum"] = np.array(float(g.norm())), np.array(float(g.sum()))
         out[f"g{k}_samples"] = g[pos].numpy()
         out[f"p{k}_after"] = p.detach().reshape(-1)[pos].double().numpy()
-    np.savez_compressed(os.path.join(HERE, "..", "tests", "golden", "grad_hrnet32_b2_128x96.npz"), **out)
+    name = "grad_train_hrnet32_b2_128x96.npz" if train_mode else "grad_hrnet32_b2_128x96.npz"
+    np.savez_compressed(os.path.join(HERE, "..", "tests", "golden", name), **out)
     print("loss", float(loss), "params", len(params), "total grad norm", float(torch.sqrt(sum(g.double().norm() ** 2 for g in grads.values()))))
 
 
 if __name__ == "__main__":
-    main()
+    main(train_mode="--train" in sys.argv)
