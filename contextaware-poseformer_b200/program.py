@@ -348,6 +348,7 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
     prog.feature_maps = [m.ref for m in maps]
     if pb.use_tc:
         fuse_basic_blocks(prog)
+        chunk_prefix(prog)
     prog.n_backbone_ops = len(prog.ops)
     if backbone_only:
         for k, m in enumerate(maps):
@@ -521,6 +522,74 @@ def fuse_basic_blocks(prog: Program):
 
 
 # ------------------------------------------------------------------------------------------------------
+# batch-chunked schedule of the high-resolution prefix
+# ------------------------------------------------------------------------------------------------------
+_PREFIX_RE = re.compile(r"^backbone\.(conv1|conv2|layer1\.|transition1\.|resnet\.conv1|resnet\.layer1\.)")
+
+
+def chunk_prefix(prog: Program, chunk: int = None):
+    """The stem, layer1 and transition1 of HRNet (pose_hrnet.py:464-472; ResNet-50's stem and layer1 for CPN) work on the
+    largest tensors of the network -- [B, H/4, W/4, 256] is 537 MB at bs = 256 -- and are bound by HBM: every op streams its
+    whole input from and its whole output to DRAM.  Frames are independent, so the same ops are issued per CHUNK of frames
+    (all prefix ops for frames [0, c), then [c, 2c), ...): a chunk's tensors (c * 2 MB) are still in the 126 MB L2 when the
+    next op reads them.  Pure scheduling: every op becomes ceil(B / c) ops on sub-views of the same buffers; results are
+    bit-identical.
+
+    MEASURED on B200 (bs = 256, HRNet-32, profiles/r2_chunk_sweep.txt): it does NOT pay -- 11.72 ms/step unchunked vs 12.85 /
+    12.19 / 11.99 / 11.84 ms at 16 / 27 / 37 / 64 frames per chunk: the ~5 us of ramp + tail every extra launch costs
+    outweighs the DRAM traffic saved.  The pass is therefore OFF by default; CAPF_CHUNK=<frames> turns it on for experiments."""
+    env = os.environ.get("CAPF_CHUNK")
+    if env is None and chunk is None:
+        return 0
+    if env is not None:
+        chunk = int(env) if int(env) > 0 else None
+        if int(env) == 0:
+            return 0
+    def in_prefix(op):
+        if op.kind == lib.OP_MAXPOOL:
+            return True
+        return op.kind in (lib.OP_CONV2D, lib.OP_CAST) and bool(_PREFIX_RE.match(op.tag or ""))
+
+    n = 0
+    while n < len(prog.ops) and in_prefix(prog.ops[n]):
+        n += 1
+    if n == 0:
+        return 0
+    B = prog.B
+    if chunk is None:
+        # frames whose widest prefix tensor (H/4 x W/4 x 256 x 2 B) keeps ~1/2 of the L2 free for the op's other operand
+        per_frame = max(int(np.prod(b.shape[1:])) * _ITEMSIZE[b.dtype] for op in prog.ops[:n] for b in op.outs if isinstance(b, Buf))
+        chunk = max(1, int(56e6 // per_frame))
+    if chunk <= 0 or chunk >= B:
+        return 0
+    head = prog.ops[:n]
+    out = []
+    for c0 in range(0, B, chunk):
+        c = min(chunk, B - c0)
+        for op in head:
+            def sub(b):
+                if not isinstance(b, Buf):
+                    return b
+                per = int(np.prod(b.shape[1:]))
+                assert b.shape[0] == B, (op.tag, b.shape)
+                return b.view(c0 * per, (c,) + tuple(b.shape[1:]), f"{b.name}[{c0}:{c0 + c}]")
+            ins = [sub(b) for b in op.ins]
+            outs = [sub(b) for b in op.outs]
+            i = list(op.i)
+            if op.kind == lib.OP_CAST:
+                cnt = ins[0].numel
+                i[0], i[1] = cnt & 0x7fffffff, cnt >> 31
+            else:
+                i[0] = c
+            o = Op(op.kind, op.dtype_in, op.dtype_out, i, list(op.f), ins, outs, tag=op.tag, flops=op.flops * c // B,
+                   nbytes=op.nbytes * c // B)
+            o.pin_lane0 = True
+            out.append(o)
+    prog.ops[:n] = out
+    return len(out)
+
+
+# ------------------------------------------------------------------------------------------------------
 # execution lanes: the branches of a HighResolutionModule are independent chains (pose_hrnet.py:289-290)
 # ------------------------------------------------------------------------------------------------------
 MAX_LANES = 4
@@ -540,7 +609,9 @@ def assign_lanes(prog: Program, enable: bool = True):
     producer_lane = {}
     for op in prog.ops:
         lane = 0
-        if op.kind == lib.OP_CONV2D:
+        if getattr(op, "pin_lane0", False):
+            pass
+        elif op.kind == lib.OP_CONV2D:
             m = _LANE_RE.search(op.tag)
             if m:
                 lane = int(next(g for g in m.groups() if g is not None))

@@ -33,7 +33,21 @@ HEADS_CTX, SAMPLES = 4, 4
 _DT = {torch.float32: lib.F32, torch.float16: lib.F16, torch.bfloat16: lib.BF16}
 
 
+PROFILE = None      # set to a list to collect (kind, shape ints, start event, end event) per launch (tools/train_bench.py --profile)
+
+
 def _run(kind, dt_in, dt_out, ints, floats, ins, outs, dev):
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _run_op(kind, dt_in, dt_out, ints, floats, ins, outs, dev)
+        e1.record()
+        PROFILE.append((kind, tuple(int(v) for v in ints[:5]), e0, e1))
+        return
+    _run_op(kind, dt_in, dt_out, ints, floats, ins, outs, dev)
+
+
+def _run_op(kind, dt_in, dt_out, ints, floats, ins, outs, dev):
     op = lib.CapfOp()
     op.kind, op.dtype_in, op.dtype_out = kind, dt_in, dt_out
     for n, v in enumerate(ints):
