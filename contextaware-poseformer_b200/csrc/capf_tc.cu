@@ -422,6 +422,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // =======================================================================================================
 struct TcConvState {
   TcHaloState* halo = nullptr;   // non-null: the op runs on the halo-band kernel instead of tc_gemm_kernel
+  TcHalo128State* h128 = nullptr; // non-null: halo band + streamed weights (C = Cout = 128)
   Tc2State* two = nullptr;       // non-null: the op runs on the 2-CTA GEMM kernel (capf_tc2.cu)
   TcBlockState* blk = nullptr;   // non-null: a fused BasicBlock op (capf_tc_block.cu)
   CUtensorMap mapA, mapB;
@@ -530,6 +531,12 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
     return CAPF_OK;
   }
   // i[13]: kernel variant hint (0 = automatic, 1 = per-tap TMA GEMM, 2 = halo band); tests use it for A/B parity
+  if (!split && op.i[13] != 1 && tc_halo128_supported(op)) {
+    e = tc_halo128_prepare(op, &s->h128);
+    if (e) { delete s; return e; }
+    *out = s;
+    return CAPF_OK;
+  }
   if (!split && op.i[13] != 1 && tc_halo_supported(op)) {
     e = tc_halo_prepare(op, &s->halo);
     if (e) { delete s; return e; }
@@ -712,6 +719,7 @@ int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
   if (s->blk) return tc_block_launch(s->blk, st);
   if (s->two) return tc2_launch(s->two, st);
   if (s->halo) return tc_halo_launch(s->halo, st);
+  if (s->h128) return tc_halo128_launch(s->h128, st);
   switch (s->dtype_out) {
     case CAPF_F32: return tc_launch_typed<float>(s, st);
     case CAPF_F16: return tc_launch_typed<__half>(s, st);
@@ -725,6 +733,7 @@ void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
   if (s->blk) { tc_block_describe(s->blk, buf, cap); return; }
   if (s->two) { tc2_describe(s->two, buf, cap); return; }
   if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
+  if (s->h128) { tc_halo128_describe(s->h128, buf, cap); return; }
   snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages%s]", 128 * s->p.msub, s->p.BN, s->p.num_stages, s->p.cpt1 ? ", bf16x3 split operands" : "");
 }
 
@@ -732,6 +741,7 @@ void tc_conv_release(TcConvState* s) {
   if (s && s->blk) tc_block_release(s->blk);
   if (s && s->two) tc2_release(s->two);
   if (s && s->halo) tc_halo_release(s->halo);
+  if (s && s->h128) tc_halo128_release(s->h128);
   delete s;
 }
 

@@ -293,6 +293,14 @@ int tc_halo_launch(const TcHaloState* s, cudaStream_t st);
 void tc_halo_release(TcHaloState* s);
 void tc_halo_describe(const TcHaloState* s, char* buf, int cap);
 
+// halo band + streamed weights for C = Cout = 128 (capf_tc_halo128.cu)
+struct TcHalo128State;
+int tc_halo128_supported(const capf_op& op);
+int tc_halo128_prepare(const capf_op& op, TcHalo128State** out);
+int tc_halo128_launch(const TcHalo128State* s, cudaStream_t st);
+void tc_halo128_release(TcHalo128State* s);
+void tc_halo128_describe(const TcHalo128State* s, char* buf, int cap);
+
 // bias + GELU + residual + ReLU on 16 accumulator columns of a 16-bit output row staged in shared memory: the residual (if
 // any) is read from, and the result written back to, the two 16-byte chunks at smem addresses s0 / s1 (runtime-flag
 // variant used by the stem kernel; the GEMM / halo kernels use the compile-time epi16 below).

@@ -53,6 +53,18 @@ HALO_CASES = [
 ]
 
 
+# 3x3 / stride 1 / pad 1, C = Cout = 128: halo band + streamed weights (csrc/capf_tc_halo128.cu) -- taken by default (variant 0)
+HALO128_CASES = [
+    ("h128_16x16", (4, 16, 16, 128, 128, 3, 1), lib.ACT_RELU, True, False),
+    ("h128_16x12_nores", (3, 16, 12, 128, 128, 3, 1), lib.ACT_NONE, False, False),
+    ("h128_tiny_8x6", (2, 8, 6, 128, 128, 3, 1), lib.ACT_RELU, True, False),
+    ("h128_multiband_32x32", (2, 32, 32, 128, 128, 3, 1), lib.ACT_RELU, True, False),
+    ("h128_many_bands", (330, 16, 16, 128, 128, 3, 1), lib.ACT_RELU, True, False),
+    ("h128_wide_5x40", (1, 5, 40, 128, 128, 3, 1), lib.ACT_NONE, True, False),
+    ("h128_ragged_bands_37x9", (2, 37, 9, 128, 128, 3, 1), lib.ACT_RELU, False, False),
+]
+
+
 def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=0, two=0, inplace=False):
     """Returns (rel_l2, max_abs, frac_bad_rows) of the tcgen05 kernel against the fp32 reference.
     inplace: the output buffer IS the residual buffer (how plan_memory runs a residual whose last reader is this op)."""

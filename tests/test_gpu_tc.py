@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from tc_cases import HALO_CASES, TC_CASES, run_tc_case
+from tc_cases import HALO128_CASES, HALO_CASES, TC_CASES, run_tc_case
 
 pytestmark = pytest.mark.gpu
 
@@ -27,6 +27,38 @@ def test_tc_gemm_tile_heights(case, msub):
     print(f"{case[0]} msub={msub}: rel-L2 {rel:.3e} max-abs {max_abs:.3e} bad-rows {bad_rows:.4f}")
     tol = 2e-5 if case[4] else 1.5e-3
     assert bad_rows == 0.0 and rel < tol
+
+
+@pytest.mark.parametrize("case", HALO128_CASES, ids=[c[0] for c in HALO128_CASES])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_halo128_conv_matches_fp32_reference(case, dt):
+    """C = Cout = 128 3x3 convolutions (HRNet branch 2; pose_hrnet.py:79-95): halo band in shared memory + weights streamed
+    through a ring, every band shape (one / several sub-tiles, several bands per image, more bands than SMs, ragged last band),
+    against plain fp32 PyTorch and against the per-tap kernel (same accumulation order -> at most one output rounding step)."""
+    import ctypes
+    from capf_b200 import lib
+    rel, max_abs, bad_rows = run_tc_case(case, dt)
+    print(f"{case[0]} {dt}: rel-L2 {rel:.3e} max-abs {max_abs:.3e} bad-rows {bad_rows:.4f}")
+    assert bad_rows == 0.0 and rel < (1.5e-3 if dt == torch.float16 else 8e-3)
+    rel1, _, _ = run_tc_case(case, dt, variant=1)
+    assert abs(rel - rel1) < 0.05 * rel1 + 1e-6
+    # the default dispatch really is the new kernel
+    name, (N, H, W, Cin, Cout, k, stride), act, use_res, _ = case
+    op = lib.CapfOp()
+    op.kind, op.dtype_in, op.dtype_out = lib.OP_CONV2D, lib.F16, lib.F16
+    x = torch.zeros(N, H, W, Cin, dtype=torch.float16, device="cuda")
+    w = torch.zeros(Cout, 9 * Cin, dtype=torch.float16, device="cuda")
+    y = torch.zeros(N, H, W, Cout, dtype=torch.float16, device="cuda")
+    for n, v in enumerate([N, H, W, Cin, Cout, 3, 3, 1, 1, H, W, act, lib.IMPL_TCGEN05]):
+        op.i[n] = v
+    op.inp[0], op.inp[1], op.out[0] = x.data_ptr(), w.data_ptr(), y.data_ptr()
+    h = ctypes.c_void_p()
+    arr = (lib.CapfOp * 1)(op)
+    lib.check(lib.load().capf_plan_create(arr, 1, 0, ctypes.byref(h)), "plan")
+    buf = ctypes.create_string_buffer(160)
+    lib.load().capf_plan_op_kernel(h, 0, buf, 160)
+    lib.load().capf_plan_destroy(h)
+    assert buf.value.decode().startswith("tc_conv3_halo128_kernel"), buf.value
 
 
 SPLIT_CASES = [c for c in TC_CASES if c[1][3] % 16 == 0]
