@@ -42,6 +42,14 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+_T0 = time.time()
+
+
+def log(msg):
+    """Phase timestamps on stderr (rank-tagged): what a slow run spent its time on."""
+    print(f"[bench +{time.time() - _T0:6.1f}s rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 # BASELINE.json configs[k] -> per-GPU workload (configs[3], [4] are 8-GPU totals: 2048/8 and 4096/8 frames per GPU)
@@ -501,6 +509,8 @@ def run_native(args, label):
         raise SystemExit("bench.py needs a B200: libcapf_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:       # torchrun pins OMP_NUM_THREADS=1: weight folding / the parity oracle would crawl on one host thread
+        torch.set_num_threads(max(1, (os.cpu_count() or world) // world))
     saved_stdout = None
     if world > 1:
         # rank 0 prints ONE JSON line on stdout: NCCL writes its version banner to fd 1 at its first collective, so fd 1
@@ -525,10 +535,14 @@ def run_native(args, label):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.tolist()
 
+    log("process group up, building the workload")
     wl = Workload(args, dev, rank, world, graph=not args.no_graph)
     B = args.batch
+    log("plan built")
     ms_total, out, win1 = timed_resident(wl, args.steps, args.warmup, barrier)
+    log(f"device-resident loop done: {ms_total / args.steps:.3f} ms/step")
     ms_e2e, h2d, d2h, win2 = timed_e2e(wl, args.steps, barrier)
+    log(f"end-to-end loop done: {ms_e2e / args.steps:.3f} ms/step")
     clocks = sampler.stop([win1, win2]) if rank == 0 else None
     ms_total, ms_e2e = reduce_max(ms_total, ms_e2e)
     frames = B * world * args.steps
@@ -540,10 +554,12 @@ def run_native(args, label):
     if rank == 0:
         peaks = load_peaks()
         roofline = roofline_of(wl, ms_total, args.steps, peaks, args.ops_csv)
+        log("per-op timing done")
         cpu_base = parity = yard = None
         n = args.cpu_sample
         if not args.no_cpu:
             parity, want = parity_of(wl, out, n)
+            log("parity vs the CPU oracle done")
             if world == 1:
                 times, threads = time_cpu_reference(args.backbone, args.height, args.width, n, args.cpu_steps, 1)
                 fps_cpu = n * len(times) / sum(times)
@@ -559,6 +575,7 @@ def run_native(args, label):
                     parity["fp32_mode_rel_l2"] = rel_l2(got32, want)
                     parity["fp32_mode_mpjpe_vs_ref_mm"] = float((got32 - want).norm(dim=-1).mean()) * 1000.0
                     del m32
+                log("cpu baseline done")
                 if not args.no_yardstick:
                     yard = gpu_yardstick(args.backbone, wl.cfg.model.backbone, wl.weights, wl.images, wl.kp2d, wl.crop,
                                          args.precision, dev, n, want)
@@ -595,6 +612,7 @@ def run_native(args, label):
                 setattr(a2, key, CONFIGS[k][key])
             a2.config = k
             rec = {"baseline_config_index": k, "workload": workload_label(a2, k), "metric": metric_name(a2)}
+            log(f"other config {k}")
             try:
                 w2 = Workload(a2, dev, rank, world, graph=not args.no_graph)
                 st = max(5, args.steps // 2)
@@ -615,6 +633,7 @@ def run_native(args, label):
                 rec["error"] = f"{type(e).__name__}: {e}"[:300]
             torch.cuda.empty_cache()
             others.append(rec)
+    log("done")
     if rank == 0:
         line["other_configs"] = others
         if saved_stdout is not None:

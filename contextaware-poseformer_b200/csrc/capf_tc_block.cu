@@ -38,6 +38,7 @@ constexpr int BLK_W_BYTES = 9 * BLK_C * BLK_C * 2;   // folded weights of one co
 constexpr int BLK_GROUPS = 4;
 constexpr int BLK_EPI_WARPS = 4 * BLK_GROUPS;
 constexpr int BLK_MAX_ACC = 16;             // 16 x 32 TMEM columns
+constexpr int BLK_ISSUERS = 3;              // MMA issuer warps 1, 2, 3 (sub-tile j is issued by warp 1 + j % 3)
 // header layout (bytes from the 1024-aligned base)
 constexpr int BH_W = 0, BH_XFULL = 8, BH_XEMPTY = 24, BH_MIDFREE = 40, BH_TFULL = 64, BH_TEMPTY = 192, BH_MIDRDY = 320, BH_TMEM = 448;
 constexpr int BH_BIAS = 512;                // bias1[32] f32, bias2[32] f32
@@ -86,9 +87,9 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     ptx::mbar_init(bar_w, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_xfull + 8 * b, 1);
-      ptx::mbar_init(bar_xempty + 8 * b, 2 + 8);               // both issuers (phase-A reads) + the 8 epilogue-2 warps (residual reads)
+      ptx::mbar_init(bar_xempty + 8 * b, BLK_ISSUERS + 8);     // the issuers (phase-A reads) + the 8 epilogue-2 warps (residual reads)
     }
-    ptx::mbar_init(bar_midfree, 2);                             // both issuers: phase-B reads of MID complete
+    ptx::mbar_init(bar_midfree, BLK_ISSUERS);                   // every issuer: phase-B reads of MID complete
     for (int a = 0; a < BLK_MAX_ACC; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);
       ptx::mbar_init(bar_tempty + 8 * a, a < p.n1max ? 256 : 128);    // phase-A slots: both E1 groups; phase-B slots: one E2 group
@@ -138,9 +139,13 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         if (++bin == p.bands_per_img) { bin = 0; ++img; }
       }
     }
-  } else if (warp == 1 || warp == 3) {
+  } else if (warp >= 1 && warp <= 3) {
     // ===================================== MMA issuers =======================================
-    const int me = warp == 1 ? 0 : 1;
+    // Three issuing warps (warp 2 joins after allocating TMEM).  Measured: 88.6 us per block with three against 88.7 us with
+    // two -- issue rate is NOT what paces this kernel; a band's 234 MMAs take ~11 k clk = 47 clk each against the 40 clk the
+    // shared-memory port needs to read the 5 KB of operands of a 128 x 32 x 16 MMA (tools/block_trace.py): the kernel sits at
+    // ~85 % of its structural bound, the rest is the wait for MID rows.
+    const int me = warp - 1;
     ptx::mbar_wait(bar_w, 0);
     ptx::tc_fence_after();
     uint32_t tap_off[9];
@@ -153,7 +158,7 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const uint32_t buf = k & 1u, ph = (k >> 1) & 1u;
       const int bh_eff = min(p.bh, p.H - bin * p.bh);
       const int n1 = ((bh_eff + 2) * p.Wp + 127) >> 7, n2 = (bh_eff * p.Wp + 127) >> 7;
-      const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && k < 32;
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && k < 32 && me < 2;
       long long tw = 0, w_x = 0, w_ta = 0, w_mid = 0, w_tb = 0;
       if (tr) tw = clock64();
       ptx::mbar_wait(bar_xfull + 8 * buf, ph);
@@ -161,7 +166,7 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       ptx::tc_fence_after();
       const uint32_t x_lo = tc_desc_lo(smem_x + buf * (uint32_t)p.x_bytes, 1u);
       // ---- phase A: conv1 over bh_eff + 2 rows --------------------------------------------------------
-      for (int j = me; j < n1; j += 2) {
+      for (int j = me; j < n1; j += BLK_ISSUERS) {
         if (tr) tw = clock64();
         ptx::mbar_wait(bar_tempty + 8 * j, ((pm >> j) & 1u) ^ 1u);
         if (tr) w_ta += clock64() - tw;
@@ -182,7 +187,7 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       __syncwarp();
       // ---- phase B: conv2 over bh_eff rows, sub-tile j as soon as the MID pixels it reads exist --------
       int ready_upto = -1;
-      for (int j = me; j < n2; j += 2) {
+      for (int j = me; j < n2; j += BLK_ISSUERS) {
         const int need = min(n1 - 1, (j * 128 + 128 + 2 * p.Wp) >> 7);
         if (tr) tw = clock64();
         while (ready_upto < need) {
