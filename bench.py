@@ -484,6 +484,76 @@ def roofline_of(wl, ms_total, steps, peaks, ops_csv=None):
     }
 
 
+def training_step_record(args, dev, steps=8):
+    """one optimisation step of volume_net (train.py:186-201) on the configs[1] workload -- frozen backbone
+    in the bench precision, lifter forward + backward in fp32 through capf_b200.train, fused AdamW -- next to the same step in
+    PyTorch-eager CUDA (autograd over the oracle's lifter, autocast backbone, torch.optim.AdamW)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import capf_b200
+    import capf_oracle
+    from capf_b200 import train
+    B, H, W = args.batch, args.height, args.width
+    model, sd, cfg = build_model(args.backbone, args.precision, dev, graph=False)
+    model.train(); model.backbone.eval(); model.volume_net.train()
+    images, kp2d, crop = [t.to(dev) for t in capf_b200.synth.make_inputs(B, H, W, 1234)]
+    gt = (torch.randn(B, 1, 17, 3, generator=torch.Generator().manual_seed(9)) * 0.3).to(dev)
+    opt = train.FusedAdamW(model.volume_net.parameters(), lr=6.4e-4, weight_decay=0.1)
+
+    def step():
+        pred = model(images, kp2d, crop.clone())
+        loss = torch.mean(torch.norm(pred - gt, dim=3))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    def timed(fn, n, warm=4):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    ms = timed(step, steps)
+    rec = {"what": f"volume_net training step on the configs[1] workload: {args.backbone} frozen in {args.precision}, bs={B}, {H}x{W}; lifter forward + "
+                   "backward (fp32, csrc/capf_train.cu) + fused AdamW; DropPath live", "value": B / ms * 1e3, "unit": "frames/s", "ms_per_step": ms, "steps": steps}
+    del model, opt
+    torch.cuda.empty_cache()
+    if not args.no_yardstick:
+        sdd = {k: v.to(dev) for k, v in sd.items()}
+        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sdd.items() if k.startswith("volume_net.") and v.is_floating_point()}
+        sd2 = dict(sdd)
+        sd2.update(leaves)
+        topt = torch.optim.AdamW([{"params": list(leaves.values()), "lr": 6.4e-4}], weight_decay=0.1)
+        adt = {"fp16": torch.float16, "bf16": torch.bfloat16}.get(args.precision, torch.float16)
+        bench_flag = torch.backends.cudnn.benchmark
+        torch.backends.cudnn.benchmark = True
+
+        def ystep():
+            with torch.no_grad(), torch.autocast("cuda", dtype=adt):
+                ref = capf_oracle.normalize_crop_(crop.clone())
+                feats = [f.float() for f in (capf_oracle.cpn_forward(sdd, images.permute(0, 3, 1, 2)) if args.backbone == "cpn"
+                                             else capf_oracle.hrnet_forward(sdd, images.permute(0, 3, 1, 2), cfg.model.backbone))]
+            loss = torch.mean(torch.norm(capf_oracle.lifter_forward(sd2, kp2d, ref, feats) - gt, dim=3))
+            topt.zero_grad()
+            loss.backward()
+            topt.step()
+
+        try:
+            yms = timed(ystep, max(3, steps // 2), warm=3)
+            rec["pytorch_eager_yardstick"] = {"value": B / yms * 1e3, "unit": "frames/s", "ms_per_step": yms,
+                                              "what": f"same step in PyTorch-eager CUDA: autocast({args.precision}) channels-last backbone under no_grad, "
+                                                      "autograd over the lifter (eval-mode blocks), torch.optim.AdamW; library kernels only"}
+        except Exception as e:  # noqa: BLE001
+            rec["pytorch_eager_yardstick"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.backends.cudnn.benchmark = bench_flag
+    return rec
+
+
 def parity_of(wl, out, n):
     """rel-L2 / MPJPE of the first n frames of this rank against the fp32 CPU oracle (+ the library's fp32 mode)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -605,14 +675,20 @@ def run_native(args, label):
     # ---- the other BASELINE configs of this node size, shorter runs, same code path ----------------------------------
     others = []
     if args.config == 1 and not args.no_other_configs and label.find("custom") < 0:
-        todo = [2] if world == 1 else ([3, 4] if world == 8 else [])
-        for k in todo:
+        # (config index, precision override): configs[2] and the configs[1] workload in the fp32-class tensor-core mode at N = 1;
+        # the two 8-GPU configs at N = 8
+        todo = [(1, "bf16x3"), (2, None)] if world == 1 else ([(3, None), (4, None)] if world == 8 else [])
+        for k, prec in todo:
             a2 = argparse.Namespace(**vars(args))
             for key in ("backbone", "batch", "height", "width", "precision"):
                 setattr(a2, key, CONFIGS[k][key])
             a2.config = k
-            rec = {"baseline_config_index": k, "workload": workload_label(a2, k), "metric": metric_name(a2)}
-            log(f"other config {k}")
+            if prec:
+                a2.precision = prec
+            rec = {"baseline_config_index": k, "workload": workload_label(a2, k if not prec else None).replace(
+                       "(custom: not a BASELINE config)", f"(BASELINE configs[{k}] workload in precision {prec}: the tensor-core mode held to 1e-3)"),
+                   "metric": metric_name(a2)}
+            log(f"other config {k} {prec or ''}")
             try:
                 w2 = Workload(a2, dev, rank, world, graph=not args.no_graph)
                 st = max(5, args.steps // 2)
@@ -627,15 +703,24 @@ def run_native(args, label):
                             "e2e": {"value": a2.batch * world * st / (ms2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2},
                             "whole_step_tflops": w2.plan.prog.flops() / (ms2 / st * 1e-3) / 1e12})
                 if rank == 0 and not args.no_cpu:
-                    rec["parity"], _ = parity_of(w2, out2, 2)
+                    rec["parity"], _ = parity_of(w2, out2, 4 if prec else 2)
                 del w2
             except Exception as e:  # noqa: BLE001
                 rec["error"] = f"{type(e).__name__}: {e}"[:300]
             torch.cuda.empty_cache()
             others.append(rec)
+    train_rec = None
+    if world == 1 and rank == 0 and args.config == 1 and not args.no_other_configs and label.find("custom") < 0:
+        log("training step")
+        try:
+            train_rec = training_step_record(args, dev)
+        except Exception as e:  # noqa: BLE001
+            train_rec = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
     log("done")
     if rank == 0:
         line["other_configs"] = others
+        line["train_step"] = train_rec
         if saved_stdout is not None:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)

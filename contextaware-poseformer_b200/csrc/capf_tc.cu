@@ -46,6 +46,7 @@ struct TcP {
   int cpt;                  // chunks per filter tap = Cin / kb (split operands: pass 0 walks the hi|lo planes, 2 * C / kb)
   int cpt1;                 // split operands only: chunks per tap of pass 1 (the hi plane alone, C / kb); else 0
   int KH;
+  int c_a1;                 // rows mode with TWO A matrices (K-concatenation): chunks that come from the first one; else num_chunks
   int cps;                  // chunks per pipeline stage = 64 / kb
   int KW, stride, pad;
   int bw, bh, bn;           // conv mode: output-pixel box (x, y, image) of one 128-row tile, bw*bh*bn <= 128
@@ -103,7 +104,7 @@ __device__ __forceinline__ void tile_range(const TcP& p, int& t0, int& t1) {
 // MODE: bit 0 = residual add, bit 1 = GELU (compile-time epilogue variants)
 template <typename TO, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcP p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapA2, const TcP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzled tiles need 1024-byte alignment
@@ -127,6 +128,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapA);
     ptx::prefetch_tmap(&mapB);
+    if (p.c_a1 < p.num_chunks) ptx::prefetch_tmap(&mapA2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
@@ -179,7 +181,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           uint32_t b_dst = a_dst + p.a_stage_bytes;
           for (int j = 0; j < nc; ++j) {
             if (p.mode == 1) ptx::tma_load_4d(&mapA, full, a_dst, cc * p.kb, ix_base + sx, iy_base + r, n0);
-            else ptx::tma_load_2d(&mapA, full, a_dst, cc * p.kb, m0);
+            else if (cc < p.c_a1) ptx::tma_load_2d(&mapA, full, a_dst, cc * p.kb, m0);
+            else ptx::tma_load_2d(&mapA2, full, a_dst, (cc - p.c_a1) * p.kb, m0);      // second operand of a K-concatenated Linear
             ptx::tma_load_2d(&mapB, full, b_dst, kcol, nb0);
             a_dst += p.a_chunk_bytes;
             b_dst += p.b_chunk_bytes;
@@ -425,7 +428,7 @@ struct TcConvState {
   TcHalo128State* h128 = nullptr; // non-null: halo band + streamed weights (C = Cout = 128)
   Tc2State* two = nullptr;       // non-null: the op runs on the 2-CTA GEMM kernel (capf_tc2.cu)
   TcBlockState* blk = nullptr;   // non-null: a fused BasicBlock op (capf_tc_block.cu)
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapA2;
   TcP p;
   int grid;
   int smem_bytes;
@@ -464,6 +467,10 @@ int tc_conv_supported(const capf_op& op) {
   const ConvGeo g = geo_of(op);
   if (g.Cin <= 0 || g.Cin % 16 || g.Cout <= 0 || g.Cout % 16) return 0;
   if (op.i[18] != 0 && (op.i[18] != 1 || op.dtype_in != CAPF_BF16)) return 0;     // split operands are bf16 hi|lo planes
+  if (op.i[19] != 0) {        // second A matrix (K-concatenation): plain 1x1 / stride 1 rows only
+    if (op.i[19] < 0 || op.i[19] % 16 || op.i[18] != 0 || g.KH != 1 || g.KW != 1 || g.stride != 1 || g.pad != 0) return 0;
+    if (!op.in[5] || ((uintptr_t)op.in[5] & 15)) return 0;
+  }
   if (g.KH < 1 || g.KW < 1 || g.KH > 7 || g.KW > 7 || g.stride < 1 || g.stride > 2 || g.pad < 0) return 0;
   if (g.N <= 0 || g.H <= 0 || g.W <= 0) return 0;
   if (g.Ho != (g.H + 2 * g.pad - g.KH) / g.stride + 1 || g.Wo != (g.W + 2 * g.pad - g.KW) / g.stride + 1) return 0;
@@ -524,7 +531,8 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   TcConvState* s = new (std::nothrow) TcConvState();
   if (!s) return set_error(CAPF_ERR_ARG, "tc_conv_prepare: out of host memory");
   const bool split = op.i[18] == 1;             // A = [.., 2 * Cin] bf16 (hi | lo planes), B = [Cout][taps * 3 * Cin], see capf_b200.h
-  if (!split && op.i[13] == 0 && tc2_supported(op)) {     // wide Linears over many rows: CTA pairs (cta_group::2)
+  const int Cin2 = op.i[19];                    // second A matrix [M][Cin2] in in[5]: out = [x | x2] W^T, W = [Cout][Cin + Cin2]
+  if (!split && !Cin2 && op.i[13] == 0 && tc2_supported(op)) {     // wide Linears over many rows: CTA pairs (cta_group::2)
     e = tc2_prepare(op, &s->two);
     if (e) { delete s; return e; }
     *out = s;
@@ -548,11 +556,13 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   memset(&p, 0, sizeof(p));
   const bool rows = (g.KH == 1 && g.KW == 1 && g.stride == 1 && g.pad == 0);
   p.mode = rows ? 0 : 1;
-  p.kb = g.Cin % 64 == 0 ? 64 : g.Cin % 32 == 0 ? 32 : 16;
+  p.kb = (g.Cin | Cin2) % 64 == 0 ? 64 : (g.Cin | Cin2) % 32 == 0 ? 32 : 16;
   p.cpt = (split ? 2 : 1) * g.Cin / p.kb;
   p.cpt1 = split ? g.Cin / p.kb : 0;
   p.cps = 64 / p.kb;
-  p.num_chunks = g.KH * g.KW * (p.cpt + p.cpt1);
+  p.num_chunks = g.KH * g.KW * (p.cpt + p.cpt1) + Cin2 / p.kb;
+  p.c_a1 = Cin2 ? p.cpt : p.num_chunks;
+  if (Cin2) p.cpt = p.num_chunks;               // rows mode: one "tap" that spans both operands
   p.KW = g.KW; p.KH = g.KH; p.stride = g.stride; p.pad = g.pad;
   p.Cout = g.Cout; p.Ho = g.Ho; p.Wo = g.Wo; p.Nimg = g.N;
   p.act = g.act;
@@ -562,7 +572,7 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   p.trace = (long long*)op.in[4];     // debug only (NULL in every program the host layer builds)
   p.M = g.N * g.Ho * g.Wo;
   const int swz = p.kb * 2;
-  const int K = g.KH * g.KW * g.Cin * (split ? 3 : 1);      // GEMM depth (3x with split operands: hi*Wh + lo*Wh + hi*Wl)
+  const int K = g.KH * g.KW * g.Cin * (split ? 3 : 1) + Cin2;      // GEMM depth (3x with split operands: hi*Wh + lo*Wh + hi*Wl)
   const int Ca = g.Cin * (split ? 2 : 1);                   // channels of the A tensor in memory
   const int osz = op.dtype_out == CAPF_F32 ? 4 : 2;
 
@@ -671,12 +681,19 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
     cuuint32_t box[2] = {(cuuint32_t)p.kb, (cuuint32_t)(128 * p.msub)};
     cuuint32_t es[2] = {1, 1};
     e = tc_encode_map(&s->mapA, dt, 2, op.in[0], dims, strides, box, es, swz, "A rows");
+    s->mapA2 = s->mapA;
+    if (!e && Cin2) {
+      cuuint64_t dims2[2] = {(cuuint64_t)Cin2, (cuuint64_t)p.M};
+      cuuint64_t strides2[1] = {(cuuint64_t)Cin2 * 2};
+      e = tc_encode_map(&s->mapA2, dt, 2, op.in[5], dims2, strides2, box, es, swz, "A2 rows");
+    }
   } else {
     cuuint64_t dims[4] = {(cuuint64_t)Ca, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
     cuuint64_t strides[3] = {(cuuint64_t)Ca * 2, (cuuint64_t)g.W * Ca * 2, (cuuint64_t)g.H * g.W * Ca * 2};
     cuuint32_t box[4] = {(cuuint32_t)p.kb, (cuuint32_t)(p.bw * g.stride), (cuuint32_t)(p.bh * g.stride), (cuuint32_t)p.bn};
     cuuint32_t es[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
     e = tc_encode_map(&s->mapA, dt, 4, op.in[0], dims, strides, box, es, swz, "A conv");
+    s->mapA2 = s->mapA;
   }
   if (!e) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)g.Cout};
@@ -699,7 +716,7 @@ static int tc_launch_mode(const TcConvState* s, cudaStream_t st) {
     if (e != cudaSuccess) return set_errorf(CAPF_ERR_CUDA, "tc_gemm_kernel smem opt-in: %s", cudaGetErrorString(e));
     max_smem = TC_SMEM_LIMIT;
   }
-  launch_k(tc_gemm_kernel<TO, MODE>, dim3(s->grid), dim3(TC_THREADS), s->smem_bytes, st, s->mapA, s->mapB, s->p);
+  launch_k(tc_gemm_kernel<TO, MODE>, dim3(s->grid), dim3(TC_THREADS), s->smem_bytes, st, s->mapA, s->mapB, s->mapA2, s->p);
   return check_launch("tc_gemm_kernel");
 }
 
@@ -734,7 +751,8 @@ void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
   if (s->two) { tc2_describe(s->two, buf, cap); return; }
   if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
   if (s->h128) { tc_halo128_describe(s->h128, buf, cap); return; }
-  snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages%s]", 128 * s->p.msub, s->p.BN, s->p.num_stages, s->p.cpt1 ? ", bf16x3 split operands" : "");
+  snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages%s%s]", 128 * s->p.msub, s->p.BN, s->p.num_stages, s->p.cpt1 ? ", bf16x3 split operands" : "",
+           s->p.c_a1 < s->p.num_chunks ? ", two A operands" : "");
 }
 
 void tc_conv_release(TcConvState* s) {

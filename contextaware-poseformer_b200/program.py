@@ -348,6 +348,7 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
     prog.feature_maps = [m.ref for m in maps]
     if pb.use_tc:
         fuse_basic_blocks(prog)
+        fuse_downsample(prog)
         chunk_prefix(prog)
     prog.n_backbone_ops = len(prog.ops)
     if backbone_only:
@@ -518,6 +519,62 @@ def fuse_basic_blocks(prog: Program):
             out.append(a)
             k += 1
     prog.ops[:] = out
+    return fused
+
+
+# ------------------------------------------------------------------------------------------------------
+# peephole: Bottleneck conv3 + downsample conv -> one GEMM over the concatenated inputs
+# ------------------------------------------------------------------------------------------------------
+def fuse_downsample(prog: Program):
+    """A Bottleneck whose shortcut is a 1x1 conv + BN (pose_hrnet.py:116-136 with `downsample`, :421-427; networks/resnet.py,
+    networks/refineNet.py:17-21) computes relu(bn3(conv3(t)) + bn_d(conv_d(x))): two per-pixel GEMMs into the same output.
+    As separate ops the shortcut tensor (256 channels: 537 MB at bs = 256 for HRNet's layer1.0) is written by one kernel and read
+    back as the residual of the other.  Here both become ONE CAPF_OP_CONV2D with two A operands (i[19] = Cin2, in[5] = x):
+    out = act([t | x] . [W3 | Wd]^T + b3 + bd), accumulated in fp32 -- the shortcut never exists in memory.  Stride-1 shortcuts
+    only (a strided shortcut is not a plain row-major matrix).  CAPF_FUSE_DOWNSAMPLE=0 keeps the two-op form."""
+    if os.environ.get("CAPF_FUSE_DOWNSAMPLE", "1") == "0":
+        return 0
+    ops = prog.ops
+    readers = {}
+    for op in ops:
+        for b in op.ins:
+            if isinstance(b, Buf):
+                readers[b.root] = readers.get(b.root, 0) + 1
+
+    def plain_1x1(op):
+        return (op.kind == lib.OP_CONV2D and op.i[12] == lib.IMPL_TCGEN05 and op.i[5:9] == [1, 1, 1, 0] and len(op.i) <= 13
+                and op.dtype_in in ("f16", "bf16") and op.i[3] % 16 == 0)
+
+    producer = {}
+    for k, op in enumerate(ops):
+        for b in op.outs:
+            if isinstance(b, Buf):
+                producer[b.root] = k
+    drop, fused = set(), 0
+    for k, b in enumerate(ops):
+        if not plain_1x1(b) or not isinstance(b.ins[3], Buf):
+            continue
+        ka = producer.get(b.ins[3].root)
+        if ka is None or ka in drop:
+            continue
+        a = ops[ka]
+        if (not plain_1x1(a) or a.ins[3] is not None or a.i[11] != lib.ACT_NONE or a.i[0:3] != b.i[0:3] or a.i[4] != b.i[4]
+                or a.dtype_in != b.dtype_in or a.dtype_out != b.dtype_out or readers.get(a.outs[0].root, 0) != 1
+                or a.outs[0].role != "act" or not _same_buf(a.outs[0], b.ins[3])):
+            continue
+        wa, wb, ba, bb = a.ins[1], b.ins[1], a.ins[2], b.ins[2]
+        cin1, cin2, cout = b.i[3], a.i[3], b.i[4]
+        w = WSlot(wb.name + "+" + wa.name, (cout, cin1 + cin2), wb.dtype,
+                  (lambda pb_, pa_: lambda st: torch.cat([pb_(st), pa_(st)], dim=1).contiguous())(wb.pack, wa.pack))
+        bias = WSlot(bb.name + "+" + ba.name, (cout,), "f32", (lambda pb_, pa_: lambda st: (pb_(st) + pa_(st)).contiguous())(bb.pack, ba.pack))
+        i = list(b.i) + [0] * (20 - len(b.i))
+        i[19] = cin2
+        ops[k] = Op(lib.OP_CONV2D, b.dtype_in, b.dtype_out, i, list(b.f), [b.ins[0], w, bias, None, None, a.ins[0]], list(b.outs),
+                    tag=b.tag + "+" + a.tag.rsplit(".", 2)[-2] + "." + a.tag.rsplit(".", 1)[-1], flops=a.flops + b.flops,
+                    nbytes=b.ins[0].nbytes + a.ins[0].nbytes + b.outs[0].nbytes + (cin1 + cin2) * cout * _ITEMSIZE[wb.dtype] + 4 * cout)
+        drop.add(ka)
+        fused += 1
+    prog.ops[:] = [op for k, op in enumerate(ops) if k not in drop]
     return fused
 
 

@@ -93,6 +93,10 @@ typedef enum capf_op_kind {
  *     i[16] = per-tap kernel column-tile width hint (0 automatic, else a multiple of 16 dividing Cout)
  *     i[17] = 2-CTA (cta_group::2) GEMM kernel for Linears over rows: 0 automatic (wide Linears with many rows),
  *             1 never, 2 always when the shape allows (K % 64 == 0, Cout % 16 == 0)
+ *     i[18] = 1: split operands (precision "bf16x3"): x is [N,H,W,2*Cin] bf16, the hi | lo planes CAPF_OP_CAST (i[2] = Cin) writes,
+ *             w is [Cout][KH*KW*(Wh | Wh)][KH*KW*Wl] bf16; the kernel accumulates hi*Wh + lo*Wh + hi*Wl (per-tap kernel only)
+ *     i[19] = Cin2 > 0: a SECOND input x2 [N,H,W,Cin2] in in[5] (1x1 / stride 1 only): out = [x | x2] . w^T with
+ *             w = [Cout][Cin + Cin2] -- a Bottleneck's conv3 and its downsample conv as one GEMM (pose_hrnet.py:116-136)
  *     in[0]=x  [N,H,W,Cin]        dtype_in
  *     in[1]=w  SIMT: [KH*KW*Cin][Cout] (tap-major rows, Cout contiguous); TCGEN05: [Cout][KH*KW*Cin];
  *              dtype_in, except x f32 -> w f32.  BatchNorm scale is pre-folded into w by the host.

@@ -48,6 +48,11 @@ class Interp:
         else:
             x = self.t(op.ins[0]).reshape(N, H, W, Cin).float().permute(0, 3, 1, 2)
             w = self.t(op.ins[1]).float()
+            cin2 = op.i[19] if len(op.i) > 19 else 0
+            if cin2:                                  # second A operand: out = [x | x2] . w^T (1x1 only)
+                x2 = self.t(op.ins[5]).reshape(N, H, W, cin2).float().permute(0, 3, 1, 2)
+                x = torch.cat([x, x2], dim=1)
+                Cin = Cin + cin2
             if impl == lib.IMPL_TCGEN05:
                 w = w.reshape(Cout, KH, KW, Cin).permute(0, 3, 1, 2)
             else:

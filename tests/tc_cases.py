@@ -143,3 +143,23 @@ def run_split_case(case, msub=0):
     d = out.cpu() - y
     d = torch.where(torch.isfinite(d), d, torch.full_like(d, 1e3))
     return float(d.double().norm() / y.double().norm()), float(d.abs().max())
+
+
+def run_dual_case(M, C1, C2, Cout, act, dt=torch.float16, out_f32=False):
+    """CAPF_OP_CONV2D with two A operands (i[19] = Cin2, in[5] = x2): out = act([x | x2] . w^T + b) against fp32 PyTorch on the
+    16-bit-rounded inputs.  Returns rel_l2."""
+    g = torch.Generator().manual_seed(M * 7 + C1 + 3 * C2 + Cout)
+    x1, x2 = torch.randn(M, C1, generator=g), torch.randn(M, C2, generator=g)
+    w = torch.randn(Cout, C1 + C2, generator=g) / (C1 + C2) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    y = torch.cat([x1.to(dt).float(), x2.to(dt).float()], 1).double() @ w.to(dt).double().t() + b.double()
+    y = y.float()
+    if act == lib.ACT_RELU:
+        y = F.relu(y)
+    odt = torch.float32 if out_f32 else dt
+    out = torch.full((M, Cout), float("nan"), dtype=odt, device=DEV)
+    ints = [M, 1, 1, C1, Cout, 1, 1, 1, 0, 1, 1, act, lib.IMPL_TCGEN05, 0, 0, 0, 0, 0, 0, C2]
+    run_op(lib.OP_CONV2D, dt, odt, ints, [], [x1.to(dt).to(DEV), w.to(dt).to(DEV), b.to(DEV), None, None, x2.to(dt).to(DEV)], [out])
+    d = out.float().cpu() - y
+    d = torch.where(torch.isfinite(d), d, torch.full_like(d, 1e3))
+    return float(d.double().norm() / y.double().norm())

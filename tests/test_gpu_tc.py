@@ -61,6 +61,19 @@ def test_halo128_conv_matches_fp32_reference(case, dt):
     assert buf.value.decode().startswith("tc_conv3_halo128_kernel"), buf.value
 
 
+@pytest.mark.parametrize("M,C1,C2,Cout", [(1000, 64, 64, 256), (4096, 128, 256, 256), (300, 64, 256, 256), (129, 32, 16, 48), (5000, 512, 256, 1024)])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_two_operand_linear_matches_fp32_reference(M, C1, C2, Cout, dt):
+    """A Bottleneck's conv3 and its downsample conv as ONE GEMM over the K-concatenated inputs (program.fuse_downsample;
+    pose_hrnet.py:116-136, networks/refineNet.py:17-45): every chunk-width combination, ragged M, both 16-bit types."""
+    from capf_b200 import lib
+    from tc_cases import run_dual_case
+    rel = run_dual_case(M, C1, C2, Cout, lib.ACT_RELU, dt)
+    print(f"dual {M}x({C1}+{C2})->{Cout} {dt}: rel-L2 {rel:.3e}")
+    assert rel < (1.5e-3 if dt == torch.float16 else 8e-3)
+    assert run_dual_case(M, C1, C2, Cout, lib.ACT_NONE, dt, out_f32=True) < 2e-5
+
+
 SPLIT_CASES = [c for c in TC_CASES if c[1][3] % 16 == 0]
 
 
