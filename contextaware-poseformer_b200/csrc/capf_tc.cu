@@ -150,12 +150,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t acc_stride = (uint32_t)p.acc_stride;
-  // PDL: this one-wave persistent grid is fully resident -> let the successor be scheduled as SMs drain; nothing
-  // produced by the predecessor (activations, residual) has been touched before this point.
+  // PDL: this one-wave persistent grid is fully resident -> let the successor be scheduled as SMs drain.  griddepcontrol.wait
+  // is per thread: every role waits right before it first touches what the predecessor produced (activations, residual,
+  // output).  The producer first does its tile arithmetic and requests the WEIGHT boxes of its first stages (constant
+  // data), so their L2 / HBM latency and its own set-up overlap the predecessor's tail; the MMA issuer never touches
+  // global memory and does not wait at all.
   if (tr && threadIdx.x == 0) p.trace[2] = clock64();
   pdl_trigger();
-  pdl_wait();
-  if (tr && threadIdx.x == 0) p.trace[3] = clock64();
   int t0, t1;
   tile_range(p, t0, t1);
   const int tile_rows = 128 * p.msub;
@@ -166,6 +167,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t stage = 0, phase = 0;
       TileWalk w;
       w.init(p, t0);
+      // weights of the first stages of the first tile, before the dependency wait
+      int pre = 0;
+      if (t0 < t1) {
+        const int k_stages = (p.num_chunks + p.cps - 1) / p.cps;
+        pre = min(p.num_stages, k_stages);
+        const int nb0 = w.n_tile * p.BN;
+        for (int s2 = 0; s2 < pre; ++s2) {
+          const int c0 = s2 * p.cps, nc = min(p.cps, p.num_chunks - c0);
+          const uint32_t full = bar_full + 8 * s2;
+          ptx::mbar_arrive_expect_tx(full, (uint32_t)(nc * p.tx_bytes_per_chunk));
+          uint32_t b_dst = stage0 + s2 * p.stage_bytes + p.a_stage_bytes;
+          for (int j = 0; j < nc; ++j) {
+            ptx::tma_load_2d(&mapB, full, b_dst, (c0 + j) * p.kb, nb0);
+            b_dst += p.b_chunk_bytes;
+          }
+        }
+      }
+      pdl_wait();
+      if (tr) p.trace[3] = clock64();
       for (int tile = t0; tile < t1; ++tile, w.next(p)) {
         const int m0 = (w.tx + p.tiles_x * (w.ty + p.tiles_y * w.tn)) * tile_rows;      // rows mode (tiles_y == 1)
         const int ix_base = w.tx * p.bw * p.stride - p.pad, iy_base = w.ty * p.bh * p.stride - p.pad, n0 = w.tn * p.bn;
@@ -173,17 +193,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int r = 0, sx = 0, cc = 0, kcol = 0;       // filter tap (r, sx), channel chunk inside the tap, B column
         int cpt = p.cpt;                           // split operands: a second pass over the taps with the hi plane only
         for (int c0 = 0; c0 < p.num_chunks; c0 += p.cps) {
-          ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          const bool primed = tile == t0 && c0 < pre * p.cps;      // B already requested, barrier already armed
+          if (!primed) ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const int nc = min(p.cps, p.num_chunks - c0);
           const uint32_t full = bar_full + 8 * stage;
-          ptx::mbar_arrive_expect_tx(full, (uint32_t)(nc * p.tx_bytes_per_chunk));
+          if (!primed) ptx::mbar_arrive_expect_tx(full, (uint32_t)(nc * p.tx_bytes_per_chunk));
           uint32_t a_dst = stage0 + stage * p.stage_bytes;
           uint32_t b_dst = a_dst + p.a_stage_bytes;
           for (int j = 0; j < nc; ++j) {
             if (p.mode == 1) ptx::tma_load_4d(&mapA, full, a_dst, cc * p.kb, ix_base + sx, iy_base + r, n0);
             else if (cc < p.c_a1) ptx::tma_load_2d(&mapA, full, a_dst, cc * p.kb, m0);
             else ptx::tma_load_2d(&mapA2, full, a_dst, (cc - p.c_a1) * p.kb, m0);      // second operand of a K-concatenated Linear
-            ptx::tma_load_2d(&mapB, full, b_dst, kcol, nb0);
+            if (!primed) ptx::tma_load_2d(&mapB, full, b_dst, kcol, nb0);
             a_dst += p.a_chunk_bytes;
             b_dst += p.b_chunk_bytes;
             kcol += p.kb;
@@ -297,6 +318,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint32_t acc = 0, acc_phase = 0;
     TileWalk w;
     w.init(p, t0);
+    pdl_wait();                                       // residual reads / output writes start below
     for (int tile = t0; tile < t1; ++tile) {
       const int myrow = row_index(w);
       const int ncol0 = w.n_tile * p.BN;
