@@ -650,7 +650,8 @@ def chunk_prefix(prog: Program, chunk: int = None):
 # execution lanes: the branches of a HighResolutionModule are independent chains (pose_hrnet.py:289-290)
 # ------------------------------------------------------------------------------------------------------
 MAX_LANES = 4
-_LANE_RE = re.compile(r"\.stage\d+\.\d+\.branches\.(\d+)\.|\.stage\d+\.\d+\.fuse_layers\.\d+\.(\d+)\.|\.transition\d+\.(\d+)\.")
+_LANE_RE = re.compile(r"\.stage\d+\.\d+\.branches\.(\d+)\.|\.stage\d+\.\d+\.fuse_layers\.\d+\.(\d+)\.|\.transition\d+\.(\d+)\."
+                      r"|\.refine_net\.cascade\.(\d+)\.")
 
 
 def assign_lanes(prog: Program, enable: bool = True):
@@ -672,6 +673,11 @@ def assign_lanes(prog: Program, enable: bool = True):
             m = _LANE_RE.search(op.tag)
             if m:
                 lane = int(next(g for g in m.groups() if g is not None))
+        elif op.kind == lib.OP_BILINEAR:
+            # CPN: the resize that ends a RefineNet cascade (refineNet.py:72-88) stays on the cascade's lane; the four cascades are
+            # independent chains of small kernels (8x8 ... 64x64 maps) that then overlap instead of queueing
+            src = op.ins[0]
+            lane = producer_lane.get(src.root, 0) if isinstance(src, Buf) else 0
         elif op.kind == lib.OP_FUSE_SUM:
             # output index i = position of the identity term: terms are ordered j = 0..n-1, j > i carry a shift
             shifts = op.i[5:5 + op.i[4]]

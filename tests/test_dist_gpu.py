@@ -69,3 +69,63 @@ def test_nccl_gather_equals_single_gpu_forward():
     for rank, rows in res:
         for graph, eq_a, eq_b, shape in rows:
             assert eq_a and eq_b and shape == (12, 1, 17, 3), (rank, graph, eq_a, eq_b, shape)
+
+
+def _ddp_worker(rank, world, port, q):
+    """train.py:362 wraps the model in DistributedDataParallel: the hand-written backward must compose with DDP's gradient
+    all-reduce (hooks on the leaf parameters), i.e. every rank ends with the MEAN of the per-shard gradients."""
+    import capf_b200
+    import protocol
+    from torch.nn.parallel import DistributedDataParallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        B, H, W = 2, 64, 64
+        cfg = capf_b200.make_config("hrnet_32")
+
+        def make():
+            m = capf_b200.CA_PF(cfg, precision="fp32")
+            w = protocol.make_weights([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 0)
+            m.load_state_dict(w, strict=True)
+            m = m.to(dev)
+            m.train()
+            m.backbone.eval()
+            m.volume_net.train()
+            m.volume_net.drop_path_rate = 0.0
+            return m
+
+        images, kp2d, crop = protocol.make_inputs(world * B, H, W, 31)
+        gt = torch.randn(world * B, 1, 17, 3, generator=torch.Generator().manual_seed(5)) * 0.3
+
+        def loss_of(model, s, e):
+            pred = model(images[s:e].to(dev), kp2d[s:e].to(dev), crop[s:e].clone().to(dev))
+            return torch.mean(torch.norm(pred - gt[s:e].to(dev), dim=3))
+
+        ddp = DistributedDataParallel(make(), device_ids=[rank])
+        loss_of(ddp, rank * B, (rank + 1) * B).backward()
+        got = {n: p.grad.detach().clone() for n, p in ddp.module.volume_net.named_parameters()}
+        solo = make()
+        for r in range(world):                       # same shards, one process: accumulate and average by hand
+            (loss_of(solo, r * B, (r + 1) * B) / world).backward()
+        worst = 0.0
+        for n, p in solo.volume_net.named_parameters():
+            worst = max(worst, float((got[n] - p.grad).norm() / p.grad.norm().clamp_min(1e-30)))
+        q.put((rank, worst))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_training_step_under_ddp_averages_gradients():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert all(w < 1e-5 for _, w in res), res
