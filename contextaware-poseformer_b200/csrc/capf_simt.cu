@@ -1485,6 +1485,24 @@ __global__ void __launch_bounds__(256) cast_split_kernel(size_t groups, int C8, 
   }
 }
 
+// fp32 weight matrix [rows][C] (optionally read transposed from [C][rows]) -> the B operand of a split-operand GEMM:
+// [rows][hi (C) | hi (C) | lo (C)] bf16 (program.split_weight_packer for one tap), for weights that change every step (training).
+__global__ void __launch_bounds__(256) pack_split_weight_kernel(int rows, int C, int transposed, const float* __restrict__ w,
+                                                                __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  const size_t total = (size_t)rows * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i - (size_t)r * C);
+    const float v = __ldg(transposed ? w + (size_t)c * rows + r : w + i);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+    __nv_bfloat16* o = out + (size_t)r * 3 * C + c;
+    o[0] = hi;
+    o[C] = hi;
+    o[2 * C] = lo;
+  }
+}
+
 int launch_embed_coord(const capf_op& op, cudaStream_t st) {
   int B = op.i[0], J = op.i[1], D = op.i[2], slabs = op.i[3];
   if (B <= 0 || J <= 0 || D <= 0 || slabs <= 0 || !op.in[0] || !op.in[1] || !op.in[2] || !op.in[3] || !op.out[0])
@@ -1513,6 +1531,13 @@ int launch_cast(const capf_op& op, cudaStream_t st) {
   size_t n = (size_t)(uint32_t)op.i[0] | ((size_t)(uint32_t)op.i[1] << 31);
   if (!n || !op.in[0] || !op.out[0]) return set_error(CAPF_ERR_ARG, "cast: bad arguments");
   int blocks = ew_blocks(n);
+  if (op.i[2] > 0 && op.i[3] > 0) {        // split WEIGHT layout: i[2] = C (input features), i[3] = 1 plain / 2 source stored transposed
+    if (op.dtype_in != CAPF_F32 || op.dtype_out != CAPF_BF16 || n % (size_t)op.i[2])
+      return set_error(CAPF_ERR_UNSUPPORTED, "cast (split weights): needs f32 -> bf16");
+    launch_k(pack_split_weight_kernel, dim3(blocks), dim3(256), 0, st, (int)(n / op.i[2]), op.i[2], op.i[3] == 2 ? 1 : 0, (const float*)op.in[0],
+             (__nv_bfloat16*)op.out[0]);
+    return check_launch("pack_split_weight");
+  }
   if (op.i[2] > 0) {                       // split planes: i[2] = channels per row
     if (op.dtype_in != CAPF_F32 || op.dtype_out != CAPF_BF16 || (op.i[2] & 7) || n % (size_t)op.i[2])
       return set_error(CAPF_ERR_UNSUPPORTED, "cast (split planes): needs f32 -> bf16 and a channel count that is a multiple of 8");

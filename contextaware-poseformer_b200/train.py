@@ -6,7 +6,9 @@ train.py:145-148) by calling ``model(images, kp2d, kp2d_crop)`` under autograd, 
 
 * ``CA_PF.forward`` in ``volume_net.train()`` mode with grad enabled runs the (frozen) backbone through its inference plan
   and the lifter through :class:`LifterFunction` -- a ``torch.autograd.Function`` whose forward and backward are
-  sequences of libcapf_b200 kernels (fp32, csrc/capf_train.cu + the inference samplers / LayerNorm / attention kernels);
+  sequences of libcapf_b200 kernels (fp32 storage; the forward and dgrad GEMMs on the tensor cores with split bfloat16
+  operands -- the `bf16x3` mode of the inference kernel, fp32-class --, wgrad and everything else in csrc/capf_train.cu, plus
+  the inference samplers / LayerNorm / attention kernels);
   autograd only routes the gradients into ``p.grad`` of the 191 ``volume_net`` parameters.
 * DropPath (timm ``drop_path``; rates ``linspace(0, 0.2, 4)``, pose_dformer.py:71,101,187): the per-sample keep masks
   are drawn with the same torch calls, in the same order and with the same shapes as the reference draws them, so a
@@ -74,19 +76,105 @@ def gemm(A, B, M, N, K, ta, tb, lda, ldb, out, ldc, bias=None, accumulate=False,
     return out
 
 
-def linear(x, W, b, M, out=None, accumulate=False, ldc=None):
-    """y[M][N] = x[M][K] W[N][K]^T + b   (nn.Linear)."""
+# ---- tensor-core path of the forward and dgrad GEMMs: split bfloat16 operands (precision "bf16x3": hi*Wh + lo*Wh + hi*Wl, fp32
+# accumulate, ~2^-16 operand precision) through the inference tcgen05 kernel.  Weights change every step, so they are packed on
+# the device (CAPF_OP_CAST i[3]); plans (TMA descriptors) are cached by pointers -- the caching allocator hands a steady-state
+# training loop the same addresses every step.  CAPF_TRAIN_TC=0 keeps everything on the fp32 CUDA-core GEMM.
+import os as _os
+
+USE_TC = _os.environ.get("CAPF_TRAIN_TC", "1") != "0"
+_TC_PLANS = {}
+_TC_PLANS_MAX = 2048
+_PACKED = None          # split-packed weights of the step in flight ({("f" | "t", data_ptr): tensor}); set by LifterFunction
+
+
+def _tc_ok(M, N, K):
+    return USE_TC and K % 16 == 0 and N % 16 == 0 and M >= 64
+
+
+def _split_rows(x, M, K):
+    """fp32 [M][K] -> bf16 [M][hi (K) | lo (K)] (CAPF_OP_CAST split planes)."""
+    xs = torch.empty(M, 2 * K, dtype=torch.bfloat16, device=x.device)
+    n = M * K
+    _run(lib.OP_CAST, lib.F32, lib.BF16, [n & 0x7fffffff, n >> 31, K], [], [x], [xs], x.device)
+    return xs
+
+
+def pack_split_weight(W, rows, C, transposed=False):
+    """fp32 weight [rows][C] (or its transpose stored [C][rows]) -> bf16 [rows][hi | hi | lo] for a split-operand GEMM."""
+    wp = torch.empty(rows, 3 * C, dtype=torch.bfloat16, device=W.device)
+    n = rows * C
+    _run(lib.OP_CAST, lib.F32, lib.BF16, [n & 0x7fffffff, n >> 31, C, 2 if transposed else 1], [], [W], [wp], W.device)
+    return wp
+
+
+def _tc_gemm(xs, wp, bias, M, K, N, out, residual=None):
+    """out[M][N] = (hi + lo)[M][K] . W^T (+ bias) (+ residual), through tc_gemm_kernel with split operands."""
+    import ctypes as C
+    dev = out.device
+    key = (xs.data_ptr(), wp.data_ptr(), 0 if bias is None else bias.data_ptr(), out.data_ptr(),
+           0 if residual is None else residual.data_ptr(), M, K, N, dev.index or 0)
+    h = _TC_PLANS.get(key)
+    L = lib.load()
+    if h is None:
+        if len(_TC_PLANS) >= _TC_PLANS_MAX:
+            for old in _TC_PLANS.values():
+                L.capf_plan_destroy(old)
+            _TC_PLANS.clear()
+        op = lib.CapfOp()
+        op.kind, op.dtype_in, op.dtype_out = lib.OP_CONV2D, lib.BF16, lib.F32
+        for n, v in enumerate([M, 1, 1, K, N, 1, 1, 1, 0, 1, 1, lib.ACT_NONE, lib.IMPL_TCGEN05, 1, 0, 0, 0, 0, 1]):
+            op.i[n] = v
+        op.inp[0], op.inp[1] = xs.data_ptr(), wp.data_ptr()
+        op.inp[2] = None if bias is None else bias.data_ptr()
+        op.inp[3] = None if residual is None else residual.data_ptr()
+        op.out[0] = out.data_ptr()
+        h = C.c_void_p()
+        arr = (lib.CapfOp * 1)(op)
+        lib.check(L.capf_plan_create(arr, 1, dev.index or 0, C.byref(h)), "train tc plan")
+        _TC_PLANS[key] = h
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.check(L.capf_plan_run(h, 0, 1, torch.cuda.current_stream(dev).cuda_stream), "train tc gemm")
+        e1.record()
+        PROFILE.append((lib.OP_CONV2D, (M, N, K), e0, e1))
+        return out
+    lib.check(L.capf_plan_run(h, 0, 1, torch.cuda.current_stream(dev).cuda_stream), "train tc gemm")
+    return out
+
+
+def linear(x, W, b, M, out=None, accumulate=False, ldc=None, packed=None):
+    """y[M][N] = x[M][K] W[N][K]^T + b   (nn.Linear).  `packed`: dict caching the split-packed weights of this step."""
     N, K = W.shape
     if out is None:
         out = _f32(M, N, dev=x.device)
+    packed = _PACKED if packed is None else packed
+    if _tc_ok(M, N, K) and (ldc is None or ldc == N):
+        wp = None if packed is None else packed.get(("f", W.data_ptr()))
+        if wp is None:
+            wp = pack_split_weight(W, N, K)
+            if packed is not None:
+                packed[("f", W.data_ptr())] = wp
+        return _tc_gemm(_split_rows(x, M, K), wp, b, M, K, N, out, residual=out if accumulate else None)
     return gemm(x, W, M, N, K, 0, 1, K, K, out, ldc or N, b, accumulate)
 
 
-def linear_bwd(x, W, dy, M, need_dx=True, need_db=True):
+def linear_bwd(x, W, dy, M, need_dx=True, need_db=True, packed=None):
     """-> (dx [M][K] or None, dW [N][K], db [N] or None) of y = x W^T + b."""
     N, K = W.shape
     dev = x.device
-    dx = gemm(dy, W, M, K, N, 0, 0, N, K, _f32(M, K, dev=dev), K) if need_dx else None
+    dx = None
+    packed = _PACKED if packed is None else packed
+    if need_dx and _tc_ok(M, K, N):
+        wt = None if packed is None else packed.get(("t", W.data_ptr()))
+        if wt is None:
+            wt = pack_split_weight(W, K, N, transposed=True)        # W^T [K][N]: the "weight" of dx = dy . W
+            if packed is not None:
+                packed[("t", W.data_ptr())] = wt
+        dx = _tc_gemm(_split_rows(dy, M, N), wt, None, M, N, K, _f32(M, K, dev=dev))
+    elif need_dx:
+        dx = gemm(dy, W, M, K, N, 0, 0, N, K, _f32(M, K, dev=dev), K)
     tiles = ((N + 63) // 64) * ((K + 63) // 64)
     splits = max(1, min(64, (296 + tiles - 1) // tiles, M // 256))
     dW = gemm(dy, x, N, K, M, 1, 0, N, K, _f32(N, K, dev=dev), K, splits=splits)
@@ -362,16 +450,27 @@ class LifterFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, geometry, maps, scales, names, kp2d, ref, *params):
+        global _PACKED
         named = dict(zip(names, params))
         P = _param_view(named)
-        out, sv = lifter_forward(P, geometry, maps, kp2d, ref, scales)
-        ctx.capf = (geometry, maps, names, P, sv, kp2d, ref, [tuple(p.shape) for p in params])
+        packed = {}
+        _PACKED = packed
+        try:
+            out, sv = lifter_forward(P, geometry, maps, kp2d, ref, scales)
+        finally:
+            _PACKED = None
+        ctx.capf = (geometry, maps, names, P, sv, kp2d, ref, [tuple(p.shape) for p in params], packed)
         return out.view(geometry.B, 1, J, 3)
 
     @staticmethod
     def backward(ctx, dout):
-        geometry, maps, names, P, sv, kp2d, ref, shapes = ctx.capf
-        G = lifter_backward(P, geometry, maps, kp2d, ref, sv, dout.contiguous().view(-1, 3).float())
+        global _PACKED
+        geometry, maps, names, P, sv, kp2d, ref, shapes, packed = ctx.capf
+        _PACKED = packed
+        try:
+            G = lifter_backward(P, geometry, maps, kp2d, ref, sv, dout.contiguous().view(-1, 3).float())
+        finally:
+            _PACKED = None
         for n in list(G):
             if n.endswith(".ow.weight"):
                 q = n[: -len(".ow.weight")]

@@ -163,6 +163,8 @@ typedef enum capf_op_kind {
  * CAPF_OP_CAST -- dtype conversion of a dense array.  i[0],i[1]=element count (lo,hi 31-bit words) in[0] out[0]
  *     i[2] = 0, or C > 0 (f32 -> bf16 only): "split planes" -- every row of C elements becomes 2C bf16 values
  *            [hi (C) | lo (C)], hi = bf16(x), lo = bf16(x - hi): the A operand of a split-operand CONV2D (i[18] = 1)
+ *     i[3] = 1 | 2 (with i[2] = C): the B operand instead -- rows [hi | hi | lo] (3C values) of a weight matrix [rows][C]
+ *            (2: the source is stored transposed, [C][rows]); used for weights that change every step (training)
  *
  * CAPF_OP_BASICBLOCK -- one fused HRNet BasicBlock (pose_hrnet.py:66-95): y = relu(bn2(conv2(relu(bn1(conv1(x))))) + x), both
  *                    convolutions 3x3 / stride 1 / pad 1, C -> C channels (C = 32), 16-bit NHWC; the intermediate never leaves

@@ -27,13 +27,19 @@ def rnd(*shape, seed=0, scale=1.0):
 
 # ---- kernels ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(300, 48, 128), (37, 3, 640), (4352, 1920, 640), (128, 128, 21760), (65, 70, 33)])
-def test_gemm_f32_all_transposes_and_split_k(M, N, K):
+@pytest.mark.parametrize("tc", [False, True], ids=["cuda-core", "tensor-core"])
+def test_linear_forward_backward_all_transposes_and_split_k(M, N, K, tc, monkeypatch):
+    """y = x W^T + b, dx = dy W, dW = dy^T x (split over the rows, fixed-order reduce), db.  cuda-core: the fp32 GEMM of
+    capf_train.cu for all three; tensor-core: forward and dgrad through the split-bf16 tcgen05 kernel where the shape allows
+    (K, N % 16 == 0), wgrad stays fp32 -- fp32-class either way."""
+    monkeypatch.setattr(train, "USE_TC", tc)
     x, W, dy = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(M, N, seed=3)
     b = rnd(N, seed=4)
+    tol = 3e-5 * max(1.0, (max(K, N) / 1280.0) ** 0.5) if tc else 2e-6     # split-bf16 operands: 2^-16 per product, random-walk over the depth
     y = train.linear(x, W, b, M)
-    assert rel_l2(y.cpu(), (x.double() @ W.double().t() + b.double()).float().cpu()) < 2e-6
+    assert rel_l2(y.cpu(), (x.double() @ W.double().t() + b.double()).float().cpu()) < tol
     dx, dW, db = train.linear_bwd(x, W, dy, M)
-    assert rel_l2(dx.cpu(), (dy.double() @ W.double()).float().cpu()) < 2e-6
+    assert rel_l2(dx.cpu(), (dy.double() @ W.double()).float().cpu()) < tol
     assert rel_l2(dW.cpu(), (dy.double().t() @ x.double()).float().cpu()) < 2e-6
     assert rel_l2(db.cpu(), dy.double().sum(0).float().cpu()) < 2e-6
     acc = y.clone()
@@ -139,10 +145,16 @@ def check_against_fixture(model, loss, fixture, tol_norm):
     return g, worst
 
 
-def test_training_step_matches_reference_fixture_and_oracle():
-    """model(images, kp, crop) under autograd -> MPJPE -> backward, blocks without DropPath (the eval-mode fixture): loss, all 191
+@pytest.mark.parametrize("tc", [False, True], ids=["cuda-core-gemms", "tensor-core-gemms"])
+def test_training_step_matches_reference_fixture_and_oracle(tc, monkeypatch):
+    """Both GEMM paths of the step (CAPF_TRAIN_TC): all-fp32 CUDA-core GEMMs hold the reference to 2e-4 per tensor; with the forward /
+    dgrad GEMMs on the tensor cores (split bf16 operands, 2^-16) the bound is 1e-3 -- the sampling-offset gradients amplify a
+    1e-5 change of the sampled positions the most (observed 2.1e-4).
+    model(images, kp, crop) under autograd -> MPJPE -> backward, blocks without DropPath (the eval-mode fixture): loss, all 191
     gradients vs the reference fixture AND element-wise vs the CPU oracle's autograd; then one optimiser step (torch.optim.AdamW
     on our gradients) vs the parameters the reference ended with."""
+    monkeypatch.setattr(train, "USE_TC", tc)
+    tol = 1e-3 if tc else 2e-4
     model, sd, cfg, images, kp2d, crop, gt = training_model("fp32", drop_path_rate=0.0)
     opt = torch.optim.AdamW([{"params": [p for p in model.volume_net.parameters() if p.requires_grad], "lr": LR}], weight_decay=0.1)
     crop_d = crop.to(DEV)
@@ -154,12 +166,12 @@ def test_training_step_matches_reference_fixture_and_oracle():
     loss = torch.mean(torch.norm(pred - gt.to(DEV), dim=3))
     opt.zero_grad()
     loss.backward()
-    g, worst = check_against_fixture(model, loss, "grad_hrnet32_b2_128x96.npz", 2e-4)
+    g, worst = check_against_fixture(model, loss, "grad_hrnet32_b2_128x96.npz", tol)
     assert worst < 5e-2
     oloss, ograds = capf_oracle.volume_net_loss_and_grads(sd, CASE[0], cfg.model.backbone, images, kp2d, crop, gt)
     for n, p in model.volume_net.named_parameters():
         e = rel_l2(p.grad.cpu(), ograds["volume_net." + n])
-        assert e < 2e-4, (n, e)
+        assert e < (5e-3 if tc else 2e-4), (n, e)
     assert all(p.grad is None for p in model.backbone.parameters())
     grads_before = {n: p.grad.detach().cpu().clone() for n, p in model.volume_net.named_parameters()}
     opt.step()
@@ -189,7 +201,7 @@ def test_training_step_with_droppath_matches_reference_train_mode():
     pred = train.forward_train(model, images.to(DEV), kp2d.to(DEV), ref, scales=drop_d)
     loss = torch.mean(torch.norm(pred - gt.to(DEV), dim=3))
     loss.backward()
-    check_against_fixture(model, loss, "grad_train_hrnet32_b2_128x96.npz", 2e-4)
+    check_against_fixture(model, loss, "grad_train_hrnet32_b2_128x96.npz", 1e-3)
     # and the public call draws its own masks on the GPU generator: runs, differentiable, different from the eval-mode output
     for p in model.volume_net.parameters():
         p.grad = None

@@ -48,7 +48,7 @@ def main():
         return loss
 
     def timed(fn, n):
-        for _ in range(2):
+        for _ in range(4):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -60,6 +60,7 @@ def main():
         return e0.elapsed_time(e1) / n, float(l)
 
     ms, loss = timed(step, a.steps)
+    print(f"tensor-core GEMM plans cached: {len(train._TC_PLANS)} (USE_TC={train.USE_TC})", file=sys.stderr)
     if a.profile:
         import collections
         import time
