@@ -18,6 +18,25 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _leave(q):
+    """Flush the result queue and exit the worker process at once: tearing NCCL communicators and captured graphs down at
+    interpreter exit was observed to stall for minutes on the 2-GPU box (the parent then waits for its non-daemon children)."""
+    try:
+        q.close()
+        q.join_thread()
+        torch.cuda.synchronize()
+    finally:
+        os._exit(0)
+
+
+def _join(procs):
+    for p in procs:
+        p.join(30)
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+
+
 def _worker(rank, world, port, q):
     import capf_b200
     import protocol
@@ -51,8 +70,10 @@ def _worker(rank, world, port, q):
                 want = solo.to(dev)(images.to(dev), kp2d.to(dev), crop.clone().to(dev))
             res.append((graph, bool(torch.equal(full_a, want)), bool(torch.equal(full_b, want)), tuple(full_b.shape)))
         q.put((rank, res))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, f"error: {type(e).__name__}: {e}"))
     finally:
-        dist.destroy_process_group()
+        _leave(q)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
@@ -64,9 +85,9 @@ def test_nccl_gather_equals_single_gpu_forward():
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in procs)
-    for p in procs:
-        p.join(60)
+    _join(procs)
     for rank, rows in res:
+        assert not isinstance(rows, str), rows
         for graph, eq_a, eq_b, shape in rows:
             assert eq_a and eq_b and shape == (12, 1, 17, 3), (rank, graph, eq_a, eq_b, shape)
 
@@ -113,8 +134,10 @@ def _ddp_worker(rank, world, port, q):
         for n, p in solo.volume_net.named_parameters():
             worst = max(worst, float((got[n] - p.grad).norm() / p.grad.norm().clamp_min(1e-30)))
         q.put((rank, worst))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, f"error: {type(e).__name__}: {e}"))
     finally:
-        dist.destroy_process_group()
+        _leave(q)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
@@ -126,6 +149,5 @@ def test_training_step_under_ddp_averages_gradients():
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in procs)
-    for p in procs:
-        p.join(60)
-    assert all(w < 1e-5 for _, w in res), res
+    _join(procs)
+    assert all(not isinstance(w, str) and w < 1e-5 for _, w in res), res
