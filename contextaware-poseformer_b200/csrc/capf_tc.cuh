@@ -105,6 +105,15 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar
       "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// shared memory (a dense box in the map's swizzled layout) -> global; out-of-bounds elements of the box are not written
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::"l"((uint64_t)map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -173,6 +182,78 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace ptx
+
+// cta_group::2 (CTA pair) variants, shared by capf_tc2.cu and capf_tc_block64.cu
+namespace ptx2 {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same variable in CTA `rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Same without the release: `mbarrier.arrive.release.cluster` is a cluster-scope fence in front of the arrive and was measured
+// at ~800 clk per call (tools/block_trace.py, 64-channel block).  Enough where what the arrive publishes is already complete
+// when it is issued: TMEM reads after tcgen05.wait::ld, shared-memory writes after fence.proxy.async.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the previously issued MMAs of this thread have completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm_hint(const CUtensorMap* map, uint32_t bar_cluster, uint32_t dst, int c0, int c1, int c2, int c3,
+                                                     uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+      "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+      : "memory");
+}
+// (lo, hi) descriptor words as in ptx::umma_f16_lohi
+__device__ __forceinline__ void umma2_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+}  // namespace ptx2
 
 constexpr int TC_SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA
 
@@ -421,6 +502,14 @@ int tc_block_prepare(const capf_op& op, TcBlockState** out);
 int tc_block_launch(const TcBlockState* s, cudaStream_t st);
 void tc_block_release(TcBlockState* s);
 void tc_block_describe(const TcBlockState* s, char* buf, int cap);
+
+// fused 64-channel BasicBlock on CTA pairs (capf_tc_block64.cu); reached through tc_block_* by channel count
+struct TcBlock64State;
+int tc_block64_supported(const capf_op& op);
+int tc_block64_prepare(const capf_op& op, TcBlock64State** out);
+int tc_block64_launch(const TcBlock64State* s, cudaStream_t st);
+void tc_block64_release(TcBlock64State* s);
+void tc_block64_describe(const TcBlock64State* s, char* buf, int cap);
 
 // 2-CTA (cta_group::2) GEMM for the wide lifter Linears (capf_tc2.cu)
 struct Tc2State;

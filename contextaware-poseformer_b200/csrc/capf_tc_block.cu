@@ -323,6 +323,7 @@ struct TcBlockState {
   CUtensorMap mapX, mapW1, mapW2;
   BlockP p;
   int grid, smem_bytes, dtype;
+  TcBlock64State* b64 = nullptr;   // non-null: a 64-channel block on CTA pairs (capf_tc_block64.cu)
 };
 
 static int block_plan(const capf_op& op, BlockP& p, int& smem_bytes) {
@@ -372,6 +373,7 @@ int tc_block_supported(const capf_op& op) {
   const char* ev = getenv("CAPF_FUSE_BLOCKS");
   if (ev && ev[0] == '0') return 0;
   if (op.kind != CAPF_OP_BASICBLOCK) return 0;
+  if (op.i[3] == 64) return tc_block64_supported(op);
   if (!op.in[0] || !op.in[1] || !op.in[3] || !op.out[0]) return 0;
   if (((uintptr_t)op.in[0] | (uintptr_t)op.in[1] | (uintptr_t)op.in[3] | (uintptr_t)op.out[0]) & 15) return 0;
   BlockP p;
@@ -385,6 +387,12 @@ int tc_block_prepare(const capf_op& op, TcBlockState** out) {
   if (e) return e;
   TcBlockState* s = new (std::nothrow) TcBlockState();
   if (!s) return set_error(CAPF_ERR_ARG, "tc_block_prepare: out of host memory");
+  if (op.i[3] == 64) {
+    e = tc_block64_prepare(op, &s->b64);
+    if (e) { delete s; return e; }
+    *out = s;
+    return CAPF_OK;
+  }
   if (!block_plan(op, s->p, s->smem_bytes)) { delete s; return set_error(CAPF_ERR_UNSUPPORTED, "fused BasicBlock: shape not supported"); }
   BlockP& p = s->p;
   const bool bf16 = op.dtype_in == CAPF_BF16;
@@ -430,12 +438,17 @@ static int block_launch_typed(const TcBlockState* s, cudaStream_t st) {
 }
 
 int tc_block_launch(const TcBlockState* s, cudaStream_t st) {
+  if (s->b64) return tc_block64_launch(s->b64, st);
   return s->dtype == CAPF_F16 ? block_launch_typed<__half>(s, st) : block_launch_typed<__nv_bfloat16>(s, st);
 }
 
-void tc_block_release(TcBlockState* s) { delete s; }
+void tc_block_release(TcBlockState* s) {
+  if (s && s->b64) tc_block64_release(s->b64);
+  delete s;
+}
 
 void tc_block_describe(const TcBlockState* s, char* buf, int cap) {
+  if (s->b64) { tc_block64_describe(s->b64, buf, cap); return; }
   snprintf(buf, cap, "tc_block32_kernel[fused BasicBlock, band %d rows, %d+%d sub-tiles]", s->p.bh, s->p.n1max, s->p.n2max);
 }
 

@@ -477,6 +477,9 @@ def _lanes_enabled():
 # ------------------------------------------------------------------------------------------------------
 FUSED_BLOCK_CHANNELS = 32
 FUSED_BLOCK_MAX_W = 128        # wider bands (input + intermediate, double buffered) do not fit one SM's shared memory
+# 64-channel blocks run on CTA pairs (csrc/capf_tc_block64.cu: each CTA keeps half of the 2 x 72 KB of weights); CAPF_FUSE_BLOCKS64=0
+# keeps the two-kernel form for them
+FUSED_BLOCK_MAX_W_BY_C = {32: FUSED_BLOCK_MAX_W, 64: 64}
 
 
 def _same_buf(a, b):
@@ -484,11 +487,14 @@ def _same_buf(a, b):
 
 
 def fuse_basic_blocks(prog: Program):
-    """conv3x3-BN-ReLU -> conv3x3-BN-(+x)-ReLU pairs (pose_hrnet.py:79-95) with 32 channels, 16-bit tensors and tcgen05
+    """conv3x3-BN-ReLU -> conv3x3-BN-(+x)-ReLU pairs (pose_hrnet.py:79-95) with 32 or 64 channels, 16-bit tensors and tcgen05
     kernels become one CAPF_OP_BASICBLOCK: the intermediate tensor disappears from the program (and from HBM).  Returns the
     number of fused pairs.  CAPF_FUSE_BLOCKS=0 keeps the two-kernel form."""
     if os.environ.get("CAPF_FUSE_BLOCKS", "1") == "0":
         return 0
+    max_w = dict(FUSED_BLOCK_MAX_W_BY_C)
+    if os.environ.get("CAPF_FUSE_BLOCKS64", "1") == "0":
+        max_w.pop(64)
     readers = {}
     for op in prog.ops:
         for b in op.ins:
@@ -502,8 +508,8 @@ def fuse_basic_blocks(prog: Program):
         ok = (b is not None and a.kind == lib.OP_CONV2D and b.kind == lib.OP_CONV2D
               and a.dtype_in == a.dtype_out == b.dtype_in == b.dtype_out and a.dtype_in in ("f16", "bf16")
               and a.i[12] == lib.IMPL_TCGEN05 and b.i[12] == lib.IMPL_TCGEN05
-              and a.i[3] == a.i[4] == b.i[3] == b.i[4] == FUSED_BLOCK_CHANNELS
-              and a.i[5:9] == [3, 3, 1, 1] and b.i[5:9] == [3, 3, 1, 1] and a.i[:3] == b.i[:3] and a.i[2] <= FUSED_BLOCK_MAX_W
+              and a.i[3] == a.i[4] == b.i[3] == b.i[4] and a.i[3] in max_w
+              and a.i[5:9] == [3, 3, 1, 1] and b.i[5:9] == [3, 3, 1, 1] and a.i[:3] == b.i[:3] and a.i[2] <= max_w[a.i[3]]
               and a.i[11] == lib.ACT_RELU and b.i[11] == lib.ACT_RELU
               and a.ins[3] is None and _same_buf(b.ins[0], a.outs[0]) and _same_buf(b.ins[3], a.ins[0])
               and readers.get(a.outs[0].root, 0) == 1 and a.outs[0].role == "act")

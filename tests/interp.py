@@ -186,8 +186,9 @@ class Interp:
         xf = x.float().permute(0, 3, 1, 2)
         w1 = self.t(op.ins[1]).float().reshape(C, 3, 3, C).permute(0, 3, 1, 2).contiguous()
         w2 = self.t(op.ins[3]).float().reshape(C, 3, 3, C).permute(0, 3, 1, 2).contiguous()
-        u = F.relu(F.conv2d(xf, w1, self.t(op.ins[2]).float(), 1, 1)).to(x.dtype).float()
-        y = F.relu(F.conv2d(u, w2, self.t(op.ins[4]).float(), 1, 1) + xf).permute(0, 2, 3, 1)
+        # the same expressions, in the same order, as the two CONV2D ops this op replaces (bias added after the convolution)
+        u = F.relu(F.conv2d(xf, w1, None, 1, 1).permute(0, 2, 3, 1) + self.t(op.ins[2])).to(x.dtype).float().permute(0, 3, 1, 2)
+        y = F.relu(F.conv2d(u, w2, None, 1, 1).permute(0, 2, 3, 1) + self.t(op.ins[4]) + x.float())
         out = self.t(op.outs[0])
         out.copy_(y.reshape(out.shape).to(out.dtype))
 

@@ -1,5 +1,6 @@
-"""Fused 32-channel HRNet BasicBlock (csrc/capf_tc_block.cu, CAPF_OP_BASICBLOCK): the program peephole, its CPU
-interpreter semantics, and on the GPU bit-identity with the two halo-band convolutions it replaces."""
+"""Fused HRNet BasicBlocks (CAPF_OP_BASICBLOCK; csrc/capf_tc_block.cu: 32 channels, one CTA per band; csrc/capf_tc_block64.cu:
+64 channels on CTA pairs): the program peephole, its CPU interpreter semantics, and on the GPU bit-identity with the two
+halo-band convolutions a block replaces."""
 import contextlib
 import ctypes
 import io
@@ -16,35 +17,38 @@ from capf_b200 import lib, program
 from conftest import rel_l2
 
 
-def _programs(B, H, W):
+def _programs(B, H, W, var="CAPF_FUSE_BLOCKS"):
     cfg = capf_b200.make_config("hrnet_32")
     with contextlib.redirect_stdout(io.StringIO()):
         m = capf_b200.CA_PF(cfg, precision="fp16").eval()
     w = protocol.make_weights([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 0)
     shapes = {k: tuple(v.shape) for k, v in w.items()}
     progs = {}
-    old = os.environ.get("CAPF_FUSE_BLOCKS")
+    old = os.environ.get(var)
     try:
         for flag in ("0", "1"):
-            os.environ["CAPF_FUSE_BLOCKS"] = flag
+            os.environ[var] = flag
             progs[flag] = program.build_forward_program("hrnet_32", m.backbone.cfg, m._pf_cfg, shapes, B, H, W, "fp16", use_tc=True)
     finally:
         if old is None:
-            os.environ.pop("CAPF_FUSE_BLOCKS", None)
+            os.environ.pop(var, None)
         else:
-            os.environ["CAPF_FUSE_BLOCKS"] = old
+            os.environ[var] = old
     return progs, w
 
 
-def test_peephole_fuses_exactly_the_32_channel_basic_blocks():
-    """CPU: 32 BasicBlocks of branch 0 (stage2: 4, stage3: 16, stage4: 12) collapse into CAPF_OP_BASICBLOCK, nothing else
-    changes, and the interpreter gives the same network output for both programs."""
+def test_peephole_fuses_exactly_the_32_and_64_channel_basic_blocks():
+    """CPU: the BasicBlocks of branches 0 and 1 (stage2: 4 + 4, stage3: 16 + 16, stage4: 12 + 12) collapse into
+    CAPF_OP_BASICBLOCK, nothing else changes, and the interpreter gives the same network output for both programs."""
     B, H, W = 1, 64, 64
     progs, w = _programs(B, H, W)
     plain, fused = progs["0"], progs["1"]
-    n_fused = sum(op.kind == lib.OP_BASICBLOCK for op in fused.ops)
-    assert n_fused == 32 and len(plain.ops) - len(fused.ops) == 32
-    assert all(op.i[3] == 32 and "branches.0." in op.tag for op in fused.ops if op.kind == lib.OP_BASICBLOCK)
+    blocks = [op for op in fused.ops if op.kind == lib.OP_BASICBLOCK]
+    assert len(blocks) == 64 and len(plain.ops) - len(fused.ops) == 64
+    assert sum(op.i[3] == 32 and "branches.0." in op.tag for op in blocks) == 32
+    assert sum(op.i[3] == 64 and "branches.1." in op.tag for op in blocks) == 32
+    only32 = _programs(B, H, W, "CAPF_FUSE_BLOCKS64")[0]["0"]
+    assert sum(op.kind == lib.OP_BASICBLOCK for op in only32.ops) == 32
     assert abs(plain.flops() - fused.flops()) == 0
     images, kp2d, crop = protocol.make_inputs(B, H, W, 3)
     crop /= torch.tensor([96.0, 128.0])
@@ -96,15 +100,18 @@ def _run_block(x, w1, b1, w2, b2, dt):
     return y
 
 
+_SHAPES = [(32, s) for s in [(3, 64, 64), (2, 64, 48), (5, 13, 9), (1, 5, 127), (2, 96, 72), (40, 64, 64)]] + \
+          [(64, s) for s in [(3, 32, 32), (2, 32, 24), (5, 13, 9), (1, 5, 61), (1, 3, 5), (3, 48, 36), (7, 31, 32), (80, 32, 32)]]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(3, 64, 64), (2, 64, 48), (5, 13, 9), (1, 5, 127), (2, 96, 72), (40, 64, 64)], ids=str)
+@pytest.mark.parametrize("C,shape", _SHAPES, ids=str)
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
-def test_fused_block_equals_two_halo_convs(shape, dt):
+def test_fused_block_equals_two_halo_convs(C, shape, dt):
     """Same MMAs in the same order, same 16-bit rounding of the intermediate: the fused kernel must reproduce the
     two-kernel result bit for bit, and both match an fp32 reference (band tails, ragged last band, tiny and wide images,
-    more bands than SMs)."""
+    more bands than SMs; for the pair kernel also an odd number of bands, i.e. a pair whose second CTA has no band)."""
     N, H, W = shape
-    C = 32
     g = torch.Generator(device="cuda").manual_seed(H * 1000 + W)
     x = torch.randn(N, H, W, C, device="cuda", generator=g).to(dt)
     w1 = (torch.randn(C, 9 * C, device="cuda", generator=g) / (9 * C) ** 0.5).to(dt)
@@ -124,8 +131,9 @@ def test_fused_block_equals_two_halo_convs(shape, dt):
 
 
 @pytest.mark.gpu
-def test_fused_block_at_benchmark_size_is_deterministic():
-    N, H, W, C = 256, 64, 64, 32
+@pytest.mark.parametrize("H,W,C", [(64, 64, 32), (32, 32, 64)], ids=str)
+def test_fused_block_at_benchmark_size_is_deterministic(H, W, C):
+    N = 256
     g = torch.Generator(device="cuda").manual_seed(9)
     x = torch.randn(N, H, W, C, device="cuda", generator=g).half()
     w1 = (torch.randn(C, 9 * C, device="cuda", generator=g) / (9 * C) ** 0.5).half()

@@ -1,4 +1,4 @@
-"""Run the fused BasicBlock op a few times (ncu captures / event timings): python tools/one_block.py N H W [reps]"""
+"""Run the fused BasicBlock op a few times (ncu captures / event timings): python tools/one_block.py N H W [reps] [C]"""
 import os
 import sys
 
@@ -13,7 +13,7 @@ from capf_b200 import lib  # noqa: E402
 
 N, H, W = [int(v) for v in sys.argv[1:4]]
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
-C = 32
+C = int(sys.argv[5]) if len(sys.argv) > 5 else 32
 g = torch.Generator(device="cuda").manual_seed(1)
 x = torch.randn(N, H, W, C, device="cuda", generator=g).half()
 w1 = (torch.randn(C, 9 * C, device="cuda", generator=g) / (9 * C) ** 0.5).half()
