@@ -12,16 +12,16 @@
 // right padding).  conv2's zero padding needs MID to be ZERO outside the image (not conv1 of the padding), which the
 // first epilogue enforces; its one-pixel border of MID costs (bh + 2) / bh more conv1 work.
 //
-// Roles (640 threads): warp 0 TMA producer, warps 1 and 3 MMA issuers (even / odd sub-tiles), warp 2 TMEM allocator,
-// warps 4..19 four 4-warp epilogue groups (two for epilogue 1, two for epilogue 2).  Every 128-pixel sub-tile of a band owns one TMEM accumulator (phase A:
-// slots [0, n1max), phase B: [n1max, n1max + n2max)), so a band needs no accumulator recycling; phase B sub-tile j starts
-// as soon as the MID rows it reads have been written (per-sub-tile "mid ready" barriers), which pipelines conv1 ->
-// epilogue 1 -> conv2 inside a band.  Barriers that are used once per band keep their phase parity in a per-role bit
-// mask (the ragged last band of an image uses fewer sub-tiles).
+// Roles (640 threads): warp 0 TMA producer, warp 1 issues conv1 and warp 3 conv2 (each sub-tile by sub-tile, in order), warp 2
+// TMEM allocator, warps 4..19 four 4-warp epilogue groups (two for epilogue 1, two for epilogue 2, each pair splitting a
+// sub-tile's channels).  Every 128-pixel sub-tile of a band owns one TMEM accumulator (phase A: slots [0, n1max), phase B:
+// [n1max, n1max + n2max)), so a band needs no accumulator recycling; phase B sub-tile j starts as soon as the MID rows it
+// reads have been written (per-sub-tile "mid ready" barriers), which pipelines conv1 -> epilogue 1 -> conv2 inside a band,
+// and conv1 of the next band is issued while conv2 of this one runs.  Barriers that are used once per band keep their phase
+// parity in a per-role bit mask (the ragged last band of an image uses fewer sub-tiles).
 //
-// Measured (tools/block_trace.py, ncu): the issuers block on MMA *issue*, ~64 clk per 128 x 32 x 16 MMA -- the shared-memory
-// port (4 KB of A + 1 KB of B per MMA, plus MID writes / residual reads / TMA writes, ~100 B/clk effective) bounds the kernel;
-// 10-25 % of a band is spent waiting for MID rows.  HBM traffic drops from 2 x 143 MB to 77 MB per block.
+// Bound (tools/microbench/mma_rate.cu): a 128 x 32 x 16 SS-MMA takes 40 clk -- the 4 KB of A it reads from shared memory at
+// 128 B/clk (+ 1 KB of B), not its 16 clk of tensor work; a band is 234 such MMAs.  HBM traffic: 77 MB per block instead of 2 x 143 MB.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -38,10 +38,8 @@ constexpr int BLK_W_BYTES = 9 * BLK_C * BLK_C * 2;   // folded weights of one co
 constexpr int BLK_GROUPS = 4;
 constexpr int BLK_EPI_WARPS = 4 * BLK_GROUPS;
 constexpr int BLK_MAX_ACC = 16;             // 16 x 32 TMEM columns
-constexpr int BLK_ISSUERS = 3;              // MMA issuer warps 1, 2, 3 (sub-tile j is issued by warp 1 + j % 3)
 // header layout (bytes from the 1024-aligned base)
-constexpr int BH_W = 0, BH_XFULL = 8, BH_XEMPTY = 24, BH_MIDFREE = 40, BH_TFULL = 64, BH_TEMPTY = 192, BH_MIDRDY = 320, BH_TMEM = 448;
-constexpr int BH_BIAS = 512;                // bias1[32] f32, bias2[32] f32
+constexpr int BH_W = 0, BH_XFULL = 8, BH_XEMPTY = 24, BH_MIDFREE = 40, BH_C1DONE = 48, BH_TFULL = 64, BH_TEMPTY = 192, BH_MIDRDY = 320, BH_TMEM = 448;
 constexpr int BLK_HEADER = 1024;
 
 struct BlockP {
@@ -69,7 +67,8 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bar_w = base + BH_W, bar_xfull = base + BH_XFULL, bar_xempty = base + BH_XEMPTY, bar_midfree = base + BH_MIDFREE;
+  const uint32_t bar_w = base + BH_W, bar_xfull = base + BH_XFULL, bar_xempty = base + BH_XEMPTY;
+  const uint32_t bar_c1done = base + BH_C1DONE;
   const uint32_t bar_tfull = base + BH_TFULL, bar_tempty = base + BH_TEMPTY, bar_midrdy = base + BH_MIDRDY, tmem_slot = base + BH_TMEM;
   const uint32_t smem_w1 = base + BLK_HEADER, smem_w2 = smem_w1 + BLK_W_BYTES;
   const uint32_t smem_x = smem_w2 + BLK_W_BYTES;
@@ -87,13 +86,13 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     ptx::mbar_init(bar_w, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_xfull + 8 * b, 1);
-      ptx::mbar_init(bar_xempty + 8 * b, BLK_ISSUERS + 8);     // the issuers (phase-A reads) + the 8 epilogue-2 warps (residual reads)
+      ptx::mbar_init(bar_xempty + 8 * b, 1 + 8);                // conv1's commit + the 8 epilogue-2 warps (residuals, in-place results, band store)
+      ptx::mbar_init(bar_c1done + 8 * b, 1);                    // conv1's commit: epilogue 2 may overwrite X[b]
     }
-    ptx::mbar_init(bar_midfree, BLK_ISSUERS);                   // every issuer: phase-B reads of MID complete
     for (int a = 0; a < BLK_MAX_ACC; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);
-      ptx::mbar_init(bar_tempty + 8 * a, a < p.n1max ? 256 : 128);    // phase-A slots: both E1 groups; phase-B slots: one E2 group
-      ptx::mbar_init(bar_midrdy + 8 * a, 256);
+      ptx::mbar_init(bar_tempty + 8 * a, 8);                    // one arrival per epilogue warp of the phase (two groups)
+      ptx::mbar_init(bar_midrdy + 8 * a, 8);
     }
     ptx::fence_mbar_init();
   }
@@ -101,9 +100,7 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
-  if (warp == 3) {                   // constants: folded-BN shifts; the zero pixel in front of MID (image column -1 of its first row)
-    reinterpret_cast<float*>(gen + BH_BIAS)[lane] = p.bias1 ? __ldg(p.bias1 + lane) : 0.f;
-    reinterpret_cast<float*>(gen + BH_BIAS)[32 + lane] = p.bias2 ? __ldg(p.bias2 + lane) : 0.f;
+  if (warp == 3) {                   // the zero pixel in front of MID (image column -1 of its first row)
     if (lane < 4) *reinterpret_cast<uint4*>(gen + (smem_mid - base) + 16 * lane) = make_uint4(0u, 0u, 0u, 0u);
     ptx::fence_proxy_async();
   }
@@ -117,7 +114,6 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const int band0 = (int)(((long long)p.num_bands * blockIdx.x) / gridDim.x);
   const int band1 = (int)(((long long)p.num_bands * (blockIdx.x + 1)) / gridDim.x);
   const int img0 = band0 / p.bands_per_img;
-  const float* const sbias = reinterpret_cast<const float*>(gen + BH_BIAS);
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
@@ -139,34 +135,33 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         if (++bin == p.bands_per_img) { bin = 0; ++img; }
       }
     }
-  } else if (warp >= 1 && warp <= 3) {
-    // ===================================== MMA issuers =======================================
-    // Three issuing warps (warp 2 joins after allocating TMEM).  Measured: 88.6 us per block with three against 88.7 us with
-    // two -- issue rate is NOT what paces this kernel; a band's 234 MMAs take ~11 k clk = 47 clk each against the 40 clk the
-    // shared-memory port needs to read the 5 KB of operands of a 128 x 32 x 16 MMA (tools/block_trace.py): the kernel sits at
-    // ~85 % of its structural bound, the rest is the wait for MID rows.
-    const int me = warp - 1;
+  } else if (warp == 1) {
+    // ===================================== MMA issuer, phase A ===============================
+    // One warp issues conv1 of every band, another (warp 3) conv2, each sub-tile by sub-tile IN ORDER: the tensor pipe
+    // finishes sub-tile j while epilogue 1 of sub-tile j - 1 runs, and this warp already issues conv1 of the next band while
+    // conv2 of the current one is in the pipe.  (Earlier: three issuers taking sub-tiles round-robin -- their MMAs interleave,
+    // all sub-tiles of a phase complete together, and 10-35 % of a band was the wait for MID rows.)  One thread sustains the
+    // pipe's 40 clk per 128 x 32 x 16 MMA (tools/microbench/mma_rate.cu: the shared-memory read of A, 4 KB per MMA, is the bound).
     ptx::mbar_wait(bar_w, 0);
     ptx::tc_fence_after();
     uint32_t tap_off[9];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) tap_off[tap] = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 4u;     // 4 x 16 B per pixel
-    const uint32_t w1_lo = tc_desc_lo(smem_w1, 1u), w2_lo = tc_desc_lo(smem_w2, 1u), mid_lo = tc_desc_lo(smem_mid, 1u);
+    const uint32_t w1_lo = tc_desc_lo(smem_w1, 1u);
     int bin = band0 - img0 * p.bands_per_img;
     uint32_t k = 0, pm = 0;           // pm: phase parity of the per-accumulator barriers (bit a flips when slot a is used)
     for (int band = band0; band < band1; ++band, ++k) {
       const uint32_t buf = k & 1u, ph = (k >> 1) & 1u;
       const int bh_eff = min(p.bh, p.H - bin * p.bh);
-      const int n1 = ((bh_eff + 2) * p.Wp + 127) >> 7, n2 = (bh_eff * p.Wp + 127) >> 7;
-      const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && k < 32 && me < 2;
-      long long tw = 0, w_x = 0, w_ta = 0, w_mid = 0, w_tb = 0;
+      const int n1 = ((bh_eff + 2) * p.Wp + 127) >> 7;
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && k < 32;
+      long long tw = 0, w_x = 0, w_ta = 0;
       if (tr) tw = clock64();
       ptx::mbar_wait(bar_xfull + 8 * buf, ph);
-      if (tr) { w_x = clock64() - tw; p.trace[(me * 8 + 0) * 32 + k] = clock64(); }
+      if (tr) { w_x = clock64() - tw; p.trace[0 * 32 + k] = clock64(); }
       ptx::tc_fence_after();
       const uint32_t x_lo = tc_desc_lo(smem_x + buf * (uint32_t)p.x_bytes, 1u);
-      // ---- phase A: conv1 over bh_eff + 2 rows --------------------------------------------------------
-      for (int j = me; j < n1; j += BLK_ISSUERS) {
+      for (int j = 0; j < n1; ++j) {
         if (tr) tw = clock64();
         ptx::mbar_wait(bar_tempty + 8 * j, ((pm >> j) & 1u) ^ 1u);
         if (tr) w_ta += clock64() - tw;
@@ -183,11 +178,34 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         __syncwarp();
       }
-      if (ptx::elect_one()) ptx::umma_commit(bar_xempty + 8 * buf);      // my phase-A reads of this X buffer
+      if (ptx::elect_one()) {                                            // conv1's reads of X[buf] complete
+        ptx::umma_commit(bar_xempty + 8 * buf);
+        ptx::umma_commit(bar_c1done + 8 * buf);
+      }
       __syncwarp();
-      // ---- phase B: conv2 over bh_eff rows, sub-tile j as soon as the MID pixels it reads exist --------
+      if (tr) { p.trace[1 * 32 + k] = w_x; p.trace[2 * 32 + k] = w_ta; p.trace[5 * 32 + k] = clock64(); }
+      pm ^= (1u << n1) - 1u;
+      if (++bin == p.bands_per_img) bin = 0;
+    }
+  } else if (warp == 3) {
+    // ===================================== MMA issuer, phase B ===============================
+    ptx::mbar_wait(bar_w, 0);
+    ptx::tc_fence_after();
+    uint32_t tap_off[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) tap_off[tap] = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 4u;
+    const uint32_t w2_lo = tc_desc_lo(smem_w2, 1u), mid_lo = tc_desc_lo(smem_mid, 1u);
+    int bin = band0 - img0 * p.bands_per_img;
+    uint32_t k = 0, pm = 0;
+    for (int band = band0; band < band1; ++band, ++k) {
+      const int bh_eff = min(p.bh, p.H - bin * p.bh);
+      const int n1 = ((bh_eff + 2) * p.Wp + 127) >> 7, n2 = (bh_eff * p.Wp + 127) >> 7;
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && k < 32;
+      long long tw = 0, w_mid = 0, w_tb = 0;
+      if (tr) p.trace[8 * 32 + k] = clock64();
+      // conv2 over bh_eff rows, sub-tile j as soon as the MID pixels it reads exist
       int ready_upto = -1;
-      for (int j = me; j < n2; j += BLK_ISSUERS) {
+      for (int j = 0; j < n2; ++j) {
         const int need = min(n1 - 1, (j * 128 + 128 + 2 * p.Wp) >> 7);
         if (tr) tw = clock64();
         while (ready_upto < need) {
@@ -211,25 +229,29 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         __syncwarp();
       }
-      if (ptx::elect_one()) ptx::umma_commit(bar_midfree);               // my phase-B reads of MID
-      __syncwarp();
-      if (tr) {
-        p.trace[(me * 8 + 1) * 32 + k] = w_x; p.trace[(me * 8 + 2) * 32 + k] = w_ta; p.trace[(me * 8 + 3) * 32 + k] = w_mid;
-        p.trace[(me * 8 + 4) * 32 + k] = w_tb; p.trace[(me * 8 + 5) * 32 + k] = clock64();
-      }
+      if (tr) { p.trace[(8 + 3) * 32 + k] = w_mid; p.trace[(8 + 4) * 32 + k] = w_tb; p.trace[(8 + 5) * 32 + k] = clock64(); }
       pm ^= ((1u << n1) - 1u) | (((1u << n2) - 1u) << p.n1max);
       if (++bin == p.bands_per_img) bin = 0;
     }
   } else if (warp >= 4) {
     // ===================================== epilogues =========================================
-    // Epilogue 1 is on the critical path (conv2 cannot start before the MID rows exist), epilogue 2 is not: when all
-    // groups took sub-tiles round-robin, an E1 queued behind two E2s of the previous band and the issuers idled 10-25 %
-    // of a band.  So the roles are dedicated: groups 0 and 1 BOTH work on every phase-A sub-tile (16 of the 32 channels
-    // each: half the latency), groups 2 and 3 alternate on the phase-B sub-tiles.
+    // Groups 0 and 1 both work on every phase-A sub-tile, groups 2 and 3 on every phase-B sub-tile, 16 of the 32 channels
+    // each (half the latency per sub-tile; a thread's 16 folded-BN shifts live in registers).  Epilogue 2 writes its result
+    // over the pixel's residual IN the X band; at the end of the band its 8 warps copy the band out, 4 lanes per pixel and 8
+    // pixels (four 128-byte lines) per instruction -- per-thread stores of a pixel's 64 bytes touch 16 lines per instruction
+    // and the load/store unit, which also carries the MID writes, paced the epilogues (measured on the 64-channel kernel).
     const int q = warp & 3, grp = (warp - 4) >> 2;
-    T* out = reinterpret_cast<T*>(p.out);
-    const uint64_t pol_out = ptx::policy_evict_last();
-    int img = img0, bin = band0 - img0 * p.bands_per_img;
+    const int ch0 = 16 * (grp & 1);                                     // this group's 16 channels = 2 chunks of the pixel row
+    float breg[16];
+    {
+      const float* bsrc = grp < 2 ? p.bias1 : p.bias2;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        const float4 v = bsrc ? __ldg(reinterpret_cast<const float4*>(bsrc + ch0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        breg[e] = v.x; breg[e + 1] = v.y; breg[e + 2] = v.z; breg[e + 3] = v.w;
+      }
+    }
+    int img = img0, bin = band0 - img0 * p.bands_per_img, n2_prev = 0;
     uint32_t k = 0, pm = 0;
     for (int band = band0; band < band1; ++band, ++k) {
       const uint32_t buf = k & 1u;
@@ -239,14 +261,26 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       if (grp < 2) {
         // ---- epilogue 1: relu(acc + b1), zero outside the image, 16-bit, into MID (shifted by one pixel) ----
         uint8_t* const mg = gen + (smem_mid - base);
-        const int ch0 = 16 * grp;                                       // this group's 16 channels = 2 chunks of the pixel row
-        if (k > 0) ptx::mbar_wait(bar_midfree, (k - 1u) & 1u);          // conv2 of the previous band has finished reading MID
+        int freed_upto = -1;
         for (int j = 0; j < n1; ++j) {
+          // MID pixels of sub-tile j were last read by conv2 sub-tiles <= j + 1 of the previous band (in-order issue: the
+          // completion of sub-tile jj implies all earlier ones); their accumulator-full barriers double as "MID rows free"
+          if (k > 0) {
+            const int jj = min(j + 1, n2_prev - 1);
+            if (jj > freed_upto) {
+              const int a = p.n1max + jj;
+              ptx::mbar_wait(bar_tfull + 8 * a, ((pm >> a) & 1u) ^ 1u);      // bit a of pm has flipped since the previous band
+              freed_upto = jj;
+            }
+          }
           ptx::mbar_wait(bar_tfull + 8 * j, (pm >> j) & 1u);
           ptx::tc_fence_after();
           uint32_t a0[16];
           ptx::tmem_ld16(tmem_base + (uint32_t)(j * BLK_C + ch0) + ((uint32_t)(q * 32) << 16), a0);
           ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * j);
           const int mp = j * 128 + q * 32 + lane;
           const int iy = blk_div_wp(mp, p.wp_magic), ix = mp - iy * p.Wp;
           const int yi = y0 - 1 + iy;
@@ -257,56 +291,61 @@ tc_block32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             for (int c = 0; c < 2; ++c) {
               float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = valid ? fmaxf(__uint_as_float(a0[8 * c + e]) + sbias[ch0 + 8 * c + e], 0.f) : 0.f;
+              for (int e = 0; e < 8; ++e) f[e] = valid ? fmaxf(__uint_as_float(a0[8 * c + e]) + breg[8 * c + e], 0.f) : 0.f;
               *reinterpret_cast<uint4*>(mg + blk_chunk(h, (uint32_t)(2 * grp + c))) = pack8<T>(f);
             }
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(bar_tempty + 8 * j);
           ptx::fence_proxy_async();                                     // generic-proxy writes of MID -> tensor-pipe reads
-          ptx::mbar_arrive(bar_midrdy + 8 * j);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_midrdy + 8 * j);
         }
       } else {
-        // ---- epilogue 2: relu(acc + b2 + x), 16-bit, 64 bytes per pixel straight from registers -------------------
+        // ---- epilogue 2: relu(acc + b2 + x) in place over x in the X band; coalesced store of the band ----------------
         uint8_t* const xg = gen + (smem_x - base) + buf * (uint32_t)p.x_bytes;
-        for (int j = grp - 2; j < n2; j += 2) {
+        ptx::mbar_wait(bar_c1done + 8 * buf, (k >> 1) & 1u);           // conv1 of this band no longer reads X[buf]
+        for (int j = 0; j < n2; ++j) {
           const int a = p.n1max + j;
           ptx::mbar_wait(bar_tfull + 8 * a, (pm >> a) & 1u);
           ptx::tc_fence_after();
-          uint32_t a0[16], a1[16];
-          const uint32_t taddr = tmem_base + (uint32_t)(a * BLK_C) + ((uint32_t)(q * 32) << 16);
-          ptx::tmem_ld16(taddr, a0);
-          ptx::tmem_ld16(taddr + 16u, a1);
+          uint32_t a0[16];
+          ptx::tmem_ld16(tmem_base + (uint32_t)(a * BLK_C + ch0) + ((uint32_t)(q * 32) << 16), a0);
           ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * a);
           const int mp = j * 128 + q * 32 + lane;
           const int iy = blk_div_wp(mp, p.wp_magic), ix = mp - iy * p.Wp;
-          const bool live = mp < bh_eff * p.Wp && ix < p.W;
-          const int myoff = live ? (((img * p.H + y0 + iy) * p.W + ix) * BLK_C) : 0;
-          const uint32_t hx = (uint32_t)((iy + 2) * p.Wp + ix + 1);    // this pixel in the X band (2 halo rows, 1 zero column)
-          uint4 o[4];
+          if (mp < bh_eff * p.Wp && ix < p.W) {
+            const uint32_t hx = (uint32_t)((iy + 2) * p.Wp + ix + 1);  // this pixel in the X band (2 halo rows, 1 zero column)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float f[8], r[8];
-            unpack8<T>(*reinterpret_cast<const uint4*>(xg + blk_chunk(hx, (uint32_t)c)), r);
+            for (int c = 0; c < 2; ++c) {
+              uint4* const slot_p = reinterpret_cast<uint4*>(xg + blk_chunk(hx, (uint32_t)(2 * (grp - 2) + c)));
+              float f[8], r[8];
+              unpack8<T>(*slot_p, r);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float acc = __uint_as_float(c < 2 ? a0[8 * c + e] : a1[8 * (c - 2) + e]);
-              f[e] = fmaxf(acc + sbias[32 + 8 * c + e] + r[e], 0.f);
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(a0[8 * c + e]) + breg[8 * c + e] + r[e], 0.f);
+              *slot_p = pack8<T>(f);
             }
-            o[c] = pack8<T>(f);
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(bar_tempty + 8 * a);
-          // four 16-byte stores per thread (they fill the pixel's two 32-byte sectors in L2); no staging tile, no shuffles
-          if (live) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) ptx::st_global_v4_hint(out + myoff + c * 8, o[c], pol_out);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");                  // the band is complete in X[buf]
+        {
+          T* const out = reinterpret_cast<T*>(p.out);
+          const uint64_t pol_out = ptx::policy_evict_last();
+          const int npix = bh_eff * p.W;
+          const int c = lane & 3;
+          for (int px = (warp - 12) * 8 + (lane >> 2); px < npix; px += 64) {
+            const int oy = px / p.W, ox = px - oy * p.W;
+            const uint32_t hx = (uint32_t)((oy + 2) * p.Wp + ox + 1);
+            const uint4 v = *reinterpret_cast<const uint4*>(xg + blk_chunk(hx, (uint32_t)c));
+            ptx::st_global_v4_hint(out + ((size_t)((img * p.H + y0 + oy) * p.W + ox)) * BLK_C + c * 8, v, pol_out);
           }
         }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_xempty + 8 * buf);          // this warp no longer reads X[buf] (residuals)
+        if (lane == 0) ptx::mbar_arrive(bar_xempty + 8 * buf);          // this warp no longer reads X[buf]
       }
       pm ^= ((1u << n1) - 1u) | (((1u << n2) - 1u) << p.n1max);
+      n2_prev = n2;
       if (++bin == p.bands_per_img) { bin = 0; ++img; }
     }
   }

@@ -18,7 +18,8 @@
 //   w          leader: the weight halves of BOTH CTAs have landed (the peer's TMA completes on the leader's barrier)
 //   xfull[b]   leader: X[b] of both CTAs landed;   xempty[b]  both: the issuers' multicast commits + the CTA's own 8 epilogue-2 warps
 //   tfull[a]   both (multicast commit);            tempty[a]  leader: the epilogue warps of both CTAs (the peer's arrive remotely)
-//   midrdy[a]  leader: epilogue-1 warps of both CTAs wrote the MID pixels of sub-tile a;   midfree  both (multicast commit)
+//   midrdy[a]  leader: epilogue-1 warps of both CTAs wrote the MID pixels of sub-tile a (MID rows are released to the next band's
+//              epilogue 1 by the tfull barriers of the conv2 sub-tiles that read them);   c1done[b]  both: conv1 finished with X[b]
 // Shared memory: header | X0 | X1 | MID | W1 | W2.  The shifted windows of a band's last sub-tile read past the band (rows that
 // are dropped); the order of the buffers makes those reads land in the next buffer of the same allocation.
 #include <algorithm>
@@ -87,7 +88,7 @@ tc_block64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bar_w = base + B6_W, bar_xfull = base + B6_XFULL, bar_xempty = base + B6_XEMPTY, bar_midfree = base + B6_MIDFREE;
+  const uint32_t bar_w = base + B6_W, bar_xfull = base + B6_XFULL, bar_xempty = base + B6_XEMPTY;
   const uint32_t bar_c1done = base + B6_C1DONE;
   const uint32_t bar_tfull = base + B6_TFULL, bar_tempty = base + B6_TEMPTY, bar_midrdy = base + B6_MIDRDY, tmem_slot = base + B6_TMEM;
   const uint32_t smem_x = base + B64_HEADER;
@@ -111,7 +112,6 @@ tc_block64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       ptx::mbar_init(bar_xempty + 8 * b, 1 + 8);                // conv1's multicast commit + this CTA's 8 epilogue-2 warps (residuals, in-place results, band store)
       ptx::mbar_init(bar_c1done + 8 * b, 1);                    // conv1's multicast commit: epilogue 2 may overwrite X[b]
     }
-    ptx::mbar_init(bar_midfree, 1);                              // conv2's multicast commit: phase-B reads of MID complete
     for (int a = 0; a < B64_MAX_ACC; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);
       ptx::mbar_init(bar_tempty + 8 * a, 16);                    // one arrival per epilogue warp of the phase, both CTAs: 2 x 8
@@ -264,8 +264,6 @@ tc_block64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           ++ready_upto;
           ptx::mbar_wait(bar_midrdy + 8 * ready_upto, (pm >> ready_upto) & 1u);
         }
-        if (ptx::elect_one()) ptx2::umma2_commit_mc(bar_midfree);               // conv2's reads of MID (both CTAs)
-        __syncwarp();
         if (tr) {
           p.trace[(8 + 3) * 32 + k] = w_mid; p.trace[(8 + 4) * 32 + k] = w_tb; p.trace[(8 + 5) * 32 + k] = clock64(); p.trace[(8 + 6) * 32 + k] = w_is;
         }
@@ -293,6 +291,7 @@ tc_block64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         breg[e] = v.x; breg[e + 1] = v.y; breg[e + 2] = v.z; breg[e + 3] = v.w;
       }
     }
+    int n2_prev = 0;
     uint32_t k = 0, pm = 0;
     for (int slot = slot0; slot < slot1; ++slot, ++k) {
       const uint32_t buf = k & 1u;
@@ -303,10 +302,20 @@ tc_block64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       if (grp < 2) {
         // ---- epilogue 1: relu(acc + b1), zero outside the image, 16-bit, into MID (shifted by one pixel) ----
         uint8_t* const mg = gen + (smem_mid - base);
-        if (k > 0) ptx::mbar_wait(bar_midfree, (k - 1u) & 1u);          // conv2 of the previous band has finished reading MID
         const bool tre = p.trace != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+        int freed_upto = -1;
         for (int j = 0; j < n1; ++j) {
           const int ev = (int)k * n1 + j;
+          // MID pixels of sub-tile j were last read by conv2 sub-tiles <= j + 1 of the previous band (in-order issue: the
+          // completion of sub-tile jj implies all earlier ones); their accumulator-full barriers double as "MID rows free"
+          if (k > 0) {
+            const int jj = min(j + 1, n2_prev - 1);
+            if (jj > freed_upto) {
+              const int a = p.n1max + jj;
+              ptx::mbar_wait(bar_tfull + 8 * a, ((pm >> a) & 1u) ^ 1u);      // bit a of pm has flipped since the previous band
+              freed_upto = jj;
+            }
+          }
           if (tre && ev < 32) p.trace[16 * 32 + ev] = clock64();
           ptx::mbar_wait(bar_tfull + 8 * j, (pm >> j) & 1u);
           ptx::tc_fence_after();
@@ -403,6 +412,7 @@ tc_block64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         if (lane == 0) ptx::mbar_arrive(bar_xempty + 8 * buf);          // this warp no longer reads X[buf]
       }
       pm ^= ((1u << n1) - 1u) | (((1u << n2) - 1u) << p.n1max);
+      n2_prev = n2;
     }
   }
 
