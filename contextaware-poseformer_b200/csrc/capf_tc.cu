@@ -450,6 +450,7 @@ struct TcConvState {
   TcHalo128State* h128 = nullptr; // non-null: halo band + streamed weights (C = Cout = 128)
   Tc2State* two = nullptr;       // non-null: the op runs on the 2-CTA GEMM kernel (capf_tc2.cu)
   TcBlockState* blk = nullptr;   // non-null: a fused BasicBlock op (capf_tc_block.cu)
+  TcChainState* chain = nullptr; // non-null: a CAPF_OP_EXPAND_REDUCE op (capf_tc_chain.cu)
   CUtensorMap mapA, mapB, mapA2;
   TcP p;
   int grid;
@@ -540,6 +541,16 @@ int tc_blockop_prepare(const capf_op& op, TcConvState** out) {
   TcConvState* s = new (std::nothrow) TcConvState();
   if (!s) return set_error(CAPF_ERR_ARG, "tc_blockop_prepare: out of host memory");
   int e = tc_block_prepare(op, &s->blk);
+  if (e) { delete s; return e; }
+  *out = s;
+  return CAPF_OK;
+}
+
+int tc_chainop_prepare(const capf_op& op, TcConvState** out) {
+  *out = nullptr;
+  TcConvState* s = new (std::nothrow) TcConvState();
+  if (!s) return set_error(CAPF_ERR_ARG, "tc_chainop_prepare: out of host memory");
+  int e = tc_chain_prepare(op, &s->chain);
   if (e) { delete s; return e; }
   *out = s;
   return CAPF_OK;
@@ -756,6 +767,7 @@ static int tc_launch_typed(const TcConvState* s, cudaStream_t st) {
 int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
   if (!s) return set_error(CAPF_ERR_ARG, "tc conv: op was not prepared");
   if (s->blk) return tc_block_launch(s->blk, st);
+  if (s->chain) return tc_chain_launch(s->chain, st);
   if (s->two) return tc2_launch(s->two, st);
   if (s->halo) return tc_halo_launch(s->halo, st);
   if (s->h128) return tc_halo128_launch(s->h128, st);
@@ -770,6 +782,7 @@ int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
 void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
   if (!s) { snprintf(buf, cap, "?"); return; }
   if (s->blk) { tc_block_describe(s->blk, buf, cap); return; }
+  if (s->chain) { tc_chain_describe(s->chain, buf, cap); return; }
   if (s->two) { tc2_describe(s->two, buf, cap); return; }
   if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
   if (s->h128) { tc_halo128_describe(s->h128, buf, cap); return; }
@@ -779,6 +792,7 @@ void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
 
 void tc_conv_release(TcConvState* s) {
   if (s && s->blk) tc_block_release(s->blk);
+  if (s && s->chain) tc_chain_release(s->chain);
   if (s && s->two) tc2_release(s->two);
   if (s && s->halo) tc_halo_release(s->halo);
   if (s && s->h128) tc_halo128_release(s->h128);

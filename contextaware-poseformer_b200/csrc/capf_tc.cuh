@@ -111,6 +111,11 @@ __device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap* map, uint32
                "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"((uint64_t)map), "r"(src), "r"(c0),
+               "r"(c1), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -510,6 +515,14 @@ int tc_block64_prepare(const capf_op& op, TcBlock64State** out);
 int tc_block64_launch(const TcBlock64State* s, cudaStream_t st);
 void tc_block64_release(TcBlock64State* s);
 void tc_block64_describe(const TcBlock64State* s, char* buf, int cap);
+
+// Bottleneck conv3 + residual -> conv1 of the next block (capf_tc_chain.cu, CAPF_OP_EXPAND_REDUCE)
+struct TcChainState;
+int tc_chain_supported(const capf_op& op);
+int tc_chain_prepare(const capf_op& op, TcChainState** out);
+int tc_chain_launch(const TcChainState* s, cudaStream_t st);
+void tc_chain_release(TcChainState* s);
+void tc_chain_describe(const TcChainState* s, char* buf, int cap);
 
 // 2-CTA (cta_group::2) GEMM for the wide lifter Linears (capf_tc2.cu)
 struct Tc2State;

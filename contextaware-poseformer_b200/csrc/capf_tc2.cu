@@ -14,7 +14,7 @@
 //              complete_tx on the leader's barrier (cp.async.bulk.tensor...cta_group::2 with a mapa'd mbarrier address)
 //   empty[s]   both CTAs: tcgen05.commit.cta_group::2...multicast::cluster from the leader's MMA thread
 //   tfull[a]   both CTAs: same multicast commit after the last stage of a tile
-//   tempty[a]  leader only: 2 x 256 arrivals -- the epilogue threads of both CTAs (the peer's arrive remotely)
+//   tempty[a]  leader only: 2 x 8 arrivals -- the epilogue warps of both CTAs (the peer's arrive remotely)
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -75,7 +75,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);
-      ptx::mbar_init(bar_tempty + 8 * a, 2 * (T2_THREADS - 128));
+      ptx::mbar_init(bar_tempty + 8 * a, 2 * 8);                 // one arrival per epilogue warp, both CTAs
     }
     ptx::fence_mbar_init();
   }
@@ -225,11 +225,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (two) epi16<TO, MODE>(a1, sbias + (c0 - cbeg) + g + 16, floor_v, stg_ptr + buf * T2_STG_BYTES + lane * 128, (uint32_t)((g / 16 + 1) * CPG), (uint32_t)lane & 7u);
           }
         }
-        if (s + 1 == nslabs) {                        // accumulator read completely: free it at the leader (both CTAs arrive there)
-          ptx::tc_fence_before();
-          ptx2::mbar_arrive_cluster(tempty_leader0 + 8 * acc);
-        }
+        ptx::tc_fence_before();
         __syncwarp();
+        // accumulator read completely (tcgen05.wait::ld above): free it at the leader, one relaxed arrival per warp -- a
+        // release.cluster arrive per thread cost ~800 clk in front of the slab's stores (measured in capf_tc_block64.cu)
+        if (s + 1 == nslabs && lane == 0) ptx2::mbar_arrive_cluster_relaxed(tempty_leader0 + 8 * acc);
         const int chs = (ncol * (int)sizeof(TO)) >> 4;
         uint8_t* gbase = reinterpret_cast<uint8_t*>(out + (size_t)m_w0 * p.Cout + ncol0 + c0);
         if (chs == 8) {
@@ -250,7 +250,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
       if (nslabs == 0) {
         ptx::tc_fence_before();
-        ptx2::mbar_arrive_cluster(tempty_leader0 + 8 * acc);
+        __syncwarp();
+        if (lane == 0) ptx2::mbar_arrive_cluster_relaxed(tempty_leader0 + 8 * acc);
       }
       if (tr && warp == 4 && lane == 0 && tile - t0 < 16) p.trace[193 + 2 * (tile - t0)] = clock64();
       if (++acc == (uint32_t)p.nacc) { acc = 0; acc_phase ^= 1u; }

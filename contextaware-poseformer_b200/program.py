@@ -349,6 +349,7 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
     if pb.use_tc:
         fuse_basic_blocks(prog)
         fuse_downsample(prog)
+        fuse_expand_reduce(prog)
         chunk_prefix(prog)
     prog.n_backbone_ops = len(prog.ops)
     if backbone_only:
@@ -585,6 +586,48 @@ def fuse_downsample(prog: Program):
 
 
 # ------------------------------------------------------------------------------------------------------
+# peephole: Bottleneck conv3 (+ residual) followed by conv1 of the next Bottleneck -> one kernel
+# ------------------------------------------------------------------------------------------------------
+def fuse_expand_reduce(prog: Program):
+    """Inside a stack of Bottlenecks (pose_hrnet.py:421-427 layer1; networks/resnet.py layer1) block i ends with
+    y = relu(bn3(conv3(t)) + x) -- 1x1, 64 -> 256 -- and block i + 1 starts with relu(bn1(conv1(y))) -- 1x1, 256 -> 64: two per-pixel
+    GEMMs.  As separate ops the second one is nothing but a read of the 256-channel tensor the first one just wrote (537 MB at
+    bs = 256).  Both become ONE CAPF_OP_EXPAND_REDUCE (csrc/capf_tc_chain.cu): y is written once (it is block i + 1's residual) and
+    never read back for conv1.  Bit-identical results.  CAPF_FUSE_CHAIN=0 keeps the two-op form."""
+    if os.environ.get("CAPF_FUSE_CHAIN", "1") == "0" or int(os.environ.get("CAPF_CHUNK", "0") or 0) > 0:
+        return 0
+    ops = prog.ops
+
+    def plain_1x1(op, cin, cout, act):
+        return (op.kind == lib.OP_CONV2D and op.i[12] == lib.IMPL_TCGEN05 and op.i[5:9] == [1, 1, 1, 0] and op.i[3] == cin and op.i[4] == cout
+                and op.i[11] == act and not any(op.i[13:]) and all(x is None for x in op.ins[4:]))
+
+    out, k, fused = [], 0, 0
+    while k < len(ops):
+        a = ops[k]
+        b = ops[k + 1] if k + 1 < len(ops) else None
+        ok = (b is not None and plain_1x1(a, 64, 256, lib.ACT_RELU) and plain_1x1(b, 256, 64, lib.ACT_RELU)
+              and a.dtype_in == a.dtype_out == b.dtype_in == b.dtype_out and a.dtype_in in ("f16", "bf16")
+              and isinstance(a.ins[3], Buf) and b.ins[3] is None and _same_buf(b.ins[0], a.outs[0]) and a.i[0:3] == b.i[0:3]
+              and a.i[9:11] == a.i[1:3] and getattr(a, "lane", 0) == getattr(b, "lane", 0))
+        if ok:
+            rows = a.i[0] * a.i[1] * a.i[2]
+            wbytes = sum(int(np.prod(w.shape)) * _ITEMSIZE[w.dtype] for w in (a.ins[1], b.ins[1]))
+            op = Op(lib.OP_EXPAND_REDUCE, a.dtype_in, a.dtype_out, [rows, 64, 256, 64], [],
+                    [a.ins[0], a.ins[1], a.ins[2], a.ins[3], b.ins[1], b.ins[2]], [a.outs[0], b.outs[0]],
+                    tag=a.tag + "+" + ".".join(b.tag.rsplit(".", 2)[-2:]), flops=a.flops + b.flops,
+                    nbytes=a.ins[0].nbytes + a.ins[3].nbytes + a.outs[0].nbytes + b.outs[0].nbytes + wbytes)
+            out.append(op)
+            fused += 1
+            k += 2
+        else:
+            out.append(a)
+            k += 1
+    prog.ops[:] = out
+    return fused
+
+
+# ------------------------------------------------------------------------------------------------------
 # batch-chunked schedule of the high-resolution prefix
 # ------------------------------------------------------------------------------------------------------
 _PREFIX_RE = re.compile(r"^backbone\.(conv1|conv2|layer1\.|transition1\.|resnet\.conv1|resnet\.layer1\.)")
@@ -660,6 +703,11 @@ _LANE_RE = re.compile(r"\.stage\d+\.\d+\.branches\.(\d+)\.|\.stage\d+\.\d+\.fuse
                       r"|\.refine_net\.cascade\.(\d+)\.")
 
 
+# the per-level Linears of the lifter (pose_dformer.py:190-193 feat_embed, :108-110 embed_proj) read and write disjoint slabs
+# of the token stream: level l on lane l, four ~2 us GEMMs side by side instead of in a row
+_LIFTER_LANE_RE = re.compile(r"\.feat_embed\.(\d+)$|\.embed_proj\.(\d+)$")
+
+
 def assign_lanes(prog: Program, enable: bool = True):
     """Lane (stream) of every op.  Branch b of an HRNet stage -- its BasicBlocks, the fuse-layer convolutions that read
     it, the transition that creates it and the fuse-sum that produces its next input -- runs on lane b; everything else
@@ -676,7 +724,7 @@ def assign_lanes(prog: Program, enable: bool = True):
         if getattr(op, "pin_lane0", False):
             pass
         elif op.kind == lib.OP_CONV2D:
-            m = _LANE_RE.search(op.tag)
+            m = _LANE_RE.search(op.tag) or _LIFTER_LANE_RE.search(op.tag)
             if m:
                 lane = int(next(g for g in m.groups() if g is not None))
         elif op.kind == lib.OP_BILINEAR:
@@ -704,16 +752,24 @@ def op_clocks(prog: Program):
     vc = [None] * n
     waits = [[] for _ in range(n)]
     last_on_lane = [-1] * MAX_LANES
-    writers, readers = {}, {}       # root buffer -> op indices
+    writers, readers = {}, {}       # root buffer -> [(op index, first byte, end byte)]: views of one root conflict only where they overlap
+
+    def span(b):
+        lo = b.root_offset * _ITEMSIZE[b.dtype]
+        return b.root, lo, lo + b.nbytes
+
+    def hits(table, r, lo, hi):
+        return [d for d, a, z in table.get(r, ()) if a < hi and lo < z]
+
     for k, op in enumerate(prog.ops):
         deps = set()
-        ins = [b.root for b in op.ins if isinstance(b, Buf)]
-        outs = [b.root for b in op.outs if isinstance(b, Buf)]
-        for r in ins:
-            deps.update(writers.get(r, ()))                 # read after write
-        for r in outs:
-            deps.update(writers.get(r, ()))                 # write after write
-            deps.update(readers.get(r, ()))                 # write after read
+        ins = [span(b) for b in op.ins if isinstance(b, Buf)]
+        outs = [span(b) for b in op.outs if isinstance(b, Buf)]
+        for r, lo, hi in ins:
+            deps.update(hits(writers, r, lo, hi))           # read after write
+        for r, lo, hi in outs:
+            deps.update(hits(writers, r, lo, hi))           # write after write
+            deps.update(hits(readers, r, lo, hi))           # write after read
         prev = last_on_lane[op.lane]
         clock = list(vc[prev]) if prev >= 0 else [-1] * MAX_LANES
         need = [-1] * MAX_LANES
@@ -727,10 +783,10 @@ def op_clocks(prog: Program):
         clock[op.lane] = k
         vc[k] = clock
         last_on_lane[op.lane] = k
-        for r in ins:
-            readers.setdefault(r, []).append(k)
-        for r in outs:
-            writers.setdefault(r, []).append(k)
+        for r, lo, hi in ins:
+            readers.setdefault(r, []).append((k, lo, hi))
+        for r, lo, hi in outs:
+            writers.setdefault(r, []).append((k, lo, hi))
     return vc, waits
 
 
@@ -739,7 +795,7 @@ def op_clocks(prog: Program):
 # ------------------------------------------------------------------------------------------------------
 def _dying_residual(op, k, last_use, keep_alive):
     """The root buffer of op's residual operand if this conv / Linear is its last reader and it may be overwritten."""
-    if op.kind != lib.OP_CONV2D or len(op.ins) < 4 or not isinstance(op.ins[3], Buf) or not op.outs:
+    if op.kind not in (lib.OP_CONV2D, lib.OP_EXPAND_REDUCE) or len(op.ins) < 4 or not isinstance(op.ins[3], Buf) or not op.outs:
         return None
     res = op.ins[3]
     root = res.root

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 10
+#define CAPF_ABI_VERSION 11
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -73,7 +73,8 @@ typedef enum capf_op_kind {
   CAPF_OP_DEFORM_BWD = 23,
   CAPF_OP_ROWS_AXPY = 24,
   CAPF_OP_JOINT_TO_LEVELS = 25,
-  CAPF_OP_ADAMW = 26
+  CAPF_OP_ADAMW = 26,
+  CAPF_OP_EXPAND_REDUCE = 27
 } capf_op_kind;
 
 /*
@@ -103,6 +104,16 @@ typedef enum capf_op_kind {
  *     in[2]=bias[Cout] f32 (folded BN shift or Linear bias; may be NULL)
  *     in[3]=residual [N,Ho,Wo,Cout] dtype_out or NULL (may alias out[0])
  *     out[0]=y [N,Ho,Wo,Cout] dtype_out.    y = relu?( gelu?(conv+bias) + residual )
+ *
+ * CAPF_OP_EXPAND_REDUCE -- the tail of one Bottleneck and the head of the next (pose_hrnet.py:116-136 inside layer1 :421-427; the
+ *                    same shapes in networks/resnet.py layer1) as one kernel over pixels (rows):
+ *                        y = relu(t . W3^T + b3 + x)     conv3 (1x1, K1 -> N1) + bn3 + residual + ReLU of block i
+ *                        u = relu(y . W1^T + b1)         conv1 (1x1, N1 -> N2) + bn1 + ReLU of block i + 1
+ *                    y never makes the HBM round trip between the two GEMMs (it is still written once: it is the next residual).
+ *                    Results are bit-identical to the two CAPF_OP_CONV2D ops (program.fuse_expand_reduce emits it for them).
+ *     i[0]=rows (N*H*W)  i[1]=K1 (64)  i[2]=N1 (256)  i[3]=N2 (64)          16-bit dtypes, dtype_in == dtype_out
+ *     in[0]=t [rows][K1]  in[1]=W3 [N1][K1]  in[2]=b3 [N1] f32 or NULL  in[3]=x [rows][N1]  in[4]=W1 [N2][N1]  in[5]=b1 [N2] f32 or NULL
+ *     out[0]=y [rows][N1] (may alias in[3])   out[1]=u [rows][N2]
  *
  * CAPF_OP_FUSE_SUM -- HighResolutionModule fuse  y_i = ReLU(sum_j f_ij(x_j))  (pose_hrnet.py:294-301) with the
  *                    nn.Upsample(mode='nearest') of the j>i terms (:244) applied on the fly.

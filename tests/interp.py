@@ -192,6 +192,24 @@ class Interp:
         out = self.t(op.outs[0])
         out.copy_(y.reshape(out.shape).to(out.dtype))
 
+    def _op27(self, op):  # EXPAND_REDUCE: y = relu(t W3^T + b3 + x); u = relu(y W1^T + b1), the expressions of the two CONV2D ops it replaces
+        rows, k1, n1, n2 = op.i[:4]
+        t = self.t(op.ins[0]).reshape(rows, k1).float()
+        x = self.t(op.ins[3]).reshape(rows, n1).float()
+        w3 = self.t(op.ins[1]).float().reshape(n1, k1)
+        w1 = self.t(op.ins[4]).float().reshape(n2, n1)
+        y = F.conv2d(t.t().reshape(1, k1, rows, 1), w3.reshape(n1, k1, 1, 1)).reshape(n1, rows).t()
+        if op.ins[2] is not None:
+            y = y + self.t(op.ins[2])
+        y = F.relu(y + x)
+        yo = self.t(op.outs[0])
+        yo.copy_(y.reshape(yo.shape).to(yo.dtype))
+        u = F.conv2d(yo.reshape(rows, n1).float().t().reshape(1, n1, rows, 1), w1.reshape(n2, n1, 1, 1)).reshape(n2, rows).t()
+        if op.ins[5] is not None:
+            u = u + self.t(op.ins[5])
+        uo = self.t(op.outs[1])
+        uo.copy_(F.relu(u).reshape(uo.shape).to(uo.dtype))
+
     def _op12(self, op):  # CAST
         out = self.t(op.outs[0])
         if len(op.i) > 2 and op.i[2] > 0:         # split planes: rows of C fp32 -> [hi (C) | lo (C)] bf16

@@ -181,16 +181,27 @@ def test_lane_parallel_memory_plan_is_race_free():
                 assert vc[first_b][prog.ops[u].lane] >= u, (a.name, b.name, u, first_b)
             shared += 1
     assert shared > 50
-    # read-after-write across lanes is always ordered
-    writer = {}
+    # read-after-write / write-after-write / write-after-read across lanes are always ordered, byte range by byte range (the
+    # per-level Linears of the lifter write disjoint slabs of one token buffer from four lanes)
+    def span(b):
+        lo = b.root_offset * program._ITEMSIZE[b.dtype]
+        return b.root, lo, lo + b.nbytes
+
+    writes, reads = [], []
     for k, op in enumerate(prog.ops):
-        for b in op.ins:
-            if isinstance(b, program.Buf) and b.root in writer:
-                w = writer[b.root]
-                assert vc[k][prog.ops[w].lane] >= w
-        for b in op.outs:
-            if isinstance(b, program.Buf):
-                writer[b.root] = k
+        ins = [span(b) for b in op.ins if isinstance(b, program.Buf)]
+        outs = [span(b) for b in op.outs if isinstance(b, program.Buf)]
+        for r, lo, hi in ins:
+            for w, wr, a, z in writes:
+                if wr is r and a < hi and lo < z:
+                    assert vc[k][prog.ops[w].lane] >= w, (k, w)
+        for r, lo, hi in outs:
+            for w, wr, a, z in writes + reads:
+                if wr is r and a < hi and lo < z and w != k:
+                    assert vc[k][prog.ops[w].lane] >= w, (k, w)
+        reads += [(k, r, lo, hi) for r, lo, hi in ins]
+        writes += [(k, r, lo, hi) for r, lo, hi in outs]
+    assert any(op.lane == 3 and "embed_proj.3" in op.tag for op in prog.ops)
 
 
 def test_state_fingerprint_and_plan_cache_hygiene():
