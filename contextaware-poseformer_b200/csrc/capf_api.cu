@@ -177,6 +177,10 @@ int capf_plan_create(const capf_op* ops, int n_ops, int device, capf_plan** out_
         return e;
       }
     }
+    if (op.kind == CAPF_OP_CONV2D && op.i[12] != CAPF_IMPL_TCGEN05 && op.i[20] != 0) {
+      capf_plan_destroy(pl);
+      return set_errorf(CAPF_ERR_UNSUPPORTED, "op %d: output segments (i[20]) need the tcgen05 kernel", k);
+    }
     if (op.kind == CAPF_OP_CONV2D && op.i[12] == CAPF_IMPL_TCGEN05) {
       if (!tc_conv_supported(op)) {
         capf_plan_destroy(pl);

@@ -64,6 +64,12 @@ struct TcP {
   const float* bias;
   const void* res;
   void* out;
+  // output segments (CONV2D i[20] > 1, kernel MODE bit 2): columns [seg_beg[s], seg_beg[s] + seg_c[s]) of the GEMM go to the dense
+  // tensor seg_out[s] [rows][seg_c[s]]; unused entries have seg_beg = INT_MAX.  Bit s of seg_noact: no ReLU on segment s.
+  int nseg;
+  int seg_beg[4], seg_c[4];
+  void* seg_out[4];
+  uint32_t seg_noact;
   long long* trace;         // optional (debug, op.in[4]): clock64 timeline of CTA 0, see tools/gemm_trace.py
 };
 
@@ -101,7 +107,7 @@ __device__ __forceinline__ void tile_range(const TcP& p, int& t0, int& t1) {
 // =======================================================================================================
 // the kernel
 // =======================================================================================================
-// MODE: bit 0 = residual add, bit 1 = GELU (compile-time epilogue variants)
+// MODE: bit 0 = residual add, bit 1 = GELU, bit 2 = output segments (compile-time epilogue variants)
 template <typename TO, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapA2, const TcP p) {
@@ -283,6 +289,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // variants (MODE), the bias slice of the column tile sits in shared memory before the accumulator is waited for,
     // and the rows-mode store addresses are affine (no shuffles, no 64-bit multiplies in the loop).
     constexpr bool HAS_RES = (MODE & 1) != 0;
+    constexpr bool SEG = (MODE & 4) != 0;
+    constexpr int EMODE = MODE & 3;
     constexpr int SW = 128 / (int)sizeof(TO);          // columns per slab
     constexpr int CPG = 16 * (int)sizeof(TO) / 16;     // 16-byte chunks per 16 columns
     const int q = warp & 3;
@@ -299,6 +307,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int by = (row / p.bw) % p.bh, bi = row / (p.bw * p.bh);
     const uint32_t tcol0 = (uint32_t)(sub * p.BN) + ((uint32_t)(q * 32) << 16);
     const float floor_v = p.act == CAPF_ACT_RELU ? 0.f : -__int_as_float(0x7f800000);
+    // segment of GEMM column `col` (boundaries are multiples of 16 columns, so a 16-column group / a 16-byte chunk has one)
+    auto seg_of = [&](int col) -> int { return (col >= p.seg_beg[1] ? 1 : 0) + (col >= p.seg_beg[2] ? 1 : 0) + (col >= p.seg_beg[3] ? 1 : 0); };
+    auto seg_floor = [&](int col) -> float { return ((p.seg_noact >> seg_of(col)) & 1u) ? -__int_as_float(0x7f800000) : floor_v; };
     uint8_t* const stg_ptr = smem_raw + (stage0 - raw) + p.stg_off + (uint32_t)(warp - 4) * (uint32_t)(p.stg_bufs * TC_STG_BYTES);
     const uint32_t stg = stage0 + p.stg_off + (uint32_t)(warp - 4) * (uint32_t)(p.stg_bufs * TC_STG_BYTES);
     float* const sbias = reinterpret_cast<float*>(smem_raw + (stage0 - raw) + p.bias_off) + (warp - 4) * 256;
@@ -376,8 +387,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               __syncwarp();
             }
             CAPF_STAMP();
-            epi16<TO, MODE>(a0, sbias + (c0 - cbeg) + g, floor_v, stg_ptr + buf * TC_STG_BYTES + lane * 128, (uint32_t)((g / 16) * CPG), (uint32_t)lane & 7u);
-            if (two) epi16<TO, MODE>(a1, sbias + (c0 - cbeg) + g + 16, floor_v, stg_ptr + buf * TC_STG_BYTES + lane * 128, (uint32_t)((g / 16 + 1) * CPG), (uint32_t)lane & 7u);
+            float fl0 = floor_v, fl1 = floor_v;
+            if constexpr (SEG) { fl0 = seg_floor(ncol0 + c0 + g); fl1 = seg_floor(ncol0 + c0 + g + 16); }
+            epi16<TO, EMODE>(a0, sbias + (c0 - cbeg) + g, fl0, stg_ptr + buf * TC_STG_BYTES + lane * 128, (uint32_t)((g / 16) * CPG), (uint32_t)lane & 7u);
+            if (two) epi16<TO, EMODE>(a1, sbias + (c0 - cbeg) + g + 16, fl1, stg_ptr + buf * TC_STG_BYTES + lane * 128, (uint32_t)((g / 16 + 1) * CPG), (uint32_t)lane & 7u);
             CAPF_STAMP();
           }
         }
@@ -387,7 +400,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         __syncwarp();
         const int chs = (ncol * (int)sizeof(TO)) >> 4;
-        if (p.mode == 0) {
+        if constexpr (SEG) {
+          // every 16-byte chunk goes to the tensor of the segment its columns belong to (rows and conv mode alike)
+          constexpr int EPC = 16 / (int)sizeof(TO);
+          const uint32_t magic = (65536u + (uint32_t)chs - 1u) / (uint32_t)chs;
+          for (int i = 0; i < chs; ++i) {
+            const int item = i * 32 + lane, r = (int)(((uint32_t)item * magic) >> 16), c = item - r * chs;
+            const int grow = __shfl_sync(0xffffffffu, myrow, r);
+            const int col = ncol0 + c0 + c * EPC;
+            const int sg = seg_of(col);
+            TO* const so = reinterpret_cast<TO*>(sg == 0 ? p.seg_out[0] : sg == 1 ? p.seg_out[1] : sg == 2 ? p.seg_out[2] : p.seg_out[3]);
+            const int sc = sg == 0 ? p.seg_c[0] : sg == 1 ? p.seg_c[1] : sg == 2 ? p.seg_c[2] : p.seg_c[3];
+            const int sb = sg == 0 ? 0 : sg == 1 ? p.seg_beg[1] : sg == 2 ? p.seg_beg[2] : p.seg_beg[3];
+            if (grow >= 0)
+              st16_hint(reinterpret_cast<uint8_t*>(so + (size_t)grow * sc + (col - sb)), *reinterpret_cast<const uint4*>(stg_ptr + slot_off(buf, r, c)), pol_out);
+          }
+        } else if (p.mode == 0) {
           // rows mode: the warp's 32 rows are consecutive matrix rows -> affine addresses
           const int m_w0 = w.tx * tile_rows + sub * 128 + q * 32;
           const int rows_live = p.M - m_w0;
@@ -494,6 +522,18 @@ int tc_conv_supported(const capf_op& op) {
     if (op.i[19] < 0 || op.i[19] % 16 || op.i[18] != 0 || g.KH != 1 || g.KW != 1 || g.stride != 1 || g.pad != 0) return 0;
     if (!op.in[5] || ((uintptr_t)op.in[5] & 15)) return 0;
   }
+  if (op.i[20] != 0) {        // output segments: plain 16-bit/fp32 conv, no residual / GELU / split operands / second input
+    const int S = op.i[20];
+    if (S < 2 || S > 4 || op.in[3] || g.act == CAPF_ACT_GELU || op.i[18] != 0 || op.i[19] != 0 || op.i[14] < 0 || op.i[14] >= (1 << S)) return 0;
+    int used = 0;
+    for (int sgm = 0; sgm < S; ++sgm) {
+      const int wd = sgm + 1 < S ? op.i[21 + sgm] : g.Cout - used;
+      if (wd <= 0 || wd % 16) return 0;
+      used += wd;
+      if (!op.out[sgm] || ((uintptr_t)op.out[sgm] & 15)) return 0;
+    }
+    if (used != g.Cout) return 0;
+  }
   if (g.KH < 1 || g.KW < 1 || g.KH > 7 || g.KW > 7 || g.stride < 1 || g.stride > 2 || g.pad < 0) return 0;
   if (g.N <= 0 || g.H <= 0 || g.W <= 0) return 0;
   if (g.Ho != (g.H + 2 * g.pad - g.KH) / g.stride + 1 || g.Wo != (g.W + 2 * g.pad - g.KW) / g.stride + 1) return 0;
@@ -565,20 +605,21 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   if (!s) return set_error(CAPF_ERR_ARG, "tc_conv_prepare: out of host memory");
   const bool split = op.i[18] == 1;             // A = [.., 2 * Cin] bf16 (hi | lo planes), B = [Cout][taps * 3 * Cin], see capf_b200.h
   const int Cin2 = op.i[19];                    // second A matrix [M][Cin2] in in[5]: out = [x | x2] W^T, W = [Cout][Cin + Cin2]
-  if (!split && !Cin2 && op.i[13] == 0 && tc2_supported(op)) {     // wide Linears over many rows: CTA pairs (cta_group::2)
+  const int nseg = op.i[20] > 1 ? op.i[20] : 0;      // output segments: per-tap kernel only
+  if (!nseg && !split && !Cin2 && op.i[13] == 0 && tc2_supported(op)) {     // wide Linears over many rows: CTA pairs (cta_group::2)
     e = tc2_prepare(op, &s->two);
     if (e) { delete s; return e; }
     *out = s;
     return CAPF_OK;
   }
   // i[13]: kernel variant hint (0 = automatic, 1 = per-tap TMA GEMM, 2 = halo band); tests use it for A/B parity
-  if (!split && op.i[13] != 1 && tc_halo128_supported(op)) {
+  if (!nseg && !split && op.i[13] != 1 && tc_halo128_supported(op)) {
     e = tc_halo128_prepare(op, &s->h128);
     if (e) { delete s; return e; }
     *out = s;
     return CAPF_OK;
   }
-  if (!split && op.i[13] != 1 && tc_halo_supported(op)) {
+  if (!nseg && !split && op.i[13] != 1 && tc_halo_supported(op)) {
     e = tc_halo_prepare(op, &s->halo);
     if (e) { delete s; return e; }
     *out = s;
@@ -603,6 +644,16 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
   p.res = op.in[3];
   p.out = op.out[0];
   p.trace = (long long*)op.in[4];     // debug only (NULL in every program the host layer builds)
+  p.nseg = nseg;
+  for (int sgm = 0, used = 0; sgm < 4; ++sgm) {
+    const bool live = sgm < nseg;
+    const int wd = !live ? 0 : sgm + 1 < nseg ? op.i[21 + sgm] : g.Cout - used;
+    p.seg_beg[sgm] = live ? used : 0x7fffffff;
+    p.seg_c[sgm] = wd;
+    p.seg_out[sgm] = live ? op.out[sgm] : nullptr;
+    used += wd;
+  }
+  p.seg_noact = nseg ? (uint32_t)op.i[14] : 0u;
   p.M = g.N * g.Ho * g.Wo;
   const int swz = p.kb * 2;
   const int K = g.KH * g.KW * g.Cin * (split ? 3 : 1) + Cin2;      // GEMM depth (3x with split operands: hi*Wh + lo*Wh + hi*Wl)
@@ -755,8 +806,9 @@ static int tc_launch_mode(const TcConvState* s, cudaStream_t st) {
 
 template <typename TO>
 static int tc_launch_typed(const TcConvState* s, cudaStream_t st) {
-  const int mode = (s->p.res ? 1 : 0) | (s->p.act == CAPF_ACT_GELU ? 2 : 0);
+  const int mode = (s->p.res ? 1 : 0) | (s->p.act == CAPF_ACT_GELU ? 2 : 0) | (s->p.nseg ? 4 : 0);
   switch (mode) {
+    case 4: return tc_launch_mode<TO, 4>(s, st);
     case 0: return tc_launch_mode<TO, 0>(s, st);
     case 1: return tc_launch_mode<TO, 1>(s, st);
     case 2: return tc_launch_mode<TO, 2>(s, st);
@@ -786,8 +838,8 @@ void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
   if (s->two) { tc2_describe(s->two, buf, cap); return; }
   if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
   if (s->h128) { tc_halo128_describe(s->h128, buf, cap); return; }
-  snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages%s%s]", 128 * s->p.msub, s->p.BN, s->p.num_stages, s->p.cpt1 ? ", bf16x3 split operands" : "",
-           s->p.c_a1 < s->p.num_chunks ? ", two A operands" : "");
+  snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages%s%s%s]", 128 * s->p.msub, s->p.BN, s->p.num_stages, s->p.cpt1 ? ", bf16x3 split operands" : "",
+           s->p.c_a1 < s->p.num_chunks ? ", two A operands" : "", s->p.nseg ? ", output segments" : "");
 }
 
 void tc_conv_release(TcConvState* s) {

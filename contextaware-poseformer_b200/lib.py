@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcapf_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # enums (mirror capf_b200.h)
 F32, F16, BF16 = 0, 1, 2
@@ -32,7 +32,7 @@ class CapfOp(C.Structure):
         ("i", C.c_int32 * 24),
         ("f", C.c_float * 4),
         ("inp", C.c_void_p * 6),
-        ("out", C.c_void_p * 2),
+        ("out", C.c_void_p * 4),
     ]
 
 

@@ -350,6 +350,7 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
         fuse_basic_blocks(prog)
         fuse_downsample(prog)
         fuse_expand_reduce(prog)
+        fuse_siblings(prog)
         chunk_prefix(prog)
     prog.n_backbone_ops = len(prog.ops)
     if backbone_only:
@@ -624,6 +625,76 @@ def fuse_expand_reduce(prog: Program):
             out.append(a)
             k += 1
     prog.ops[:] = out
+    return fused
+
+
+# ------------------------------------------------------------------------------------------------------
+# horizontal fusion: sibling convolutions of a fuse layer that read the same branch -> one GEMM, one tensor per sibling
+# ------------------------------------------------------------------------------------------------------
+SIBLING_MAX_COUT = 256      # one column tile of the per-tap kernel (N <= 256)
+
+
+def fuse_siblings(prog: Program):
+    """The fuse layers of a HighResolutionModule (pose_hrnet.py:235-277) start several convolutions from the same branch output:
+    branch 0 of a 4-branch module feeds three 3x3 / stride-2 convs (32 -> 64 towards output 1, 32 -> 32 + ReLU as the first step of
+    the chains towards outputs 2 and 3), branch 3 feeds three 1x1 convs (256 -> 32 / 64 / 128), and so on.  As separate launches
+    each of them fetches the same input again (nine times per launch for the 3x3 ones: the per-tap kernel is bound by that feed).
+    Siblings with identical geometry become ONE CAPF_OP_CONV2D over the Cout-concatenated weights with OUTPUT SEGMENTS (i[20..23],
+    per-segment ReLU mask i[14]): every sibling still gets its own dense tensor, so no consumer changes.  A column of the GEMM is
+    computed exactly as before (same K order), results are bit-identical.  Only convs that run on the per-tap kernel anyway (1x1, or
+    stride 2) are merged; 3x3 / stride-1 convs keep their halo kernels.  CAPF_FUSE_SIBLINGS=0 keeps the separate launches."""
+    if os.environ.get("CAPF_FUSE_SIBLINGS", "1") == "0":
+        return 0
+    ops = prog.ops
+
+    def key(op):
+        if (op.kind != lib.OP_CONV2D or len(op.i) > 13 or op.i[12] != lib.IMPL_TCGEN05 or op.dtype_in not in ("f16", "bf16")
+                or op.dtype_out != op.dtype_in or len(op.ins) != 4 or op.ins[3] is not None or op.i[11] not in (lib.ACT_NONE, lib.ACT_RELU)
+                or not isinstance(op.ins[0], Buf) or len(op.outs) != 1 or op.outs[0].role != "act" or op.i[4] % 16
+                or (op.i[5] == 3 and op.i[7] == 1)):
+            return None
+        src = op.ins[0]
+        return (id(src.root), src.root_offset, tuple(src.shape), tuple(op.i[0:4]), tuple(op.i[5:11]), op.dtype_in)
+
+    groups = {}
+    for k, op in enumerate(ops):
+        kk = key(op)
+        if kk is not None:
+            groups.setdefault(kk, []).append(k)
+    replace, drop, fused = {}, set(), 0
+    for members in groups.values():
+        batch = []
+        for k in members + [None]:
+            if k is not None and len(batch) < 4 and sum(ops[m].i[4] for m in batch) + ops[k].i[4] <= SIBLING_MAX_COUT:
+                batch.append(k)
+                continue
+            if len(batch) > 1:
+                first = ops[batch[0]]
+                sib = [ops[m] for m in batch]
+                couts = [o.i[4] for o in sib]
+                wdt = first.ins[1].dtype
+                K = first.i[3] * first.i[5] * first.i[6]
+                w = WSlot("+".join(o.ins[1].name for o in sib), (sum(couts), K), wdt,
+                          (lambda packs: lambda st: torch.cat([pk(st) for pk in packs], dim=0).contiguous())([o.ins[1].pack for o in sib]))
+                bias = WSlot("+".join(o.ins[2].name for o in sib), (sum(couts),), "f32",
+                             (lambda packs: lambda st: torch.cat([pk(st) for pk in packs]).contiguous())([o.ins[2].pack for o in sib]))
+                relu = any(o.i[11] == lib.ACT_RELU for o in sib)
+                i = list(first.i) + [0] * (24 - len(first.i))
+                i[4] = sum(couts)
+                i[11] = lib.ACT_RELU if relu else lib.ACT_NONE
+                i[14] = sum(1 << n for n, o in enumerate(sib) if relu and o.i[11] != lib.ACT_RELU)
+                i[20] = len(sib)
+                for n, c in enumerate(couts[:-1]):
+                    i[21 + n] = c
+                src = first.ins[0]
+                replace[batch[0]] = Op(lib.OP_CONV2D, first.dtype_in, first.dtype_out, i, [], [src, w, bias, None], [o.outs[0] for o in sib],
+                                       tag=first.tag + "".join("+" + ".".join(o.tag.split(".")[-4:]) for o in sib[1:]),
+                                       flops=sum(o.flops for o in sib),
+                                       nbytes=src.nbytes + sum(o.outs[0].nbytes for o in sib) + sum(couts) * K * _ITEMSIZE[wdt] + 4 * sum(couts))
+                drop.update(batch[1:])
+                fused += len(batch) - 1
+            batch = [k] if k is not None else []
+    prog.ops[:] = [replace.get(k, op) for k, op in enumerate(ops) if k not in drop]
     return fused
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 11
+#define CAPF_ABI_VERSION 12
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -89,7 +89,7 @@ typedef enum capf_op_kind {
  *     i[0..10] = N,H,W,Cin,Cout,KH,KW,stride,pad,Ho,Wo   i[11]=act  i[12]=impl
  *     i[13] = tcgen05 kernel variant hint: 0 automatic, 1 per-tap TMA implicit GEMM, 2 shared-memory halo band
  *             (3x3 / stride 1 / pad 1 whose folded weights fit in shared memory); used by the A/B parity tests
- *     i[14] = reserved (a former epilogue-variant hint; ignored)
+ *     i[14] = with output segments (i[20] > 1): bit s set = segment s SKIPS the activation i[11] (NONE / RELU only); else ignored
  *     i[15] = per-tap kernel tile height hint: 0 automatic, 1 = 128 rows, 2 = 256 rows (two accumulators per B stage)
  *     i[16] = per-tap kernel column-tile width hint (0 automatic, else a multiple of 16 dividing Cout)
  *     i[17] = 2-CTA (cta_group::2) GEMM kernel for Linears over rows: 0 automatic (wide Linears with many rows),
@@ -98,6 +98,11 @@ typedef enum capf_op_kind {
  *             w is [Cout][KH*KW*(Wh | Wh)][KH*KW*Wl] bf16; the kernel accumulates hi*Wh + lo*Wh + hi*Wl (per-tap kernel only)
  *     i[19] = Cin2 > 0: a SECOND input x2 [N,H,W,Cin2] in in[5] (1x1 / stride 1 only): out = [x | x2] . w^T with
  *             w = [Cout][Cin + Cin2] -- a Bottleneck's conv3 and its downsample conv as one GEMM (pose_hrnet.py:116-136)
+ *     i[20] = S in 2..4: OUTPUT SEGMENTS (tcgen05 per-tap kernel; no residual, no GELU, no split operands / second input).  Sibling
+ *             convolutions that read the same x with the same geometry -- the fuse-layer convs of a HighResolutionModule that
+ *             start from one branch (pose_hrnet.py:235-277) -- run as ONE GEMM over the Cout-concatenated weights; segment s
+ *             (i[21], i[22], i[23] = channel widths of segments 0..2, multiples of 16; the last segment takes the rest of Cout)
+ *             is written to its own dense tensor out[s] [N,Ho,Wo,width_s].  Bit-identical to the separate convolutions.
  *     in[0]=x  [N,H,W,Cin]        dtype_in
  *     in[1]=w  SIMT: [KH*KW*Cin][Cout] (tap-major rows, Cout contiguous); TCGEN05: [Cout][KH*KW*Cin];
  *              dtype_in, except x f32 -> w f32.  BatchNorm scale is pre-folded into w by the host.
@@ -241,7 +246,7 @@ typedef struct capf_op {
   int32_t i[24];
   float f[4];
   const void* in[6];
-  void* out[2];
+  void* out[4];
 } capf_op;
 
 typedef struct capf_plan capf_plan;

@@ -64,6 +64,19 @@ class Interp:
             y = F.gelu(y)
         if op.ins[3] is not None:
             y = y + self.t(op.ins[3]).reshape(N, Ho, Wo, Cout).float()
+        nseg = op.i[20] if len(op.i) > 20 else 0
+        if nseg > 1:                                  # output segments: channel ranges of the GEMM go to separate tensors
+            widths = [op.i[21 + s] for s in range(nseg - 1)]
+            widths.append(Cout - sum(widths))
+            c0 = 0
+            for s, wd in enumerate(widths):
+                ys = y[..., c0:c0 + wd]
+                if act == lib.ACT_RELU and not (op.i[14] >> s) & 1:
+                    ys = F.relu(ys)
+                out = self.t(op.outs[s])
+                out.copy_(ys.reshape(out.shape).to(out.dtype))
+                c0 += wd
+            return
         if act == lib.ACT_RELU:
             y = F.relu(y)
         out = self.t(op.outs[0])

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert L.capf_abi_version() == lib.ABI_VERSION
     m = re.search(r"#define CAPF_ABI_VERSION (\d+)", header)
     assert int(m.group(1)) == lib.ABI_VERSION
-    assert ctypes.sizeof(lib.CapfOp) == 16 + 24 * 4 + 16 + 6 * 8 + 2 * 8
+    assert ctypes.sizeof(lib.CapfOp) == 16 + 24 * 4 + 16 + 6 * 8 + 4 * 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

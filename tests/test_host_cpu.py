@@ -2,6 +2,7 @@
 with the real memory plan), frame sharding.  No GPU, no compute calls into the shared library."""
 import copy
 import os
+import re
 
 import numpy as np
 import pytest
@@ -244,3 +245,39 @@ def test_forward_rejects_misshaped_crop_without_gpu():
     m = capf_b200.CA_PF(capf_b200.make_config("hrnet_32")).eval()
     with pytest.raises(lib.CapfError):           # CPU tensors: there is no CPU path
         m(torch.zeros(1, 64, 64, 3), torch.zeros(1, 17, 2), torch.zeros(1, 17, 2))
+
+
+def test_sibling_convs_become_one_gemm_with_output_segments(monkeypatch):
+    """program.fuse_siblings: the fuse-layer convolutions of a HighResolutionModule that start from the same branch
+    (pose_hrnet.py:235-277) run as one GEMM over the Cout-concatenated weights, one dense tensor per sibling.  The program with
+    the merged ops computes exactly what the separate convolutions compute (TEST interpreter, same memory plan rules)."""
+    case = next(c for c in golden_cases() if c["name"] == "hrnet32_b2_128x96")
+    g = load_golden(case["name"])
+    m, w, cfg = build_case_model(case["backbone"], case["weight_seed"])
+    B, H, W = case["B"], case["H"], case["W"]
+    images, kp2d, crop = protocol.make_inputs(B, H, W, case["input_seed"])
+    shapes = {k: tuple(v.shape) for k, v in w.items()}
+    outs, progs = [], []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("CAPF_FUSE_SIBLINGS", flag)
+        prog = program.build_forward_program("hrnet_32", m.backbone.cfg, m._pf_cfg, shapes, B, H, W, "fp16", use_tc=True)
+        it = interp.Interp(prog, w)
+        it.t(prog.inputs["images"]).copy_(images)
+        it.t(prog.inputs["kp2d"]).copy_(kp2d.reshape(-1, 2))
+        it.t(prog.inputs["ref"]).copy_(torch.from_numpy(g["crop_after"]).reshape(-1, 2))
+        it.run()
+        outs.append(it.t(prog.outputs["out"]).clone())
+        progs.append(prog)
+    merged = [op for op in progs[0].ops if op.kind == lib.OP_CONV2D and len(op.i) > 20 and op.i[20] > 1]
+    # stage3: 4 modules x {branch 0: 2 stride-2 convs, branch 2: 2 1x1 convs}; stage4: 2 multi-output modules x {branch 0: 3,
+    # branch 1: 2, branch 2: 2, branch 3: 3}
+    assert sorted(op.i[20] for op in merged) == [2] * 12 + [3] * 4
+    assert len(progs[1].ops) - len(progs[0].ops) == sum(op.i[20] - 1 for op in merged) == 20
+    for op in merged:
+        widths = [op.i[21 + s] for s in range(op.i[20] - 1)]
+        widths.append(op.i[4] - sum(widths))
+        assert [o.shape[-1] for o in op.outs] == widths and op.i[4] <= program.SIBLING_MAX_COUT
+        assert op.lane == int(re.search(r"fuse_layers\.\d+\.(\d+)\.", op.tag).group(1))
+    assert sum(op.flops for op in progs[0].ops) == sum(op.flops for op in progs[1].ops)
+    assert torch.equal(outs[0], outs[1])
+    assert rel_l2(outs[0].view(B, 1, 17, 3), g["out"]) < 2.5e-3
