@@ -476,6 +476,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 struct TcConvState {
   TcHaloState* halo = nullptr;   // non-null: the op runs on the halo-band kernel instead of tc_gemm_kernel
   TcHalo128State* h128 = nullptr; // non-null: halo band + streamed weights (C = Cout = 128)
+  TcHalo256State* h256 = nullptr; // non-null: halo tile in four planes + streamed weights (C = 256 -> 32)
   Tc2State* two = nullptr;       // non-null: the op runs on the 2-CTA GEMM kernel (capf_tc2.cu)
   TcBlockState* blk = nullptr;   // non-null: a fused BasicBlock op (capf_tc_block.cu)
   TcChainState* chain = nullptr; // non-null: a CAPF_OP_EXPAND_REDUCE op (capf_tc_chain.cu)
@@ -613,6 +614,12 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out) {
     return CAPF_OK;
   }
   // i[13]: kernel variant hint (0 = automatic, 1 = per-tap TMA GEMM, 2 = halo band); tests use it for A/B parity
+  if (!nseg && !split && !Cin2 && op.i[13] != 1 && tc_halo256_supported(op)) {
+    e = tc_halo256_prepare(op, &s->h256);
+    if (e) { delete s; return e; }
+    *out = s;
+    return CAPF_OK;
+  }
   if (!nseg && !split && op.i[13] != 1 && tc_halo128_supported(op)) {
     e = tc_halo128_prepare(op, &s->h128);
     if (e) { delete s; return e; }
@@ -823,6 +830,7 @@ int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
   if (s->two) return tc2_launch(s->two, st);
   if (s->halo) return tc_halo_launch(s->halo, st);
   if (s->h128) return tc_halo128_launch(s->h128, st);
+  if (s->h256) return tc_halo256_launch(s->h256, st);
   switch (s->dtype_out) {
     case CAPF_F32: return tc_launch_typed<float>(s, st);
     case CAPF_F16: return tc_launch_typed<__half>(s, st);
@@ -838,6 +846,7 @@ void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
   if (s->two) { tc2_describe(s->two, buf, cap); return; }
   if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
   if (s->h128) { tc_halo128_describe(s->h128, buf, cap); return; }
+  if (s->h256) { tc_halo256_describe(s->h256, buf, cap); return; }
   snprintf(buf, cap, "tc_gemm_kernel[%dx%d tile, %d stages%s%s%s]", 128 * s->p.msub, s->p.BN, s->p.num_stages, s->p.cpt1 ? ", bf16x3 split operands" : "",
            s->p.c_a1 < s->p.num_chunks ? ", two A operands" : "", s->p.nseg ? ", output segments" : "");
 }
@@ -848,6 +857,7 @@ void tc_conv_release(TcConvState* s) {
   if (s && s->two) tc2_release(s->two);
   if (s && s->halo) tc_halo_release(s->halo);
   if (s && s->h128) tc_halo128_release(s->h128);
+  if (s && s->h256) tc_halo256_release(s->h256);
   delete s;
 }
 

@@ -387,6 +387,14 @@ int tc_halo128_launch(const TcHalo128State* s, cudaStream_t st);
 void tc_halo128_release(TcHalo128State* s);
 void tc_halo128_describe(const TcHalo128State* s, char* buf, int cap);
 
+// halo tile in four 64-channel planes + streamed weights: 3x3 / stride 1 with C = 256 -> Cout = 32 (capf_tc_halo256.cu)
+struct TcHalo256State;
+int tc_halo256_supported(const capf_op& op);
+int tc_halo256_prepare(const capf_op& op, TcHalo256State** out);
+int tc_halo256_launch(const TcHalo256State* s, cudaStream_t st);
+void tc_halo256_release(TcHalo256State* s);
+void tc_halo256_describe(const TcHalo256State* s, char* buf, int cap);
+
 // bias + GELU + residual + ReLU on 16 accumulator columns of a 16-bit output row staged in shared memory: the residual (if
 // any) is read from, and the result written back to, the two 16-byte chunks at smem addresses s0 / s1 (runtime-flag
 // variant used by the stem kernel; the GEMM / halo kernels use the compile-time epi16 below).

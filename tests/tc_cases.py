@@ -65,6 +65,19 @@ HALO128_CASES = [
 ]
 
 
+# 3x3 / stride 1 / pad 1, C = 256 -> Cout = 32 (HRNet transition1.0): halo tile in four planes + streamed weights
+# (csrc/capf_tc_halo256.cu) -- taken by default (variant 0)
+HALO256_CASES = [
+    ("h256_64x64", (3, 64, 64, 256, 32, 3, 1), lib.ACT_RELU, False, False),
+    ("h256_64x48_none", (2, 64, 48, 256, 32, 3, 1), lib.ACT_NONE, False, False),
+    ("h256_32x24", (3, 32, 24, 256, 32, 3, 1), lib.ACT_RELU, False, False),
+    ("h256_tiny_5x3", (2, 5, 3, 256, 32, 3, 1), lib.ACT_RELU, False, False),
+    ("h256_many_tiles", (40, 64, 64, 256, 32, 3, 1), lib.ACT_RELU, False, False),
+    ("h256_ragged_37x45", (2, 37, 45, 256, 32, 3, 1), lib.ACT_NONE, False, False),
+    ("h256_wide_6x130", (1, 6, 130, 256, 32, 3, 1), lib.ACT_RELU, False, False),
+]
+
+
 def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=0, two=0, inplace=False):
     """Returns (rel_l2, max_abs, frac_bad_rows) of the tcgen05 kernel against the fp32 reference.
     inplace: the output buffer IS the residual buffer (how plan_memory runs a residual whose last reader is this op)."""

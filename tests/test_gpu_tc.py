@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from tc_cases import HALO128_CASES, HALO_CASES, TC_CASES, run_tc_case
+from tc_cases import HALO128_CASES, HALO256_CASES, HALO_CASES, TC_CASES, run_tc_case
 
 pytestmark = pytest.mark.gpu
 
@@ -59,6 +59,44 @@ def test_halo128_conv_matches_fp32_reference(case, dt):
     lib.load().capf_plan_op_kernel(h, 0, buf, 160)
     lib.load().capf_plan_destroy(h)
     assert buf.value.decode().startswith("tc_conv3_halo128_kernel"), buf.value
+
+
+def _dispatched_kernel(case, dt=None):
+    import ctypes
+    from capf_b200 import lib
+    name, (N, H, W, Cin, Cout, k, stride), act, use_res, _ = case
+    op = lib.CapfOp()
+    op.kind, op.dtype_in, op.dtype_out = lib.OP_CONV2D, lib.F16, lib.F16
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    x = torch.zeros(N, H, W, Cin, dtype=torch.float16, device="cuda")
+    w = torch.zeros(Cout, k * k * Cin, dtype=torch.float16, device="cuda")
+    y = torch.zeros(N, Ho, Wo, Cout, dtype=torch.float16, device="cuda")
+    for n, v in enumerate([N, H, W, Cin, Cout, k, k, stride, pad, Ho, Wo, act, lib.IMPL_TCGEN05]):
+        op.i[n] = v
+    op.inp[0], op.inp[1], op.out[0] = x.data_ptr(), w.data_ptr(), y.data_ptr()
+    h = ctypes.c_void_p()
+    arr = (lib.CapfOp * 1)(op)
+    lib.check(lib.load().capf_plan_create(arr, 1, 0, ctypes.byref(h)), "plan")
+    buf = ctypes.create_string_buffer(160)
+    lib.load().capf_plan_op_kernel(h, 0, buf, 160)
+    lib.load().capf_plan_destroy(h)
+    return buf.value.decode()
+
+
+@pytest.mark.parametrize("case", HALO256_CASES, ids=[c[0] for c in HALO256_CASES])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_halo256_conv_matches_fp32_reference(case, dt):
+    """C = 256 -> 32 3x3 convolutions (HRNet transition1.0; pose_hrnet.py:372-411): halo tile in four 64-channel planes (plane-major
+    K loop, per-plane barriers) + weights streamed through a ring -- full-width and split tiles, ragged last tile row / column, more
+    tiles than SMs, both accumulator stages -- against plain fp32 PyTorch and against the per-tap kernel (a different summation
+    order of the same fp32 accumulation: the errors must agree)."""
+    rel, max_abs, bad_rows = run_tc_case(case, dt)
+    print(f"{case[0]} {dt}: rel-L2 {rel:.3e} max-abs {max_abs:.3e} bad-rows {bad_rows:.4f}")
+    assert bad_rows == 0.0 and rel < (1.5e-3 if dt == torch.float16 else 8e-3)
+    rel1, _, _ = run_tc_case(case, dt, variant=1)
+    assert abs(rel - rel1) < 0.05 * rel1 + 1e-6
+    assert _dispatched_kernel(case).startswith("tc_conv3_halo256_kernel")
 
 
 @pytest.mark.parametrize("M,C1,C2,Cout", [(1000, 64, 64, 256), (4096, 128, 256, 256), (300, 64, 256, 256), (129, 32, 16, 48), (5000, 512, 256, 1024)])
