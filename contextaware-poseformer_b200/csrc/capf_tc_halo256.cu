@@ -10,12 +10,16 @@
 //       by TMA outside the image) as FOUR 64-channel planes of 128-byte-swizzled pixel rows (pitch Wp = tw + 2); tap (r, s),
 //       K step kk of plane pl is the plane's buffer read through a descriptor whose start moves by (r * Wp + s) pixels
 //       (the shifted window of capf_tc_halo.cu);
-//   K   the loop runs PLANE-major (plane, tap, k): each plane has its own full / empty barrier pair, so the tile of band
-//       b + 1 streams into plane 0 while planes 1-3 of band b are still being multiplied -- the 170 KB tile is
-//       "double buffered" without a second buffer;
-//   B   the folded weights [32][9 * 256] stream through a ring of 4 KB (plane, tap) chunks (8 stages); every chunk feeds all
-//       128-row sub-tiles of the tile;
+//   K   the loop runs PLANE-major (plane, filter row, tap, k) and the planes of consecutive tiles rotate through THREE plane
+//       buffers, each with its own full / empty barrier pair: the next planes stream in while the current one is being
+//       multiplied, and the fourth buffer's 42 KB go to the weight ring instead;
+//   B   the folded weights [32][9 * 256] stream through a ring of 12 KB chunks (the three taps of one filter row of one plane;
+//       7 stages = 84 KB in flight); every chunk feeds all 128-row sub-tiles of the tile: 12 MMAs per issuer and barrier round trip;
 //   D   two accumulator stages (n_sub x 32 TMEM columns each): the epilogue of tile b overlaps the MMAs of tile b + 1.
+//
+// Measured with the wait-cycle counters of CTA 0 (ONE_TRACE=1 tools/one_conv.py): with 4 KB (plane, tap) chunks and an 8-deep ring
+// the even issuer spent 62 % of the kernel blocked on MMA issue (82 clk per MMA = the N = 32 operand-port time of its own and the
+// other issuer's MMA), 13 % waiting for weights and 21 % in per-chunk overhead -- hence the larger chunks and the deeper ring.
 //
 // L2 -> SM bytes per launch: 1.5 x the input (tile halo) + one pass over the 147 KB of weights per tile = 1.6 GB instead of
 // 4.8 GB; what remains is the shared-memory operand port of N = 32 MMAs (4 KB of A + 1 KB of B per 16 tensor clocks of work).
@@ -35,9 +39,11 @@ constexpr int H256_HEADER = 2048;            // barriers (first 512 B) + 32 fp32
 constexpr int H256_BIAS_OFF = 1024;
 constexpr int H256_C = 256, H256_NPL = 4;    // input channels = 4 planes of 64
 constexpr int H256_COUT = 32;
-constexpr int H256_CHUNK_BYTES = H256_COUT * 128;   // one weight chunk: 32 output channels x 64 input channels x 2 B
+constexpr int H256_NPB = 3;                  // plane BUFFERS: the 4 planes of consecutive tiles rotate through 3 buffers
+constexpr int H256_TAP_BYTES = H256_COUT * 128;     // weights of one (plane, tap): 32 output channels x 64 input channels x 2 B
+constexpr int H256_CHUNK_BYTES = 3 * H256_TAP_BYTES;   // one weight chunk = the three taps of a filter row of one plane
 constexpr int H256_MAX_B = 8;                // weight ring stages
-constexpr int H256_MIN_B = 6;
+constexpr int H256_MIN_B = 4;
 constexpr int H256_EPI_WARPS = 8;
 constexpr int H256_STG_BYTES = 32 * 64;      // staging tile of one warp: 32 pixels x 32 channels x 2 B
 constexpr int H256_ACC_STRIDE = 128;         // TMEM columns per accumulator stage (up to 4 sub-tiles x 32)
@@ -55,6 +61,7 @@ struct H256P {
   int act;
   const float* bias;
   void* out;
+  long long* trace;         // optional (debug, op.in[4]): wait-cycle counters of CTA 0's even issuer, see tools/one_conv.py
 };
 
 // linear band index -> (image, band row, tile column); tile column fastest
@@ -82,13 +89,13 @@ tc_conv3_halo256_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t bar_bfull = base;                          // [H256_MAX_B] weight chunk landed
   const uint32_t bar_bempty = base + 64;                    // [H256_MAX_B] weight chunk consumed (both issuers)
-  const uint32_t bar_pfull = base + 128;                    // [4] plane of the tile landed
-  const uint32_t bar_pempty = base + 160;                   // [4] plane consumed (both issuers)
+  const uint32_t bar_pfull = base + 128;                    // [H256_NPB] plane buffer filled
+  const uint32_t bar_pempty = base + 160;                   // [H256_NPB] plane buffer consumed (both issuers)
   const uint32_t bar_tfull = base + 192;                    // [2] accumulator stage complete (both issuers)
   const uint32_t bar_tempty = base + 208;                   // [2] accumulator stage drained (256 arrivals)
   const uint32_t tmem_slot = base + 224;
-  const uint32_t smem_a = base + H256_HEADER;               // 4 planes
-  const uint32_t smem_b = smem_a + (uint32_t)H256_NPL * (uint32_t)p.plane_bytes;
+  const uint32_t smem_a = base + H256_HEADER;               // H256_NPB plane buffers
+  const uint32_t smem_b = smem_a + (uint32_t)H256_NPB * (uint32_t)p.plane_bytes;
   const uint32_t smem_stg = smem_b + (uint32_t)(p.nb * H256_CHUNK_BYTES);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,9 +109,9 @@ tc_conv3_halo256_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
       ptx::mbar_init(bar_bfull + 8 * s, 1);
       ptx::mbar_init(bar_bempty + 8 * s, 2);
     }
-    for (int pl = 0; pl < H256_NPL; ++pl) {
-      ptx::mbar_init(bar_pfull + 8 * pl, 1);
-      ptx::mbar_init(bar_pempty + 8 * pl, 2);
+    for (int pb = 0; pb < H256_NPB; ++pb) {
+      ptx::mbar_init(bar_pfull + 8 * pb, 1);
+      ptx::mbar_init(bar_pempty + 8 * pb, 2);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 2);
@@ -137,11 +144,13 @@ tc_conv3_halo256_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
       uint32_t stage = 0, phase = 0;
       for (int b = 0; b < nbands; ++b) {
         for (int pl = 0; pl < H256_NPL; ++pl) {
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int trow = 0; trow < 3; ++trow) {
             ptx::mbar_wait(bar_bempty + 8 * stage, phase ^ 1u);
             const uint32_t full = bar_bfull + 8 * stage;
             ptx::mbar_arrive_expect_tx(full, (uint32_t)H256_CHUNK_BYTES);
-            ptx::tma_load_2d(&mapB, full, smem_b + stage * H256_CHUNK_BYTES, tap * H256_C + pl * 64, 0);
+#pragma unroll
+            for (int ts = 0; ts < 3; ++ts)
+              ptx::tma_load_2d(&mapB, full, smem_b + stage * H256_CHUNK_BYTES + ts * H256_TAP_BYTES, (trow * 3 + ts) * H256_C + pl * 64, 0);
             if (++stage == (uint32_t)p.nb) { stage = 0; phase ^= 1u; }
           }
         }
@@ -152,12 +161,14 @@ tc_conv3_halo256_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
     if (ptx::elect_one()) {
       H256Walk w;
       w.init(p, band0);
+      uint32_t pb = 0, pphase = 0;                     // plane buffer of the running (tile, plane) sequence and its fill parity
       for (int b = 0; b < nbands; ++b, w.next(p)) {
         const int x_left = w.tx * p.tw - 1, y_top = w.by * p.bh - 1;
         for (int pl = 0; pl < H256_NPL; ++pl) {
-          ptx::mbar_wait(bar_pempty + 8 * pl, (uint32_t)(b & 1) ^ 1u);      // the previous tile's MMAs are done with this plane
-          ptx::mbar_arrive_expect_tx(bar_pfull + 8 * pl, (uint32_t)p.plane_tx_bytes);
-          ptx::tma_load_4d(&mapA, bar_pfull + 8 * pl, smem_a + (uint32_t)pl * (uint32_t)p.plane_bytes, 64 * pl, x_left, y_top, w.img);
+          ptx::mbar_wait(bar_pempty + 8 * pb, pphase ^ 1u);      // the MMAs that read this buffer's previous plane are complete
+          ptx::mbar_arrive_expect_tx(bar_pfull + 8 * pb, (uint32_t)p.plane_tx_bytes);
+          ptx::tma_load_4d(&mapA, bar_pfull + 8 * pb, smem_a + pb * (uint32_t)p.plane_bytes, 64 * pl, x_left, y_top, w.img);
+          if (++pb == (uint32_t)H256_NPB) { pb = 0; pphase ^= 1u; }
         }
       }
     }
@@ -166,46 +177,62 @@ tc_conv3_halo256_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
     const int parity = warp == 1 ? 0 : 1;
     const uint32_t a_lo0 = tc_desc_lo(smem_a, 1u), plane16 = (uint32_t)p.plane_bytes >> 4;
     const uint32_t b_lo0 = tc_desc_lo(smem_b, 1u);
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, pb = 0, pphase = 0;
     H256Walk w;
     w.init(p, band0);
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && parity == 0;
+    long long t_acc = 0, t_plane = 0, t_w = 0, t_issue = 0, t_all = tr ? clock64() : 0, t0 = 0;
     for (int b = 0; b < nbands; ++b, w.next(p)) {
       const int bh_eff = min(p.bh, p.H - w.by * p.bh);
       const int n_sub = (bh_eff * p.Wp + 127) >> 7;
       const uint32_t acc = (uint32_t)(b & 1);
+      if (tr) t0 = clock64();
       ptx::mbar_wait(bar_tempty + 8 * acc, (uint32_t)((b >> 1) & 1) ^ 1u);      // this stage's previous accumulators drained
       ptx::tc_fence_after();
+      if (tr) t_acc += clock64() - t0;
       const uint32_t d_base = tmem_base + acc * (uint32_t)H256_ACC_STRIDE;
       for (int pl = 0; pl < H256_NPL; ++pl) {
-        ptx::mbar_wait(bar_pfull + 8 * pl, (uint32_t)(b & 1));
+        if (tr) t0 = clock64();
+        ptx::mbar_wait(bar_pfull + 8 * pb, pphase);
         ptx::tc_fence_after();
-        const uint32_t a_pl = a_lo0 + (uint32_t)pl * plane16;
-        int tr = 0, ts = 0;                                  // filter tap (row, column)
+        if (tr) t_plane += clock64() - t0;
+        const uint32_t a_pl = a_lo0 + pb * plane16;
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int trow = 0; trow < 3; ++trow) {
+          if (tr) t0 = clock64();
           ptx::mbar_wait(bar_bfull + 8 * stage, phase);
           ptx::tc_fence_after();
+          if (tr) { const long long t1 = clock64(); t_w += t1 - t0; t0 = t1; }
           if (ptx::elect_one()) {
-            const uint32_t a_c = a_pl + (uint32_t)(tr * p.Wp + ts) * 8u;      // shifted window: 16-byte units, 128 B per pixel
-            const uint32_t b_c = b_lo0 + stage * (uint32_t)(H256_CHUNK_BYTES >> 4);
+            const uint32_t a_r = a_pl + (uint32_t)(trow * p.Wp) * 8u;      // shifted window: 16-byte units, 128 B per pixel
+            const uint32_t b_r = b_lo0 + stage * (uint32_t)(H256_CHUNK_BYTES >> 4);
             for (int j = parity; j < n_sub; j += 2) {
               const uint32_t d_tmem = d_base + (uint32_t)(j * H256_COUT);
-              const uint32_t a_j = a_c + (uint32_t)(j * 128) * 8u;
+              const uint32_t a_j = a_r + (uint32_t)(j * 128) * 8u;
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                ptx::umma_f16_lohi(d_tmem, a_j + 2u * kk, p.desc_hi, b_c + 2u * kk, p.desc_hi, p.idesc, (pl | tap | kk) ? 1u : 0u);
+              for (int ts = 0; ts < 3; ++ts) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  ptx::umma_f16_lohi(d_tmem, a_j + 8u * ts + 2u * kk, p.desc_hi, b_r + (uint32_t)(ts * (H256_TAP_BYTES >> 4)) + 2u * kk, p.desc_hi, p.idesc,
+                                     (pl | trow | ts | kk) ? 1u : 0u);
+              }
             }
             ptx::umma_commit(bar_bempty + 8 * stage);
-            if (tap == 8) {
-              ptx::umma_commit(bar_pempty + 8 * pl);
+            if (trow == 2) {
+              ptx::umma_commit(bar_pempty + 8 * pb);
               if (pl == H256_NPL - 1) ptx::umma_commit(bar_tfull + 8 * acc);
             }
           }
           __syncwarp();
-          if (++ts == 3) { ts = 0; ++tr; }
+          if (tr) t_issue += clock64() - t0;
           if (++stage == (uint32_t)p.nb) { stage = 0; phase ^= 1u; }
         }
+        if (++pb == (uint32_t)H256_NPB) { pb = 0; pphase ^= 1u; }
       }
+    }
+    if (tr && lane == 0) {
+      p.trace[0] = clock64() - t_all; p.trace[1] = nbands; p.trace[2] = t_acc; p.trace[3] = t_plane; p.trace[4] = t_w; p.trace[5] = t_issue;
+      p.trace[6] = p.bh; p.trace[7] = p.tw; p.trace[8] = p.nb;
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =========================================
@@ -295,7 +322,7 @@ static int h256_plan(const capf_op& op, H256P& p, int& smem_bytes) {
     for (int bh = 1; bh <= H && bh + 2 <= 256; ++bh) {
       const int n_sub = (bh * Wp + 127) / 128;
       if (n_sub > 4) break;
-      if (fixed + H256_NPL * (long long)h256_plane_bytes(bh, Wp) + H256_MIN_B * H256_CHUNK_BYTES > TC_SMEM_LIMIT) break;
+      if (fixed + H256_NPB * (long long)h256_plane_bytes(bh, Wp) + H256_MIN_B * H256_CHUNK_BYTES > TC_SMEM_LIMIT) break;
       const int full = H / bh, rem = H - full * bh;
       const double cost = tiles_x * ((double)full * (n_sub + 0.3) + (rem ? ((rem * Wp + 127) / 128 + 0.3) : 0.0));
       if (cost < best_cost - 1e-9) { best_cost = cost; best_bh = bh; best_tx = tiles_x; }
@@ -313,12 +340,12 @@ static int h256_plan(const capf_op& op, H256P& p, int& smem_bytes) {
   p.num_bands = (int)nbands;
   p.plane_bytes = h256_plane_bytes(p.bh, p.Wp);
   p.plane_tx_bytes = (p.bh + 2) * p.Wp * 128;
-  int nb = (TC_SMEM_LIMIT - fixed - H256_NPL * p.plane_bytes) / H256_CHUNK_BYTES;
+  int nb = (TC_SMEM_LIMIT - fixed - H256_NPB * p.plane_bytes) / H256_CHUNK_BYTES;
   if (nb > H256_MAX_B) nb = H256_MAX_B;
   if (nb < H256_MIN_B) return 0;
   p.nb = nb;
   p.n_sub_max = (p.bh * p.Wp + 127) / 128;
-  smem_bytes = fixed + H256_NPL * p.plane_bytes + nb * H256_CHUNK_BYTES;
+  smem_bytes = fixed + H256_NPB * p.plane_bytes + nb * H256_CHUNK_BYTES;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;     // one CTA per SM
   return 1;
 }
@@ -343,6 +370,7 @@ int tc_halo256_prepare(const capf_op& op, TcHalo256State** out) {
   p.act = op.i[11];
   p.bias = (const float*)op.in[2];
   p.out = op.out[0];
+  p.trace = (long long*)op.in[4];       // debug only (NULL in every program the host layer builds)
   s->grid = p.num_bands < num_sms() ? p.num_bands : num_sms();
   s->dtype = op.dtype_in;
   const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;

@@ -40,6 +40,10 @@ def main():
     op.inp[0], op.inp[1], op.inp[2] = x.data_ptr(), w.data_ptr(), bias.data_ptr()
     op.inp[3] = res.data_ptr() if use_res else None
     op.out[0] = out.data_ptr()
+    trace = None
+    if os.environ.get("ONE_TRACE"):         # kernels with a debug timeline (in[4]): print the raw counters of CTA 0
+        trace = torch.zeros(256, dtype=torch.int64, device=dev)
+        op.inp[4] = trace.data_ptr()
     L = lib.load()
     arr = (lib.CapfOp * 1)(op)
     h = ctypes.c_void_p()
@@ -55,6 +59,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
+    if trace is not None:
+        print("trace:", trace[:16].tolist())
     fl = 2.0 * N * Ho * Wo * Cout * k * k * Cin
     best = min(ts)
     print(f"conv {a[:8]} res={use_res}: best {best:.1f} us  median {sorted(ts)[len(ts) // 2]:.1f} us  {fl / best / 1e6:.1f} TFLOP/s (L2 flushed)")
