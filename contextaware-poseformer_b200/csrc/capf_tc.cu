@@ -228,34 +228,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer ========================================
-    // The whole warp walks the pipeline (uniform control flow); one elected lane issues the tcgen05 ops.
-    // A full stage is always 4 MMAs of K = 16 per 128-row sub-tile: (64 / kb) chunks x (kb / 16) steps; the msub
-    // sub-tiles of a tile read the same B stage and accumulate into neighbouring TMEM column ranges.
-    uint32_t a_off[4], b_off[4];
-    {
-      const int ksteps = p.kb >> 4;
+    // ===================================== MMA issuer (one elected thread) ====================
+    // One thread walks the pipeline: barrier waits, descriptor arithmetic and the tcgen05 ops are all single-thread work, and
+    // a stage of an N <= 64 GEMM is only 4-8 MMAs of ~40 clk -- a per-stage warp re-convergence + election would be a
+    // visible fraction of it.  A full stage is always 4 MMAs of K = 16 per 128-row sub-tile: (64 / kb) chunks x (kb / 16) steps;
+    // the msub sub-tiles of a tile read the same B stage and accumulate into neighbouring TMEM column ranges.
+    if (ptx::elect_one()) {
+      uint32_t a_off[4], b_off[4];
+      {
+        const int ksteps = p.kb >> 4;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = i / ksteps, k = i - j * ksteps;
-        a_off[i] = (uint32_t)(j * p.a_chunk_bytes + 32 * k) >> 4;
-        b_off[i] = (uint32_t)(j * p.b_chunk_bytes + 32 * k) >> 4;
+        for (int i = 0; i < 4; ++i) {
+          const int j = i / ksteps, k = i - j * ksteps;
+          a_off[i] = (uint32_t)(j * p.a_chunk_bytes + 32 * k) >> 4;
+          b_off[i] = (uint32_t)(j * p.b_chunk_bytes + 32 * k) >> 4;
+        }
       }
-    }
-    const int mma_per_chunk = p.kb >> 4;
-    const uint32_t a_sub16 = (uint32_t)p.a_sub_bytes >> 4;
-    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int tile = t0; tile < t1; ++tile) {
-      ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * acc_stride;
-      uint32_t accumulate = 0;
-      for (int c0 = 0; c0 < p.num_chunks; c0 += p.cps) {
-        ptx::mbar_wait(bar_full + 8 * stage, phase);
+      const int mma_per_chunk = p.kb >> 4;
+      const uint32_t a_sub16 = (uint32_t)p.a_sub_bytes >> 4;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = t0; tile < t1; ++tile) {
+        ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
         ptx::tc_fence_after();
-        const int nmma = min(p.cps, p.num_chunks - c0) * mma_per_chunk;
-        const bool last = c0 + p.cps >= p.num_chunks;
-        if (ptx::elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        uint32_t accumulate = 0;
+        for (int c0 = 0; c0 < p.num_chunks; c0 += p.cps) {
+          ptx::mbar_wait(bar_full + 8 * stage, phase);
+          ptx::tc_fence_after();
+          const int nmma = min(p.cps, p.num_chunks - c0) * mma_per_chunk;
+          const bool last = c0 + p.cps >= p.num_chunks;
           const uint32_t a_src = stage0 + stage * p.stage_bytes;
           const uint64_t a_desc = make_desc(a_src, p.desc_hi), b_desc = make_desc(a_src + p.a_stage_bytes, p.desc_hi);
           for (int sub = 0; sub < p.msub; ++sub) {
@@ -269,12 +270,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           ptx::umma_commit(bar_empty + 8 * stage);      // smem slot reusable once these MMAs have read it
           if (last) ptx::umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
           if (tr) { const int n = (tile - t0) * ((p.num_chunks + p.cps - 1) / p.cps) + c0 / p.cps; if (n < 64) p.trace[128 + n] = clock64(); }
+          accumulate = 1;
+          if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        accumulate = 1;
-        if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1u; }
+        if (++acc == (uint32_t)p.nacc) { acc = 0; acc_phase ^= 1u; }
       }
-      if (++acc == (uint32_t)p.nacc) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =========================================
