@@ -374,35 +374,51 @@ template <> struct Vec16B<__nv_bfloat16> {
   }
 };
 
+// Every block owns a contiguous range of output rows (n, y) and every thread a fixed 16-byte slot of the row (for the HRNet
+// shapes a row is exactly 256 vectors: one per thread), so the per-vector work is one 32-bit multiply-add per term for the
+// address, the loads, the fp32 sum and one store -- the first version spent three integer divisions and four 64-bit address
+// chains per vector and was bound by instruction issue (ncu: SM 58 %, DRAM 34 %, profiles/r2u_ncu_full_summary.md).
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseP p, T* __restrict__ y) {
   pdl_wait();
   constexpr int E = Vec16B<T>::E;
-  const uint32_t CV = (uint32_t)p.C / E;                      // 16-byte vectors per pixel
-  const uint32_t rowv = (uint32_t)p.W * CV;                   // ... per image row
-  const uint32_t total = (uint32_t)p.N * p.H * rowv;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t r = i / rowv, inrow = i - r * rowv;        // r = n * H + y
-    const uint32_t xx = inrow / CV, cv = inrow - xx * CV;
-    const uint32_t n = r / (uint32_t)p.H, yy = r - n * (uint32_t)p.H;
-    Vec16B<T> a;
+  const int CV = p.C / E;                                     // 16-byte vectors per pixel
+  const int rowv = p.W * CV;                                  // ... per output row
+  const int rows = p.N * p.H;
+  const int r0 = (int)(((long long)rows * blockIdx.x) / gridDim.x);
+  const int r1 = (int)(((long long)rows * (blockIdx.x + 1)) / gridDim.x);
+  if (r0 >= r1) return;
+  const int n0 = r0 / p.H, y0 = r0 - n0 * p.H;
+  uint32_t hs[4], rs[4];                                      // rows per image and vectors per row of term t
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (t < p.nt) {
-        const int s = p.sh[t];
-        const size_t off = (((size_t)n * (p.H >> s) + (yy >> s)) * (p.W >> s) + (xx >> s)) * p.C + cv * E;
-        Vec16B<T> v;
-        v.load((const T*)p.t[t] + off);
-        // first term initialises (reference: y = x[0] ... then y = y + term)
+  for (int t = 0; t < 4; ++t) { hs[t] = (uint32_t)(p.H >> p.sh[t]); rs[t] = (uint32_t)((p.W >> p.sh[t]) * CV); }
+  for (int i = threadIdx.x; i < rowv; i += blockDim.x) {
+    const int xx = i / CV, cv = i - xx * CV;
+    uint32_t col[4];                                          // this thread's vector inside a source row of term t
 #pragma unroll
-        for (int e = 0; e < E; ++e) a.v[e] = t == 0 ? v.v[e] : a.v[e] + v.v[e];
+    for (int t = 0; t < 4; ++t) col[t] = (uint32_t)((xx >> p.sh[t]) * CV + cv);
+    int n = n0, yy = y0;
+    uint4* dst = reinterpret_cast<uint4*>(y) + (size_t)r0 * rowv + i;
+    for (int r = r0; r < r1; ++r, dst += rowv) {
+      Vec16B<T> a;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t < p.nt) {
+          const uint32_t off = ((uint32_t)n * hs[t] + (uint32_t)(yy >> p.sh[t])) * rs[t] + col[t];
+          Vec16B<T> v;
+          v.load(reinterpret_cast<const T*>(reinterpret_cast<const uint4*>(p.t[t]) + off));
+          // first term initialises (reference: y = x[0] ... then y = y + term)
+#pragma unroll
+          for (int e = 0; e < E; ++e) a.v[e] = t == 0 ? v.v[e] : a.v[e] + v.v[e];
+        }
       }
-    }
-    if (p.relu) {
+      if (p.relu) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) a.v[e] = fmaxf(a.v[e], 0.f);
+        for (int e = 0; e < E; ++e) a.v[e] = fmaxf(a.v[e], 0.f);
+      }
+      a.store(reinterpret_cast<T*>(dst));
+      if (++yy == p.H) { yy = 0; ++n; }
     }
-    a.store(y + (size_t)i * E);
   }
 }
 
@@ -423,7 +439,8 @@ int launch_fuse_sum(const capf_op& op, cudaStream_t st) {
   if (total >= (1ull << 31)) return set_error(CAPF_ERR_UNSUPPORTED, "fuse_sum: tensor too large for 32-bit indexing");
   for (int t = 0; t < p.nt; ++t)
     if ((uintptr_t)p.t[t] & 15) return set_error(CAPF_ERR_ARG, "fuse_sum: terms must be 16-byte aligned");
-  int blocks = (int)((total + 255) / 256 < (size_t)num_sms() * 16 ? (total + 255) / 256 : (size_t)num_sms() * 16);
+  const long long rows = (long long)p.N * p.H;                 // a block owns whole output rows
+  int blocks = (int)(rows < (long long)num_sms() * 16 ? rows : (long long)num_sms() * 16);
   if (blocks < 1) blocks = 1;
   switch (op.dtype_out) {
     case CAPF_F32: launch_k(fuse_sum_kernel<float>, dim3(blocks), dim3(256), 0, st, p, (float*)op.out[0]); break;

@@ -102,7 +102,28 @@ def test_fuse_sum(dt):
     want = F.relu(want)
     out = torch.empty(N, H, W, C, dtype=dt, device=DEV)
     run_op(lib.OP_FUSE_SUM, dt, dt, [N, H, W, C, 4, 0, 1, 2, 3, 1], [], [t.to(DEV) for t in terms], [out])
-    assert rel_l2(out.float().cpu(), want.to(dt).float()) < 1e-6 if dt == torch.float32 else 1e-3
+    assert rel_l2(out.float().cpu(), want.to(dt).float()) < (1e-6 if dt == torch.float32 else 1e-3)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 8, 48, (0, 1, 2, 3)), (5, 64, 64, 32, (0, 1, 2, 3)), (3, 32, 32, 64, (0, 0, 1, 2)), (300, 8, 8, 256, (0, 0, 0, 0)),
+                                   (2, 96, 72, 48, (0, 1, 2)), (3, 24, 18, 192, (0, 0, 0)), (1, 4, 4, 16, (0, 1)), (7, 16, 16, 128, (0, 0, 0, 1))],
+                         ids=lambda s: "x".join(str(v) for v in s[:4]) + f"_t{len(s[4])}")
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16, torch.float32], ids=["f16", "bf16", "f32"])
+def test_fuse_sum_rows_kernel_is_exact(shape, dt):
+    """HighResolutionModule fuse (pose_hrnet.py:294-301): fp32 sum of the terms in order, nearest-upsampled on the fly, ReLU, one
+    rounding -- exactly the torch expression, for rows of 256 vectors (the benchmark shapes), longer and shorter rows, channel
+    counts that are not powers of two, more rows than blocks and 2..4 terms."""
+    N, H, W, C, shifts = shape
+    g = _gen(sum(shape[:4]))
+    terms = [torch.randn(N, H >> s, W >> s, C, generator=g).to(dt) for s in shifts]
+    want = None
+    for s, t in zip(shifts, terms):
+        u = t.float().repeat_interleave(1 << s, 1).repeat_interleave(1 << s, 2) if s else t.float()
+        want = u if want is None else want + u
+    want = F.relu(want).to(dt)
+    out = torch.full((N, H, W, C), float("nan"), dtype=dt, device=DEV)
+    run_op(lib.OP_FUSE_SUM, dt, dt, [N, H, W, C, len(shifts)] + list(shifts) + [0] * (4 - len(shifts)) + [1], [], [t.to(DEV) for t in terms], [out])
+    assert torch.equal(out.cpu(), want)
 
 
 def test_maxpool_and_bilinear():
