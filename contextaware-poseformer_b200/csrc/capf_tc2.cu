@@ -32,6 +32,10 @@ constexpr int T2_A_BYTES = 128 * 128;       // A stage of one CTA: 128 rows x 64
 struct Tc2P {
   int M, K, Cout, BN, n_tiles_n, num_tiles, num_k, num_stages, nacc, tmem_cols;
   int stage_bytes, stg_bufs, act;
+  // conv mode (3x3 / stride 1 / pad 1 over WHOLE small images: H * W divides 128, e.g. the 8 x 8 maps of HRNet's 256-channel branch):
+  // a CTA's 128 rows are img_per_cta complete images = contiguous NHWC rows, so only the A loads differ from the Linear case --
+  // K step ks = (tap, 64-channel chunk) is one 4-D box {64, W, H, img_per_cta} at (chunk, s - 1, r - 1, image), zero-filled outside
+  int conv, cpt, img_hw;
   uint32_t idesc, desc_hi, stg_off, bias_off;
   const float* bias;
   const void* res;
@@ -115,17 +119,28 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       pdl_wait();
       if (tr) p.trace[3] = clock64();
       uint32_t stage = 0, phase = 0;
+      const uint64_t pol_a = ptx::policy_evict_last();          // conv mode: every input pixel is fetched once per tap
       for (int tile = t0; tile < t1; ++tile) {
         const int n_tile = tile % p.n_tiles_n, m_tile = tile / p.n_tiles_n;
         const int m0 = m_tile * 256 + (int)rank * 128;
         const int nb0 = n_tile * p.BN + (int)rank * half_bn;
+        const int img0 = p.conv ? m0 / p.img_hw : 0;
+        int cc = 0, tap_s = 0, tap_r = 0;                        // conv mode: channel chunk inside the tap, filter column / row
         for (int ks = 0; ks < p.num_k; ++ks) {
           const bool primed = tile == t0 && ks < pre;
           if (!primed) ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t full_leader = ptx2::mapa(bar_full + 8 * stage, 0u);
           if (leader && !primed) ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(2 * p.stage_bytes));
           const uint32_t a_dst = stage0 + stage * p.stage_bytes;
-          ptx2::tma_load_2d_2sm(&mapA, full_leader, a_dst, ks * 64, m0);
+          if (p.conv) {
+            ptx2::tma_load_4d_2sm_hint(&mapA, full_leader, a_dst, cc * 64, tap_s - 1, tap_r - 1, img0, pol_a);
+            if (++cc == p.cpt) {
+              cc = 0;
+              if (++tap_s == 3) { tap_s = 0; ++tap_r; }
+            }
+          } else {
+            ptx2::tma_load_2d_2sm(&mapA, full_leader, a_dst, ks * 64, m0);
+          }
           if (!primed) ptx2::tma_load_2d_2sm(&mapB, full_leader, a_dst + T2_A_BYTES, ks * 64, nb0);
           if (tr) { const int n = (tile - t0) * p.num_k + ks; if (n < 64) p.trace[64 + n] = clock64(); }
           if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1u; }
@@ -287,8 +302,16 @@ int tc2_supported(const capf_op& op) {
   const char* ev = getenv("CAPF_TC2");
   if (ev && ev[0] == '0') return 0;
   if (op.i[17] == 1) return 0;                                  // i[17]: 1 = never, 2 = force (tests)
-  if (op.kind != CAPF_OP_CONV2D || op.i[5] != 1 || op.i[6] != 1 || op.i[7] != 1 || op.i[8] != 0) return 0;
   if (op.dtype_in != CAPF_F16 && op.dtype_in != CAPF_BF16) return 0;
+  if (op.kind == CAPF_OP_CONV2D && op.i[5] == 3 && op.i[6] == 3 && op.i[7] == 1 && op.i[8] == 1) {
+    // conv mode: whole small images per CTA (see Tc2P); taken by default for the 256-channel branch, whose per-tap launches are bound by
+    // every CTA streaming the whole 1.2 MB weight matrix for 128 rows -- a pair streams half of it per CTA
+    const int hw = op.i[1] * op.i[2], Cin = op.i[3], N = op.i[4];
+    if (hw < 1 || hw > 128 || 128 % hw || Cin % 64 || N % 16 || op.i[0] < 1) return 0;
+    if (op.i[17] == 2) return 1;
+    return (Cin >= 256 && N >= 256 && (long long)op.i[0] * hw >= 2048) ? 1 : 0;
+  }
+  if (op.kind != CAPF_OP_CONV2D || op.i[5] != 1 || op.i[6] != 1 || op.i[7] != 1 || op.i[8] != 0) return 0;
   const int M = op.i[0] * op.i[1] * op.i[2], K = op.i[3], N = op.i[4];
   if (K % 64 || N % 16 || M < 1) return 0;
   if (op.i[17] == 2) return 1;
@@ -304,6 +327,8 @@ int tc2_prepare(const capf_op& op, Tc2State** out) {
   Tc2P& p = s->p;
   memset(&p, 0, sizeof(p));
   p.M = op.i[0] * op.i[1] * op.i[2]; p.K = op.i[3]; p.Cout = op.i[4];
+  p.conv = op.i[5] == 3 ? 1 : 0;
+  if (p.conv) { p.cpt = op.i[3] / 64; p.img_hw = op.i[1] * op.i[2]; p.K = 9 * op.i[3]; }
   p.act = op.i[11];
   p.bias = (const float*)op.in[2];
   p.res = op.in[3];
@@ -364,7 +389,14 @@ int tc2_prepare(const capf_op& op, Tc2State** out) {
   s->grid = 2 * g;
   s->dtype_out = op.dtype_out;
   const CUtensorMapDataType dt = op.dtype_in == CAPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  {
+  if (p.conv) {
+    const int Cin = op.i[3], H = op.i[1], W = op.i[2];
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)op.i[0]};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)H, (cuuint32_t)(128 / p.img_hw)};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    e = tc_encode_map(&s->mapA, dt, 4, op.in[0], dims, strides, box, es, 128, "A whole-image boxes (2-CTA)");
+  } else {
     cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
     cuuint64_t strides[1] = {(cuuint64_t)p.K * 2};
     cuuint32_t box[2] = {64, 128};
@@ -432,7 +464,7 @@ int tc2_launch(const Tc2State* s, cudaStream_t st) {
 void tc2_release(Tc2State* s) { delete s; }
 
 void tc2_describe(const Tc2State* s, char* buf, int cap) {
-  snprintf(buf, cap, "tc_gemm2_kernel[2-CTA 256x%d tile, %d stages]", s->p.BN, s->p.num_stages);
+  snprintf(buf, cap, "tc_gemm2_kernel[2-CTA 256x%d tile, %d stages%s]", s->p.BN, s->p.num_stages, s->p.conv ? ", 3x3 over whole-image boxes" : "");
 }
 
 }  // namespace capf

@@ -78,6 +78,19 @@ HALO256_CASES = [
 ]
 
 
+# 3x3 / stride 1 / pad 1 over WHOLE small images (H * W divides 128) on CTA pairs (csrc/capf_tc2.cu, conv mode): the 256-channel
+# branch of HRNet at 8 x 8 takes it by default, the other shapes are forced (i[17] = 2)
+TC2CONV_CASES = [
+    ("t2c_c256_8x8_auto", (64, 8, 8, 256, 256, 3, 1), lib.ACT_RELU, True, False),
+    ("t2c_c256_8x8_n5_ragged", (5, 8, 8, 256, 256, 3, 1), lib.ACT_RELU, True, False),
+    ("t2c_c256_8x8_nores", (9, 8, 8, 256, 256, 3, 1), lib.ACT_RELU, False, False),
+    ("t2c_c64_4x4", (19, 4, 4, 64, 64, 3, 1), lib.ACT_NONE, True, False),
+    ("t2c_c128_8x4_n48", (7, 8, 4, 128, 48, 3, 1), lib.ACT_RELU, False, False),
+    ("t2c_c64_2x2_wide", (300, 2, 2, 64, 512, 3, 1), lib.ACT_NONE, False, False),
+    ("t2c_c192_8x8", (11, 8, 8, 192, 192, 3, 1), lib.ACT_RELU, True, False),
+]
+
+
 def run_tc_case(case, dt=torch.float16, impl=None, variant=0, epi=0, msub=0, bn=0, two=0, inplace=False):
     """Returns (rel_l2, max_abs, frac_bad_rows) of the tcgen05 kernel against the fp32 reference.
     inplace: the output buffer IS the residual buffer (how plan_memory runs a residual whose last reader is this op)."""

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from tc_cases import HALO128_CASES, HALO256_CASES, HALO_CASES, TC_CASES, run_tc_case
+from tc_cases import HALO128_CASES, HALO256_CASES, HALO_CASES, TC2CONV_CASES, TC_CASES, run_tc_case
 
 pytestmark = pytest.mark.gpu
 
@@ -97,6 +97,24 @@ def test_halo256_conv_matches_fp32_reference(case, dt):
     rel1, _, _ = run_tc_case(case, dt, variant=1)
     assert abs(rel - rel1) < 0.05 * rel1 + 1e-6
     assert _dispatched_kernel(case).startswith("tc_conv3_halo256_kernel")
+
+
+@pytest.mark.parametrize("case", TC2CONV_CASES, ids=[c[0] for c in TC2CONV_CASES])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_pair_gemm_conv_mode_matches_fp32_reference(case, dt):
+    """3x3 convolutions over whole small images on CTA pairs (cta_group::2; HRNet's 256-channel branch at 8 x 8,
+    pose_hrnet.py:79-95): per K step one 4-D TMA box per CTA (zero fill = padding), half of the weight tile per CTA.  Against plain
+    fp32 PyTorch, and bit for bit against the per-tap kernel (same K order, same fp32 accumulation); the residual may be updated
+    in place."""
+    rel, max_abs, bad_rows = run_tc_case(case, dt, two=2)
+    print(f"{case[0]} {dt}: rel-L2 {rel:.3e} max-abs {max_abs:.3e} bad-rows {bad_rows:.4f}")
+    assert bad_rows == 0.0 and rel < (1.5e-3 if dt == torch.float16 else 8e-3)
+    rel1, max1, _ = run_tc_case(case, dt, variant=1, two=1)
+    assert rel == rel1 and max_abs == max1
+    if case[3]:
+        assert run_tc_case(case, dt, two=2, inplace=True)[0] == rel
+    if "auto" in case[0]:
+        assert _dispatched_kernel(case).startswith("tc_gemm2_kernel")
 
 
 @pytest.mark.parametrize("M,C1,C2,Cout", [(1000, 64, 64, 256), (4096, 128, 256, 256), (300, 64, 256, 256), (129, 32, 16, 48), (5000, 512, 256, 1024)])
