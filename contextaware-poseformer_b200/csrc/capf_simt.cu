@@ -962,6 +962,179 @@ __global__ void __launch_bounds__(128) attention17_kernel(int groups, int heads,
   }
 }
 
+// ---- attention over the 17 joints of a frame on the warp-level tensor-core path (mma.sync m16n8k16) ----------------------------
+// The kernel above spends ~9 k instructions per lane on 17 x 17 x 80 scalar FMAs and half->float conversions (30 us per joint
+// block at bs = 256, instruction-bound with 15 of 32 lanes idle).  Here one warp still owns a (frame, head) pair, but
+//   S = Q K^T   is 2 x 3 x 5 MMAs (queries padded to 32 rows, keys to 24; padded rows re-read row 16, so no value is ever NaN),
+//   softmax     runs on the accumulator fragments (a row lives in the 4 lanes of a quad: two shuffles per reduction),
+//   O = P V     re-uses the S fragments as the A operand (two 16 x 8 C tiles = one 16 x 16 A tile) with P SPLIT into
+//               hi = T(p) and lo = T(p - hi): two MMAs per tile keep P at fp32-class precision (2^-22 / 2^-16 for fp16 / bf16),
+//               so the result matches the fp32-math kernel to the output rounding; V fragments come from ldmatrix.trans.
+// tcgen05 is the wrong tool for 17 x 17 problems (M = 128 minimum); this is the one place the legacy warp MMA is the right size.
+template <typename T> struct Mma16816;
+template <> struct Mma16816<__half> {
+  static __device__ __forceinline__ void run(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  static __device__ __forceinline__ uint32_t pack2(float x, float y) { const __half2 h = __floats2half2_rn(x, y); return *reinterpret_cast<const uint32_t*>(&h); }
+};
+template <> struct Mma16816<__nv_bfloat16> {
+  static __device__ __forceinline__ void run(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  static __device__ __forceinline__ uint32_t pack2(float x, float y) { const __nv_bfloat162 h = __floats2bfloat162_rn(x, y); return *reinterpret_cast<const uint32_t*>(&h); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) attention17_mma_kernel(int groups, int heads, int grp_stride, float scale, const T* __restrict__ qkv,
+                                                              T* __restrict__ out) {
+  pdl_wait();
+  constexpr int SEQ = 17, HD = 80, LD = 88;      // rows padded to 176 bytes: the 32-bit fragment loads of a quad-row pattern hit 32 distinct banks
+  __shared__ __align__(16) T sq[4][SEQ * LD];
+  __shared__ __align__(16) T sk[4][SEQ * LD];
+  __shared__ __align__(16) T sv[4][SEQ * LD];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * 4 + wib;
+  if (item >= (long long)groups * heads) return;
+  const int g = (int)(item / heads), h = (int)(item % heads);
+  const int D = heads * HD;
+  const T* base = qkv + (size_t)g * grp_stride * (3 * D) + h * HD;       // token t: + t * 3D (tok_stride == 1)
+  T* const q_s = sq[wib];
+  T* const k_s = sk[wib];
+  T* const v_s = sv[wib];
+  for (int c = lane; c < SEQ * (HD / 8); c += 32) {
+    const int t = c / (HD / 8), k = c - t * (HD / 8);
+    const T* src = base + (size_t)t * (3 * D) + 8 * k;
+    *reinterpret_cast<uint4*>(q_s + t * LD + 8 * k) = __ldg(reinterpret_cast<const uint4*>(src));
+    *reinterpret_cast<uint4*>(k_s + t * LD + 8 * k) = __ldg(reinterpret_cast<const uint4*>(src + D));
+    *reinterpret_cast<uint4*>(v_s + t * LD + 8 * k) = __ldg(reinterpret_cast<const uint4*>(src + 2 * D));
+  }
+  __syncwarp();
+  const int gid = lane >> 2, t4 = lane & 3;
+  auto ld32 = [](const T* p) { return *reinterpret_cast<const uint32_t*>(p); };
+  // ---- S = Q K^T: s[mt][nt] = rows 16 mt + {gid, gid + 8}, keys 8 nt + 2 t4 + {0, 1}
+  float s[2][3][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < HD / 16; ++kk) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r0 = min(16 * mt + gid, SEQ - 1), r1 = min(16 * mt + gid + 8, SEQ - 1);
+      a[mt][0] = ld32(q_s + r0 * LD + 16 * kk + 2 * t4);
+      a[mt][1] = ld32(q_s + r1 * LD + 16 * kk + 2 * t4);
+      a[mt][2] = ld32(q_s + r0 * LD + 16 * kk + 8 + 2 * t4);
+      a[mt][3] = ld32(q_s + r1 * LD + 16 * kk + 8 + 2 * t4);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      const int n = min(8 * nt + gid, SEQ - 1);
+      const uint32_t b0 = ld32(k_s + n * LD + 16 * kk + 2 * t4), b1 = ld32(k_s + n * LD + 16 * kk + 8 + 2 * t4);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) Mma16816<T>::run(s[mt][nt], a[mt], b0, b1);
+    }
+  }
+  // ---- softmax over the 17 keys of every row; P fragments (hi | lo) for the second GEMM
+  uint32_t phi[2][4][2], plo[2][4][2];            // [mt][key tile 0..3][row half]: keys 8 nt + 2 t4 + {0, 1}
+  float inv[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      float v[3][2], mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool ok = 8 * nt + 2 * t4 + e < SEQ;
+          v[nt][e] = ok ? s[mt][nt][2 * hr + e] * scale : -INFINITY;
+          mx = fmaxf(mx, v[nt][e]);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float den = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { v[nt][e] = __expf(v[nt][e] - mx); den += v[nt][e]; }      // exp(-inf) = 0 for the padded keys
+      den += __shfl_xor_sync(0xffffffffu, den, 1);
+      den += __shfl_xor_sync(0xffffffffu, den, 2);
+      inv[mt][hr] = 1.0f / den;
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) Mma16816<T>::split2(v[nt][0], v[nt][1], phi[mt][nt][hr], plo[mt][nt][hr]);
+      phi[mt][3][hr] = 0u;
+      plo[mt][3][hr] = 0u;
+    }
+  }
+  // ---- O = P V: o[mt][ct] = rows 16 mt + {gid, gid + 8}, channels 8 ct + 2 t4 + {0, 1}
+  float o[2][HD / 8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ct = 0; ct < HD / 8; ++ct)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][ct][e] = 0.f;
+  const uint32_t v_addr = (uint32_t)__cvta_generic_to_shared(v_s);
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      ah[mt][0] = phi[mt][2 * ks][0]; ah[mt][1] = phi[mt][2 * ks][1]; ah[mt][2] = phi[mt][2 * ks + 1][0]; ah[mt][3] = phi[mt][2 * ks + 1][1];
+      al[mt][0] = plo[mt][2 * ks][0]; al[mt][1] = plo[mt][2 * ks][1]; al[mt][2] = plo[mt][2 * ks + 1][0]; al[mt][3] = plo[mt][2 * ks + 1][1];
+    }
+    // ldmatrix row address of this lane: lanes 0-7 = keys 16 ks + lane, lanes 8-15 = keys 16 ks + 8 + (lane - 8); padded keys re-read row 16 (P = 0 there)
+    const int key = min(16 * ks + (lane & 15), SEQ - 1);
+    const uint32_t row_addr = v_addr + (uint32_t)(key * LD) * (uint32_t)sizeof(T);
+#pragma unroll
+    for (int ct = 0; ct < HD / 8; ++ct) {
+      uint32_t b0, b1;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(row_addr + 16u * ct));
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        Mma16816<T>::run(o[mt][ct], ah[mt], b0, b1);
+        Mma16816<T>::run(o[mt][ct], al[mt], b0, b1);
+      }
+    }
+  }
+  // ---- out[row][h * 80 + channel] = o / den
+  T* const obase = out + (size_t)g * grp_stride * D + h * HD;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int row = 16 * mt + gid + 8 * hr;
+      if (row < SEQ) {
+        const float sc = inv[mt][hr];
+#pragma unroll
+        for (int ct = 0; ct < HD / 8; ++ct)
+          *reinterpret_cast<uint32_t*>(obase + (size_t)row * D + 8 * ct + 2 * t4) = Mma16816<T>::pack2(o[mt][ct][2 * hr] * sc, o[mt][ct][2 * hr + 1] * sc);
+      }
+    }
+  }
+}
+
 // Attention over the 5 level tokens of one joint (pose_dformer.py:231-234; 8 heads x 16): one LANE per (joint, head), a
 // warp covers 4 joints.  q/k/v of a lane are 15 x 32 bytes, loaded straight into registers (the 8 heads of a token are
 // 256 contiguous bytes, so a warp's loads are full sectors); no shared memory, no synchronisation.
@@ -1034,6 +1207,12 @@ static int attention_fast(const capf_op& op, cudaStream_t st, bool& taken) {
   T* out = (T*)op.out[0];
   if (seq == 17 && hd == 80 && ts == 1) {
     const long long items = (long long)groups * heads;
+    static const bool use_mma = []() { const char* ev = getenv("CAPF_ATTN_MMA"); return !(ev && ev[0] == '0'); }();
+    if (use_mma) {
+      launch_k(attention17_mma_kernel<T>, dim3((unsigned)((items + 3) / 4)), dim3(128), 0, st, groups, heads, gs, op.f[0], qkv, out);
+      taken = true;
+      return check_launch("attention17_mma");
+    }
     launch_k(attention17_kernel<T, 10>, dim3((unsigned)((items + 3) / 4)), dim3(128), 0, st, groups, heads, gs, op.f[0], qkv, out);
     taken = true;
     return check_launch("attention17");

@@ -210,6 +210,10 @@ def test_attention_16bit(seq, heads, hd, groups, dt):
     out = torch.full((rows, D), float("nan"), dtype=dt, device=DEV)
     run_op(lib.OP_ATTENTION, dt, dt, [groups, seq, heads, hd, ts, gs], [hd ** -0.5], [qkv.to(DEV)], [out])
     assert rel_l2(out.float().cpu(), want) < (1e-3 if dt == torch.float16 else 6e-3)
+    if seq == 17 and hd == 80:
+        # warp-MMA kernel (mma.sync m16n8k16, P split into hi + lo): fp32-class arithmetic, so what is left is the rounding of the output
+        rounding = rel_l2(want.to(dt).float(), want)
+        assert rel_l2(out.float().cpu(), want) < 1.15 * rounding + 1e-6
 
 
 def test_samplers_match_aten_values():
