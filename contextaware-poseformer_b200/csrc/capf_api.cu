@@ -87,6 +87,7 @@ static int dispatch(const capf_op& op, const TcConvState* tc, cudaStream_t st) {
       return launch_conv_simt(op, st);
     case CAPF_OP_BASICBLOCK: return tc_conv_launch(op, tc, st);
     case CAPF_OP_EXPAND_REDUCE: return tc_conv_launch(op, tc, st);
+    case CAPF_OP_MLP: return tc_conv_launch(op, tc, st);
     case CAPF_OP_FUSE_SUM: return launch_fuse_sum(op, st);
     case CAPF_OP_MAXPOOL3X3S2: return launch_maxpool(op, st);
     case CAPF_OP_BILINEAR: return launch_bilinear(op, st);
@@ -177,6 +178,13 @@ int capf_plan_create(const capf_op* ops, int n_ops, int device, capf_plan** out_
         return e;
       }
     }
+    if (op.kind == CAPF_OP_MLP) {
+      e = tc_mlpop_prepare(op, &pl->tc[k]);
+      if (e) {
+        capf_plan_destroy(pl);
+        return e;
+      }
+    }
     if (op.kind == CAPF_OP_CONV2D && op.i[12] != CAPF_IMPL_TCGEN05 && op.i[20] != 0) {
       capf_plan_destroy(pl);
       return set_errorf(CAPF_ERR_UNSUPPORTED, "op %d: output segments (i[20]) need the tcgen05 kernel", k);
@@ -228,6 +236,7 @@ int capf_plan_op_kernel(const capf_plan* plan, int k, char* buf, int cap) {
       break;
     case CAPF_OP_BASICBLOCK: tc_conv_describe(plan->tc[k], buf, cap); break;
     case CAPF_OP_EXPAND_REDUCE: tc_conv_describe(plan->tc[k], buf, cap); break;
+    case CAPF_OP_MLP: tc_conv_describe(plan->tc[k], buf, cap); break;
     case CAPF_OP_FUSE_SUM: snprintf(buf, cap, "fuse_sum_kernel"); break;
     case CAPF_OP_MAXPOOL3X3S2: snprintf(buf, cap, "maxpool3x3s2_kernel"); break;
     case CAPF_OP_BILINEAR: snprintf(buf, cap, "bilinear_ac_kernel"); break;

@@ -73,6 +73,7 @@ int tc_conv_prepare(const capf_op& op, TcConvState** out);
 int tc_block_supported(const capf_op& op);            // fused BasicBlock op (capf_tc_block.cu)
 int tc_blockop_prepare(const capf_op& op, TcConvState** out);
 int tc_chainop_prepare(const capf_op& op, TcConvState** out);   // CAPF_OP_EXPAND_REDUCE (capf_tc_chain.cu)
+int tc_mlpop_prepare(const capf_op& op, TcConvState** out);     // CAPF_OP_MLP (capf_tc_mlp.cu)
 int tc_conv_launch(const capf_op& op, const TcConvState* s, cudaStream_t st);
 void tc_conv_release(TcConvState* s);
 void tc_conv_describe(const TcConvState* s, char* buf, int cap);   // kernel name + tile shape

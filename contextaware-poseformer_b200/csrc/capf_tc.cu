@@ -480,6 +480,7 @@ struct TcConvState {
   Tc2State* two = nullptr;       // non-null: the op runs on the 2-CTA GEMM kernel (capf_tc2.cu)
   TcBlockState* blk = nullptr;   // non-null: a fused BasicBlock op (capf_tc_block.cu)
   TcChainState* chain = nullptr; // non-null: a CAPF_OP_EXPAND_REDUCE op (capf_tc_chain.cu)
+  TcMlpState* mlp = nullptr;     // non-null: a CAPF_OP_MLP op (capf_tc_mlp.cu)
   CUtensorMap mapA, mapB, mapA2;
   TcP p;
   int grid;
@@ -592,6 +593,16 @@ int tc_chainop_prepare(const capf_op& op, TcConvState** out) {
   TcConvState* s = new (std::nothrow) TcConvState();
   if (!s) return set_error(CAPF_ERR_ARG, "tc_chainop_prepare: out of host memory");
   int e = tc_chain_prepare(op, &s->chain);
+  if (e) { delete s; return e; }
+  *out = s;
+  return CAPF_OK;
+}
+
+int tc_mlpop_prepare(const capf_op& op, TcConvState** out) {
+  *out = nullptr;
+  TcConvState* s = new (std::nothrow) TcConvState();
+  if (!s) return set_error(CAPF_ERR_ARG, "tc_mlpop_prepare: out of host memory");
+  int e = tc_mlp_prepare(op, &s->mlp);
   if (e) { delete s; return e; }
   *out = s;
   return CAPF_OK;
@@ -827,6 +838,7 @@ int tc_conv_launch(const capf_op&, const TcConvState* s, cudaStream_t st) {
   if (!s) return set_error(CAPF_ERR_ARG, "tc conv: op was not prepared");
   if (s->blk) return tc_block_launch(s->blk, st);
   if (s->chain) return tc_chain_launch(s->chain, st);
+  if (s->mlp) return tc_mlp_launch(s->mlp, st);
   if (s->two) return tc2_launch(s->two, st);
   if (s->halo) return tc_halo_launch(s->halo, st);
   if (s->h128) return tc_halo128_launch(s->h128, st);
@@ -843,6 +855,7 @@ void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
   if (!s) { snprintf(buf, cap, "?"); return; }
   if (s->blk) { tc_block_describe(s->blk, buf, cap); return; }
   if (s->chain) { tc_chain_describe(s->chain, buf, cap); return; }
+  if (s->mlp) { tc_mlp_describe(s->mlp, buf, cap); return; }
   if (s->two) { tc2_describe(s->two, buf, cap); return; }
   if (s->halo) { tc_halo_describe(s->halo, buf, cap); return; }
   if (s->h128) { tc_halo128_describe(s->h128, buf, cap); return; }
@@ -854,6 +867,7 @@ void tc_conv_describe(const TcConvState* s, char* buf, int cap) {
 void tc_conv_release(TcConvState* s) {
   if (s && s->blk) tc_block_release(s->blk);
   if (s && s->chain) tc_chain_release(s->chain);
+  if (s && s->mlp) tc_mlp_release(s->mlp);
   if (s && s->two) tc2_release(s->two);
   if (s && s->halo) tc_halo_release(s->halo);
   if (s && s->h128) tc_halo128_release(s->h128);

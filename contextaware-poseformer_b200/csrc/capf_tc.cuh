@@ -533,6 +533,14 @@ void tc_chain_release(TcChainState* s);
 void tc_chain_describe(const TcChainState* s, char* buf, int cap);
 
 // 2-CTA (cta_group::2) GEMM for the wide lifter Linears (capf_tc2.cu)
+// fused Mlp of a 128-wide transformer block: fc1 + GELU + fc2 + residual (capf_tc_mlp.cu)
+struct TcMlpState;
+int tc_mlp_supported(const capf_op& op);
+int tc_mlp_prepare(const capf_op& op, TcMlpState** out);
+int tc_mlp_launch(const TcMlpState* s, cudaStream_t st);
+void tc_mlp_release(TcMlpState* s);
+void tc_mlp_describe(const TcMlpState* s, char* buf, int cap);
+
 struct Tc2State;
 int tc2_supported(const capf_op& op);
 int tc2_prepare(const capf_op& op, Tc2State** out);

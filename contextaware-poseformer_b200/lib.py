@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcapf_b200.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # enums (mirror capf_b200.h)
 F32, F16, BF16 = 0, 1, 2
@@ -18,7 +18,7 @@ IMPL_SIMT, IMPL_TCGEN05 = 0, 1
 (OP_CONV2D, OP_FUSE_SUM, OP_MAXPOOL, OP_BILINEAR, OP_LAYERNORM, OP_ATTENTION, OP_REF_SAMPLE,
  OP_DEFORM_SAMPLE, OP_EMBED_COORD, OP_LEVELS_TO_JOINT, OP_CROP_NORMALIZE, OP_CAST, OP_PREPROCESS_U8, OP_BASICBLOCK, OP_WARP_AFFINE_U8, OP_POSE_ERRORS,
  OP_GEMM_F32, OP_COLSUM, OP_LAYERNORM_BWD, OP_GELU, OP_GELU_BWD, OP_ATTENTION_BWD, OP_DEFORM_BWD, OP_ROWS_AXPY, OP_JOINT_TO_LEVELS,
- OP_ADAMW, OP_EXPAND_REDUCE) = range(1, 28)
+ OP_ADAMW, OP_EXPAND_REDUCE, OP_MLP) = range(1, 29)
 
 DTYPE_CODE = {"f32": F32, "f16": F16, "bf16": BF16}
 

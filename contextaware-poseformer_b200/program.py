@@ -466,6 +466,8 @@ def build_forward_program(backbone: str, bb_cfg, pf_cfg, shapes: dict, B: int, H
               WSlot("b:head.1", (3,), "f32", vec_packer([vn + "head.1.bias"]))], [out],
              tag=vn + "head", flops=2 * R * E * 3)
     prog.outputs["out"] = out
+    if pb.use_tc:
+        fuse_mlp(prog, prog.n_backbone_ops)
     assign_lanes(prog, _lanes_enabled())
     return prog
 
@@ -619,6 +621,51 @@ def fuse_expand_reduce(prog: Program):
                     tag=a.tag + "+" + ".".join(b.tag.rsplit(".", 2)[-2:]), flops=a.flops + b.flops,
                     nbytes=a.ins[0].nbytes + a.ins[3].nbytes + a.outs[0].nbytes + b.outs[0].nbytes + wbytes)
             out.append(op)
+            fused += 1
+            k += 2
+        else:
+            out.append(a)
+            k += 1
+    prog.ops[:] = out
+    return fused
+
+
+# ------------------------------------------------------------------------------------------------------
+# peephole: Mlp of a 128-wide transformer block (fc1 + GELU -> fc2 + residual) -> one kernel
+# ------------------------------------------------------------------------------------------------------
+def fuse_mlp(prog: Program, first: int = 0):
+    """The Mlp of the DeformableBlocks and of the res blocks (pose_dformer.py:25-31, :138-141, :78) is x + fc2(gelu(fc1(norm2(x)))) with
+    128 -> 256 -> 128 features: two GEMM launches whose hidden tensor makes an HBM round trip and which each pay the fixed cost of a
+    tcgen05 kernel for ~1 us of tensor work.  Both become ONE CAPF_OP_MLP (csrc/capf_tc_mlp.cu): the hidden tile stays in shared
+    memory, the fp32 token stream is updated in place.  Bit-identical results.  CAPF_FUSE_MLP=0 keeps the two-op form."""
+    if os.environ.get("CAPF_FUSE_MLP", "1") == "0":
+        return 0
+    ops = prog.ops
+    readers = {}
+    for op in ops:
+        for b in op.ins:
+            if isinstance(b, Buf):
+                readers[b.root] = readers.get(b.root, 0) + 1
+
+    def rows_linear(op, cin, cout, act):
+        return (op.kind == lib.OP_CONV2D and op.i[12] == lib.IMPL_TCGEN05 and op.i[1:3] == [1, 1] and op.i[5:9] == [1, 1, 1, 0] and op.i[3] == cin
+                and op.i[4] == cout and op.i[11] == act and not any(op.i[13:]) and all(x is None for x in op.ins[4:]) and op.ins[2] is not None)
+
+    out, k, fused = list(ops[:first]), first, 0
+    while k < len(ops):
+        a = ops[k]
+        b = ops[k + 1] if k + 1 < len(ops) else None
+        ok = (b is not None and rows_linear(a, 128, 256, lib.ACT_GELU) and rows_linear(b, 256, 128, lib.ACT_NONE)
+              and a.dtype_in in ("f16", "bf16") and a.dtype_out == a.dtype_in and b.dtype_in == a.dtype_in and b.dtype_out == "f32"
+              and a.ins[3] is None and isinstance(b.ins[3], Buf) and _same_buf(b.ins[3], b.outs[0]) and _same_buf(b.ins[0], a.outs[0])
+              and a.i[0] == b.i[0] and readers.get(a.outs[0].root, 0) == 1 and a.outs[0].role == "act")
+        if ok:
+            rows = a.i[0]
+            wbytes = sum(int(np.prod(w.shape)) * _ITEMSIZE[w.dtype] for w in (a.ins[1], b.ins[1]))
+            out.append(Op(lib.OP_MLP, a.dtype_in, "f32", [rows, 128, 256, 128], [],
+                          [a.ins[0], a.ins[1], a.ins[2], b.ins[3], b.ins[1], b.ins[2]], [b.outs[0]],
+                          tag=a.tag.rsplit(".", 1)[0], flops=a.flops + b.flops,
+                          nbytes=a.ins[0].nbytes + 2 * b.outs[0].nbytes + wbytes))
             fused += 1
             k += 2
         else:

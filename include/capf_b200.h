@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAPF_ABI_VERSION 12
+#define CAPF_ABI_VERSION 13
 
 typedef enum capf_status {
   CAPF_OK = 0,
@@ -74,7 +74,8 @@ typedef enum capf_op_kind {
   CAPF_OP_ROWS_AXPY = 24,
   CAPF_OP_JOINT_TO_LEVELS = 25,
   CAPF_OP_ADAMW = 26,
-  CAPF_OP_EXPAND_REDUCE = 27
+  CAPF_OP_EXPAND_REDUCE = 27,
+  CAPF_OP_MLP = 28
 } capf_op_kind;
 
 /*
@@ -119,6 +120,13 @@ typedef enum capf_op_kind {
  *     i[0]=rows (N*H*W)  i[1]=K1 (64)  i[2]=N1 (256)  i[3]=N2 (64)          16-bit dtypes, dtype_in == dtype_out
  *     in[0]=t [rows][K1]  in[1]=W3 [N1][K1]  in[2]=b3 [N1] f32 or NULL  in[3]=x [rows][N1]  in[4]=W1 [N2][N1]  in[5]=b1 [N2] f32 or NULL
  *     out[0]=y [rows][N1] (may alias in[3])   out[1]=u [rows][N2]
+ *
+ * CAPF_OP_MLP -- the Mlp of a 128-wide transformer block (pose_dformer.py:25-31; DeformableBlock :138-141, Block :78) as one kernel over
+ *                    token rows:  X = X + gelu(t . W1^T + b1) . W2^T + b2   (fc1 128 -> 256, GELU erf form, hidden rounded to dtype_in and kept in
+ *                    shared memory, fc2 256 -> 128, residual add in fp32).  Bit-identical to the two CAPF_OP_CONV2D ops (program.fuse_mlp emits it).
+ *     i[0]=rows  i[1]=K1 (128)  i[2]=N1 (256)  i[3]=N2 (128)      dtype_in f16 | bf16, dtype_out f32
+ *     in[0]=t [rows][K1] dtype_in (the LayerNorm output)  in[1]=W1 [N1][K1]  in[2]=b1 f32[N1] or NULL  in[3]=X [rows][N2] f32 (residual; may alias
+ *     out[0])  in[4]=W2 [N2][N1]  in[5]=b2 f32[N2] or NULL        out[0]=X [rows][N2] f32
  *
  * CAPF_OP_FUSE_SUM -- HighResolutionModule fuse  y_i = ReLU(sum_j f_ij(x_j))  (pose_hrnet.py:294-301) with the
  *                    nn.Upsample(mode='nearest') of the j>i terms (:244) applied on the fly.

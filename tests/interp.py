@@ -205,6 +205,22 @@ class Interp:
         out = self.t(op.outs[0])
         out.copy_(y.reshape(out.shape).to(out.dtype))
 
+    def _op28(self, op):  # MLP: X = X + gelu(t W1^T + b1) W2^T + b2, the expressions of the two CONV2D ops it replaces (hidden rounded to dtype_in)
+        rows, k1, n1, n2 = op.i[:4]
+        t = self.t(op.ins[0]).reshape(rows, k1)
+        w1 = self.t(op.ins[1]).float().reshape(n1, k1)
+        w2 = self.t(op.ins[4]).float().reshape(n2, n1)
+        h = F.conv2d(t.float().t().reshape(1, k1, rows, 1), w1.reshape(n1, k1, 1, 1)).reshape(n1, rows).t()
+        if op.ins[2] is not None:
+            h = h + self.t(op.ins[2])
+        h = F.gelu(h).to(t.dtype)
+        y = F.conv2d(h.float().t().reshape(1, n1, rows, 1), w2.reshape(n2, n1, 1, 1)).reshape(n2, rows).t()
+        if op.ins[5] is not None:
+            y = y + self.t(op.ins[5])
+        y = y + self.t(op.ins[3]).reshape(rows, n2).float()
+        out = self.t(op.outs[0])
+        out.copy_(y.reshape(out.shape).to(out.dtype))
+
     def _op27(self, op):  # EXPAND_REDUCE: y = relu(t W3^T + b3 + x); u = relu(y W1^T + b1), the expressions of the two CONV2D ops it replaces
         rows, k1, n1, n2 = op.i[:4]
         t = self.t(op.ins[0]).reshape(rows, k1).float()
