@@ -315,7 +315,7 @@ int tc2_supported(const capf_op& op) {
   const int M = op.i[0] * op.i[1] * op.i[2], K = op.i[3], N = op.i[4];
   if (K % 64 || N % 16 || M < 1) return 0;
   if (op.i[17] == 2) return 1;
-  return (M >= 2048 && K >= 512 && N >= 1024) ? 1 : 0;         // the joint-block qkv / fc1 Linears (1920 / 1280 wide)
+  { const char* t = getenv("CAPF_TC2_MIN_N"); const int min_n = t ? atoi(t) : 512; return (M >= 2048 && K >= 512 && N >= min_n) ? 1 : 0; }   // the joint-block Linears (qkv 1920, fc1 1280, proj / fc2 640 wide: 311 -> 290 us per forward with the 640-wide ones on pairs too)
 }
 
 int tc2_prepare(const capf_op& op, Tc2State** out) {

@@ -9,13 +9,14 @@
 //
 // Shared memory is exactly the 227 KB of an SM: W (64 KB, TIME-SHARED: W1 for GEMM 1, then W2 streams in while epilogue 1 runs the
 // GELUs, then W1 of the next tile while epilogue 2 runs) | T[2] (2 x 32 KB, the t tile: two 64-column chunks; next tile prefetched) |
-// H (64 KB, four 64-column chunks of h) | staging (4 warps x 2 x 4 KB: residual in by cp.async, result out with 16-byte
+// H (64 KB, four 64-column chunks of h) | staging (8 warps x 4 KB: residual in by cp.async, result out with 16-byte
 // coalesced stores, the epilogue of capf_tc.cu).  TMEM: GEMM 1 = two 128-column halves (epilogue 1 of half 0 overlaps the MMAs of
 // half 1), GEMM 2 = 128 columns.
 // Results are bit-identical to the two CAPF_OP_CONV2D ops (same K order, same epilogue arithmetic): tests/test_mlp.py.
 //
-// Roles (512 threads): warp 0 TMA loads, warp 1 MMA issuer, warp 2 TMEM, warps 4-11 epilogue 1 (column half x lane quadrant),
-// warps 12-15 epilogue 2 (lane quadrant).
+// Roles (640 threads): warp 0 TMA loads, warp 1 MMA issuer, warp 2 TMEM, warps 4-19 = SIXTEEN epilogue warps (lane quadrant x column
+// quarter).  All sixteen run epilogue 1 -- 32 K erff evaluations per tile are what bounds the kernel, the first version (8 warps) spent
+// ~5 us per tile there --; the warps of column quarters 0 and 1 then also run epilogue 2 (two 32-column fp32 slabs each).
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -24,7 +25,7 @@
 
 namespace capf {
 
-constexpr int ML_THREADS = 512;
+constexpr int ML_THREADS = 640;
 constexpr int ML_K1 = 128, ML_N1 = 256, ML_N2 = 128;
 constexpr int ML_CHUNK = 128 * 128;                 // 128 rows x 64 elements x 2 B
 constexpr int ML_T_BYTES = 2 * ML_CHUNK;            // t tile: K1 = two 64-column chunks
@@ -35,7 +36,7 @@ constexpr int ML_HEADER = 2048;                     // barriers, TMEM slot, then
 constexpr int MB_TFULL = 0, MB_TFREE = 16, MB_W1FULL = 32, MB_W2FULL = 40, MB_G1DONE = 48, MB_G2DONE = 56, MB_A1FULL = 64, MB_A1EMPTY = 80,
               MB_HREADY = 96, MB_A2FULL = 104, MB_A2EMPTY = 112, MB_TMEM = 120;
 constexpr int MB_BIAS = 512;                        // 384 floats = 1536 B
-constexpr int ML_SMEM = 1024 + ML_HEADER + ML_W_BYTES + 2 * ML_T_BYTES + ML_H_BYTES + 4 * 2 * ML_STG_BYTES;
+constexpr int ML_SMEM = 1024 + ML_HEADER + ML_W_BYTES + 2 * ML_T_BYTES + ML_H_BYTES + 8 * ML_STG_BYTES;
 static_assert(ML_SMEM <= TC_SMEM_LIMIT, "fused MLP kernel: shared memory budget");
 
 struct MlpP {
@@ -74,15 +75,15 @@ tc_mlp128_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant
       ptx::mbar_init(bar_tfull + 8 * b, 1);
       ptx::mbar_init(bar_tfree + 8 * b, 1);
       ptx::mbar_init(bar_a1full + 8 * b, 1);           // b = column half of GEMM 1
-      ptx::mbar_init(bar_a1empty + 8 * b, 4);          // the four epilogue-1 warps of the half
+      ptx::mbar_init(bar_a1empty + 8 * b, 8);          // the eight epilogue-1 warps of the half
     }
     ptx::mbar_init(bar_w1full, 1);
     ptx::mbar_init(bar_w2full, 1);
     ptx::mbar_init(bar_g1done, 1);
     ptx::mbar_init(bar_g2done, 1);
-    ptx::mbar_init(bar_hready, 8);                     // all eight epilogue-1 warps
+    ptx::mbar_init(bar_hready, 16);                    // all sixteen epilogue-1 warps
     ptx::mbar_init(bar_a2full, 1);
-    ptx::mbar_init(bar_a2empty, 4);
+    ptx::mbar_init(bar_a2empty, 8);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -177,94 +178,91 @@ tc_mlp128_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant
         ptx::umma_commit(bar_g2done);
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // ===================================== epilogue 1: h = gelu(acc + b1) -> H (swizzled operand layout) ====
-    const int q = warp & 3, h = (warp - 4) >> 2;             // rows 32 q .. 32 q + 31, columns 128 h .. 128 h + 127 (chunks 2 h, 2 h + 1)
+  } else if (warp >= 4) {
+    // ===================================== epilogue warps: (lane quadrant q, column quarter cq) ===================================
+    const int q = warp & 3, cq = (warp - 4) >> 2;            // rows 32 q .. 32 q + 31
+    const int h = cq >> 1;                                   // epilogue 1: columns 64 cq .. 64 cq + 63 of h = chunk cq, accumulator half h
     const uint32_t row = (uint32_t)(q * 32 + lane);
     uint8_t* const hb = gen + (smem_h - base);
-    for (int k = 0; k < ntiles; ++k) {
-      const uint32_t ph = (uint32_t)k & 1u;
-      ptx::mbar_wait(bar_a1full + 8 * h, ph);                // every MMA issued before it -- GEMM 2 of the previous tile too -- is complete
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(128 * h) + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-      for (int g = 0; g < 8; g += 2) {                        // 32 columns per step
-        uint32_t a0[16], a1[16];
-        ptx::tmem_ld16(taddr + (uint32_t)(16 * g), a0);
-        ptx::tmem_ld16(taddr + (uint32_t)(16 * g + 16), a1);
-        ptx::tmem_ld_wait();
-        if (g == 6) {                                         // accumulator half read completely
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_a1empty + 8 * h);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {                         // 8 columns = one 16-byte chunk
-          const int col = 16 * g + 8 * c;                     // column inside the half
-          const float4 bA = *reinterpret_cast<const float4*>(sbias + 128 * h + col), bB = *reinterpret_cast<const float4*>(sbias + 128 * h + col + 4);
-          const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = gelu_erf(__uint_as_float(c < 2 ? a0[8 * c + e] : a1[8 * (c - 2) + e]) + bb[e]);
-          *reinterpret_cast<uint4*>(hb + (uint32_t)(2 * h + (col >> 6)) * ML_CHUNK + ml_chunk(row, (uint32_t)((col & 63) >> 3))) = pack8<T>(f);
-        }
-      }
-      ptx::fence_proxy_async();                               // generic-proxy writes of H -> tensor-pipe reads
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_hready);
-    }
-  } else if (warp >= 12) {
-    // ===================================== epilogue 2: X = X + acc2 + b2 (fp32, through the staging tiles) ====
-    const int q = warp & 3;
-    const uint32_t stg = smem_stg + (uint32_t)q * (2u * ML_STG_BYTES);
+    // epilogue 2 (cq < 2): fp32 slabs 2 cq and 2 cq + 1 (32 columns each) through one private staging tile
+    const uint32_t stg = smem_stg + (uint32_t)(q + 4 * (cq & 1)) * (uint32_t)ML_STG_BYTES;
     uint8_t* const stg_ptr = gen + (stg - base);
-    auto slot_off = [](uint32_t buf, int r, int c) { return buf * (uint32_t)ML_STG_BYTES + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); };
+    auto slot_off = [](int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); };
     const uint64_t pol_out = ptx::policy_evict_last();
     const float ninf = -__int_as_float(0x7f800000);
     for (int k = 0; k < ntiles; ++k) {
       const uint32_t ph = (uint32_t)k & 1u;
       const int m_w0 = (t0 + k) * 128 + q * 32;                // first token row of this warp
       const int rows_live = p.M - m_w0;
-      auto prefetch_res = [&](int s, uint32_t buf) {
-        const uint8_t* gbase = reinterpret_cast<const uint8_t*>(p.res + (size_t)m_w0 * ML_N2 + 32 * s);
+      auto prefetch_res = [&](int slab) {
+        const uint8_t* gbase = reinterpret_cast<const uint8_t*>(p.res + (size_t)m_w0 * ML_N2 + 32 * slab);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + (lane >> 3), c = lane & 7;
-          if (r < rows_live) ptx::cp_async16(stg + slot_off(buf, r, c), gbase + (size_t)r * (ML_N2 * 4) + 16 * c);
+          if (r < rows_live) ptx::cp_async16(stg + slot_off(r, c), gbase + (size_t)r * (ML_N2 * 4) + 16 * c);
         }
         ptx::cp_async_commit();
       };
-      prefetch_res(0, 0);                                      // independent of the MMAs
+      if (cq < 2) prefetch_res(2 * cq);                        // residual of the first slab: independent of everything on chip
+      // ---- epilogue 1: h = gelu(acc + b1) -> H (swizzled operand layout), 64 columns
+      ptx::mbar_wait(bar_a1full + 8 * h, ph);                  // every MMA issued before it -- GEMM 2 of the previous tile too -- is complete
+      ptx::tc_fence_after();
+      const uint32_t taddr1 = tmem_base + (uint32_t)(64 * cq) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int g = 0; g < 4; g += 2) {                         // 32 columns per step
+        uint32_t a0[16], a1[16];
+        ptx::tmem_ld16(taddr1 + (uint32_t)(16 * g), a0);
+        ptx::tmem_ld16(taddr1 + (uint32_t)(16 * g + 16), a1);
+        ptx::tmem_ld_wait();
+        if (g == 2) {                                          // this warp's part of the accumulator half has been read
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_a1empty + 8 * h);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                          // 8 columns = one 16-byte chunk
+          const int col = 16 * g + 8 * c;                      // column inside the quarter = inside chunk cq
+          const float4 bA = *reinterpret_cast<const float4*>(sbias + 64 * cq + col), bB = *reinterpret_cast<const float4*>(sbias + 64 * cq + col + 4);
+          const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = gelu_erf(__uint_as_float(c < 2 ? a0[8 * c + e] : a1[8 * (c - 2) + e]) + bb[e]);
+          *reinterpret_cast<uint4*>(hb + (uint32_t)cq * ML_CHUNK + ml_chunk(row, (uint32_t)(col >> 3))) = pack8<T>(f);
+        }
+      }
+      ptx::fence_proxy_async();                                // generic-proxy writes of H -> tensor-pipe reads
       __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_hready);
+      if (cq >= 2) continue;
+      // ---- epilogue 2: X = X + acc2 + b2 (fp32), two slabs of 32 columns through the staging tile
       ptx::mbar_wait(bar_a2full, ph);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + 256u + ((uint32_t)(q * 32) << 16);
-      uint32_t buf = 0;
+      const uint32_t taddr2 = tmem_base + 256u + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int s = 0; s < 4; ++s) {                            // slabs of 32 fp32 columns
-        if (s + 1 < 4) prefetch_res(s + 1, buf ^ 1u);
+      for (int sl = 0; sl < 2; ++sl) {
+        const int slab = 2 * cq + sl;
         uint32_t a0[16], a1[16];
-        ptx::tmem_ld16(taddr + (uint32_t)(32 * s), a0);
-        ptx::tmem_ld16(taddr + (uint32_t)(32 * s + 16), a1);
+        ptx::tmem_ld16(taddr2 + (uint32_t)(32 * slab), a0);
+        ptx::tmem_ld16(taddr2 + (uint32_t)(32 * slab + 16), a1);
         ptx::tmem_ld_wait();
-        if (s + 1 < 4) ptx::cp_async_wait_group1(); else ptx::cp_async_wait_all();
+        ptx::cp_async_wait_all();
         __syncwarp();
-        epi16<float, 1>(a0, sbias + ML_N1 + 32 * s, ninf, stg_ptr + buf * ML_STG_BYTES + lane * 128, 0u, (uint32_t)lane & 7u);
-        epi16<float, 1>(a1, sbias + ML_N1 + 32 * s + 16, ninf, stg_ptr + buf * ML_STG_BYTES + lane * 128, 4u, (uint32_t)lane & 7u);
-        if (s == 3) {                                          // the accumulator has been read completely
+        epi16<float, 1>(a0, sbias + ML_N1 + 32 * slab, ninf, stg_ptr + lane * 128, 0u, (uint32_t)lane & 7u);
+        epi16<float, 1>(a1, sbias + ML_N1 + 32 * slab + 16, ninf, stg_ptr + lane * 128, 4u, (uint32_t)lane & 7u);
+        if (sl == 1) {                                         // this warp's part of the accumulator has been read
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bar_a2empty);
         }
         __syncwarp();
-        uint8_t* gout = reinterpret_cast<uint8_t*>(p.out + (size_t)m_w0 * ML_N2 + 32 * s);
+        uint8_t* gout = reinterpret_cast<uint8_t*>(p.out + (size_t)m_w0 * ML_N2 + 32 * slab);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + (lane >> 3), c = lane & 7;
-          if (r < rows_live) st16_hint(gout + (size_t)r * (ML_N2 * 4) + 16 * c, *reinterpret_cast<const uint4*>(stg_ptr + slot_off(buf, r, c)), pol_out);
+          if (r < rows_live) st16_hint(gout + (size_t)r * (ML_N2 * 4) + 16 * c, *reinterpret_cast<const uint4*>(stg_ptr + slot_off(r, c)), pol_out);
         }
         __syncwarp();
-        buf ^= 1u;
+        if (sl == 0) prefetch_res(slab + 1);                   // the staging tile is free again: residual of the second slab
       }
     }
   }
