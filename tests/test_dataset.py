@@ -117,3 +117,46 @@ def test_gpu_nvjpeg_decode_agrees_with_cv2_and_feeds_the_crop():
     dc = (a["images"].int() - b["images"].int()).abs().float()
     assert a["images"].shape == b["images"].shape and float(dc.mean()) < 3.5       # measured 2.1 after the 3x down-scaling crop
     assert torch.equal(a["keypoints_2d_cpn"], b["keypoints_2d_cpn"])
+
+
+_BATCHED_DECODE = r"""
+import os, sys, numpy as np
+sys.path.insert(0, {root!r})
+from capf_b200.mvn.datasets.human36m import Human36MSingleViewDataset
+ds = Human36MSingleViewDataset(os.path.join({mini!r}, "processed"), os.path.join({mini!r}, "labels.pkl"), image_shape=(48, 64))
+idx = list(range(len(ds)))
+frames, sizes = ds.decode_frames(idx, "cuda")
+np.save({out!r}, frames.cpu().numpy())
+"""
+
+
+@pytest.mark.gpu
+def test_gpu_nvjpeg_batched_backend_decodes_the_same_frames(tmp_path):
+    """CAPF_JPEG_BACKEND=gpu_hybrid (nvjpegDecodeBatched, Huffman stage on the SMs; 3.5x the per-frame default on 1000x1000 frames,
+    profiles/r3f_jpeg_throughput.txt) is read once per process, so it runs in a child: same sizes, padding untouched, pixels within
+    the decoder tolerance of the default backend's; an unknown backend name is an error, not a fallback."""
+    pytest.importorskip("cv2")
+    import subprocess
+    import sys
+    from capf_b200 import lib
+    if not lib.load().capf_jpeg_available():
+        pytest.skip("libnvjpeg not loadable on this machine")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "frames.npy")
+    code = _BATCHED_DECODE.format(root=os.path.dirname(here), mini=MINI, out=out)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CAPF_JPEG_BACKEND="gpu_hybrid"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = np.load(out).astype(np.int32)
+    ds = open_ds()
+    idx = list(range(len(ds)))
+    base, _ = ds.decode_frames(idx, "cuda")
+    base = base.cpu().numpy().astype(np.int32)
+    assert got.shape == base.shape
+    for k in idx:
+        want = ds.read_frame(k).astype(np.int32)
+        d = np.abs(got[k, :want.shape[0], :want.shape[1]] - want)
+        assert d.mean() < 5.0 and (d <= 16).mean() > 0.98, (k, d.mean(), d.max())
+        assert not got[k, want.shape[0]:].any() and not got[k, :, want.shape[1]:].any()
+    assert np.abs(got - base).mean() < 1.0                       # the two nvJPEG backends against each other
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CAPF_JPEG_BACKEND="no_such_backend"), capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "CAPF_JPEG_BACKEND" in r.stderr

@@ -3,7 +3,7 @@
 Runs the fp32 op program through tests/interp.py with selectable rounding points and prints the rel-L2 of the
 [B,1,17,3] output against the committed reference fixture.
 
-  python tools/precision_study.py [case] [dtype]
+  python tools/precision_study.py [case] [dtype] [only: comma-separated substrings of the variant labels]
 """
 import os
 import sys
@@ -125,7 +125,10 @@ def main():
         ("all, but backbone weights exact", {"bb_a", "bb_store", "lf_w", "lf_a", "lf_store"}),
         ("all, but lifter exact weights", {"bb_w", "bb_a", "bb_store", "lf_a", "lf_store"}),
     ]
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
     for label, flags in variants:
+        if only is not None and not any(o in label for o in only):
+            continue
         prog = program.build_forward_program(case["backbone"], cfg.model.backbone, m._pf_cfg, shapes, B, H, W, "fp32")
         it = Study(prog, w, flags, dt)
         it.t(prog.inputs["images"]).copy_(images)
