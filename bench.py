@@ -733,10 +733,40 @@ def run_native(args, label):
 
     # ---- the other BASELINE configs of this node size, shorter runs, same code path ----------------------------------
     others = []
+    train_rec = None
+
+    def emit(note=None):
+        """Rank 0 prints THE line (the headline above is complete; the extras are whatever finished)."""
+        if rank != 0:
+            return
+        line["other_configs"] = others
+        line["train_step"] = train_rec
+        if note:
+            line["extras_note"] = note
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+
+    # The extra records must never cost the headline: if they stall (a rank that failed inside one of them leaves its peers waiting in
+    # the next collective), every rank's watchdog fires after the same limit, rank 0 prints the line without them and all exit 0.
+    def watchdog_fire():
+        log("extra records exceeded their time limit: printing the headline line without them")
+        try:
+            emit("the extra records (other_configs / train_step) did not finish within their time limit and were dropped")
+        finally:
+            os._exit(0)
+
+    import threading
+    watchdog = threading.Timer(float(os.environ.get("CAPF_BENCH_EXTRAS_LIMIT_S", "240")), watchdog_fire)
+    watchdog.daemon = True
+    watchdog.start()
     if args.config == 1 and not args.no_other_configs and label.find("custom") < 0:
         # (config index, precision override): configs[2] and the configs[1] workload in the fp32-class tensor-core mode at N = 1;
         # the two 8-GPU configs at N = 8
         todo = [(1, "bf16x3"), (2, None)] if world == 1 else ([(3, None), (4, None)] if world == 8 else [])
+        if os.environ.get("CAPF_BENCH_FORCE_OTHERS"):          # testing: e.g. "3,4" exercises the 8-GPU list on 2 GPUs
+            todo = [(int(v), None) for v in os.environ["CAPF_BENCH_FORCE_OTHERS"].split(",")]
         for k, prec in todo:
             a2 = argparse.Namespace(**vars(args))
             for key in ("backbone", "batch", "height", "width", "precision"):
@@ -768,7 +798,6 @@ def run_native(args, label):
                 rec["error"] = f"{type(e).__name__}: {e}"[:300]
             torch.cuda.empty_cache()
             others.append(rec)
-    train_rec = None
     if world == 1 and rank == 0 and args.config == 1 and not args.no_other_configs and label.find("custom") < 0:
         log("training step")
         try:
@@ -776,14 +805,9 @@ def run_native(args, label):
         except Exception as e:  # noqa: BLE001
             train_rec = {"error": f"{type(e).__name__}: {e}"[:300]}
         torch.cuda.empty_cache()
+    watchdog.cancel()
     log("done")
-    if rank == 0:
-        line["other_configs"] = others
-        line["train_step"] = train_rec
-        if saved_stdout is not None:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-        print(json.dumps(line), flush=True)
+    emit()
     if world > 1:
         if rank == 0 and saved_stdout is not None:
             os.dup2(2, 1)
