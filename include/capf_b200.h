@@ -283,7 +283,10 @@ int capf_op_run(const capf_op* op, int device, void* stream);
  * JPEG streams in host memory -> interleaved BGR uint8 frames in the padded device storage [n,Hs,Ws,3] that
  * CAPF_OP_WARP_AFFINE_U8 crops from, decoded by nvJPEG (loaded with dlopen on first use; without it these return
  * CAPF_ERR_UNSUPPORTED and capf_jpeg_available() 0).  sizes_hw (host, [n,2], may be NULL) receives each frame's (h, w).
- * Work is enqueued on `stream`; the decoder is bound to the device of its first use (one process per GPU). */
+ * Work is enqueued on `stream`; the decoder is bound to the device of its first use (one process per GPU).
+ * Environment CAPF_JPEG_BACKEND (read at the first decode): unset / "default" = one nvjpegDecode per frame; "gpu_hybrid",
+ * "hybrid", "hardware" = the whole batch through nvjpegDecodeBatched on that nvJPEG backend (CAPF_ERR_UNSUPPORTED if the
+ * GPU / driver does not offer it; never a silent fallback). */
 int capf_jpeg_available(void);
 int capf_jpeg_info(const unsigned char* data, size_t length, int device, int* height, int* width);
 int capf_jpeg_decode_batch(const unsigned char* const* data, const size_t* lengths, int n, unsigned char* frames, int Hs, int Ws,
