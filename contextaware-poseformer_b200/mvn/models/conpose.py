@@ -90,6 +90,8 @@ class CA_PF(PlanCacheMixin, nn.Module):
             # conpose.py:34-35 normalises [..., :2]; anything but a [B,17,2] tensor would be mis-strided by the float2 kernel
             raise ValueError(f"keypoints_2d_cpn_crop must be [B,{J},2], got {tuple(keypoints_2d_cpn_crop.shape)}")
         dev = images.device
+        if B == 0:          # an empty shard (ragged last batch of a rank): the reference's torch ops return an empty [0,1,17,3] as well
+            return torch.zeros((0, 1, J, 3), dtype=torch.float32, device=dev)
         plan = None if train_step else self.plan_for(B, H, W, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
 
